@@ -1,0 +1,799 @@
+// align_abi.cu -- host side of the C ABI declared in include/ambivert_align.h.
+//
+// Everything computes on the GPU (kernels.cuh).  There is deliberately no CPU implementation of
+// any alignment in this library: if CUDA is unavailable the calls fail (NULL / ABV_ERR_NO_DEVICE).
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/ambivert_align.h"
+#include "kernels.cuh"
+
+namespace {
+
+using namespace abv;
+
+thread_local std::string t_err;
+thread_local double t_timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  t_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ABV_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---- process-wide context: one device per process (one process per GPU) ----------------------
+struct Options {
+  int path = ABV_PATH_AUTO;
+  int wf32_blocks_per_sm = 4;
+  int mm16_blocks_per_sm = 0;   // 0 = what the occupancy query returns
+};
+
+struct Ctx {
+  std::recursive_mutex mu;
+  bool inited = false;
+  int device = 0;
+  int sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  Options opt;
+};
+Ctx g;
+
+int ctx_init() {
+  if (g.inited) return ABV_OK;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(ABV_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (g.device >= n) return fail(ABV_ERR_ARGS, "device %d out of range (%d devices)", g.device, n);
+  CU(cudaSetDevice(g.device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, g.device));
+  if (prop.major < 10)
+    return fail(ABV_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", g.device, prop.major, prop.minor);
+  g.sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  for (auto &ev : g.ev) CU(cudaEventCreate(&ev));
+  g.inited = true;
+  return ABV_OK;
+}
+
+// RAII device allocation
+struct DevMem {
+  void *p = nullptr;
+  size_t bytes = 0;
+  DevMem() = default;
+  DevMem(const DevMem &) = delete;
+  DevMem &operator=(const DevMem &) = delete;
+  ~DevMem() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  cudaError_t alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Scoring {
+  int alpha, go, ge;
+  const unsigned char *map256;   // may be NULL (inputs are codes)
+  const int *matrix;
+};
+
+int check_scoring(const Scoring &sc) {
+  if (!sc.matrix) return fail(ABV_ERR_ARGS, "score_matrix is NULL");
+  if (sc.alpha <= 0 || sc.alpha > 256) return fail(ABV_ERR_ARGS, "alpha_len %d out of range", sc.alpha);
+  if (sc.go > 0 || sc.ge > 0) return fail(ABV_ERR_ARGS, "gap penalties must be <= 0 (global_align.c:121)");
+  return ABV_OK;
+}
+
+// lengths of a concatenated sequence set; rejects what the reference rejects
+int check_seqs(const char *buf, const long long *off, int n, const char *what, int &maxlen, int &minlen) {
+  maxlen = 0; minlen = INT_MAX;
+  if (n < 0) return fail(ABV_ERR_ARGS, "%s: negative count", what);
+  if (n == 0) { minlen = 0; return ABV_OK; }
+  if (!buf || !off) return fail(ABV_ERR_ARGS, "%s: NULL buffer", what);
+  for (int i = 0; i < n; ++i) {
+    long long l = off[i + 1] - off[i];
+    if (l <= 0) return fail(ABV_ERR_ARGS, "%s %d has length %lld (the reference returns NULL for length <= 0)", what, i, l);
+    if (l > (1 << 24)) return fail(ABV_ERR_ARGS, "%s %d is longer than 2^24", what, i);
+    maxlen = std::max(maxlen, (int)l);
+    minlen = std::min(minlen, (int)l);
+  }
+  return ABV_OK;
+}
+
+int check_mode_lengths(int mode, int min_la, int min_lb) {
+  if (mode < 0 || mode > 3) return fail(ABV_ERR_ARGS, "unknown mode %d", mode);
+  if (mode == ABV_GLOCAL && min_lb < 2) return fail(ABV_ERR_UNDEFINED, "glocal with a target of length 1 is undefined in the reference (glocal_align.c:138,172)");
+  if (mode == ABV_OVERLAP && min_la < 2) return fail(ABV_ERR_UNDEFINED, "overlap with a first sequence of length 1 is undefined in the reference (align.c:183)");
+  return ABV_OK;
+}
+
+// upload a concatenated sequence set and encode it on the device
+int upload_encoded(const char *buf, const long long *off, int n, const Scoring &sc, cudaStream_t st,
+                   DevMem &d_codes, DevMem &d_off, DevMem &d_map, double &h2d_bytes) {
+  const long long total = n ? off[n] - off[0] : 0;
+  std::vector<long long> rel(n + 1);
+  for (int i = 0; i <= n; ++i) rel[i] = n ? off[i] - off[0] : 0;
+  CU(d_off.alloc(sizeof(long long) * (n + 1)));
+  CU(cudaMemcpyAsync(d_off.p, rel.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));   // rel is a local
+  CU(d_codes.alloc((size_t)total + 16));
+  DevMem raw;
+  unsigned char ident[256];
+  const unsigned char *m = sc.map256;
+  if (!m) { for (int i = 0; i < 256; ++i) ident[i] = (unsigned char)i; m = ident; }
+  unsigned char clamped[256];
+  for (int i = 0; i < 256; ++i) clamped[i] = (unsigned char)std::min<int>(m[i], sc.alpha - 1);
+  if (!d_map.p) CU(d_map.alloc(256));
+  CU(cudaMemcpyAsync(d_map.p, clamped, 256, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  if (total > 0) {
+    CU(raw.alloc((size_t)total));
+    CU(cudaMemcpyAsync(raw.p, buf + off[0], (size_t)total, cudaMemcpyHostToDevice, st));
+    int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    encode_kernel<<<blocks, 256, 0, st>>>(raw.as<uint8_t>(), d_codes.as<uint8_t>(), total, d_map.as<uint8_t>());
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+  }
+  h2d_bytes += (double)total + sizeof(long long) * (n + 1) + 256;
+  return ABV_OK;
+}
+
+// ---- wf32 launcher ----------------------------------------------------------------------------
+template <bool TRACE>
+void wf32_dispatch(int mode, int grid, cudaStream_t st, const Wf32Params &p) {
+  switch (mode) {
+    case ABV_OVERLAP: wf32_kernel<OVERLAP, TRACE><<<grid, WF32_WARPS * 32, 0, st>>>(p); break;
+    case ABV_LOCAL:   wf32_kernel<LOCAL, TRACE><<<grid, WF32_WARPS * 32, 0, st>>>(p); break;
+    case ABV_GLOBAL:  wf32_kernel<GLOBAL, TRACE><<<grid, WF32_WARPS * 32, 0, st>>>(p); break;
+    default:          wf32_kernel<GLOCAL, TRACE><<<grid, WF32_WARPS * 32, 0, st>>>(p); break;
+  }
+}
+
+int wf32_grid(long long n_pairs, size_t scratch_per_warp) {
+  long long want = (n_pairs + WF32_WARPS - 1) / WF32_WARPS;
+  long long cap = (long long)g.sms * g.opt.wf32_blocks_per_sm;
+  const size_t budget = (size_t)3 << 30;   // bound the per-warp scratch to 3 GiB
+  if (scratch_per_warp > 0) {
+    long long by_mem = (long long)(budget / (scratch_per_warp * WF32_WARPS));
+    cap = std::max<long long>(1, std::min(cap, by_mem));
+  }
+  return (int)std::max<long long>(1, std::min(want, cap));
+}
+
+// ---- mm16 launcher ----------------------------------------------------------------------------
+const int MM16_KS[] = {2, 4, 6, 8, 10, 12, 16};
+constexpr int MM16_NK = 7;
+
+template <int MODE, int K>
+int mm16_launch_one(int grid_cap, cudaStream_t st, const Mm16Params &p, int &launched) {
+  const Mm16Smem L = mm16_smem_layout(K, p.a1, p.tp_stride);
+  auto kern = mm16_kernel<MODE, K>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MM16_WARPS * 32, L.total));
+  if (per_sm < 1) return fail(ABV_ERR_CUDA, "mm16 kernel K=%d does not fit (smem %d)", K, L.total);
+  if (g.opt.mm16_blocks_per_sm > 0) per_sm = std::min(per_sm, g.opt.mm16_blocks_per_sm);
+  int grid = std::min(p.n_list, g.sms * per_sm);
+  if (grid_cap > 0) grid = std::min(grid, grid_cap);
+  kern<<<grid, MM16_WARPS * 32, L.total, st>>>(p);
+  CU(cudaGetLastError());
+  ++launched;
+  return ABV_OK;
+}
+
+template <int MODE>
+int mm16_launch_mode(int K, cudaStream_t st, const Mm16Params &p, int &launched) {
+  switch (K) {
+    case 2: return mm16_launch_one<MODE, 2>(0, st, p, launched);
+    case 4: return mm16_launch_one<MODE, 4>(0, st, p, launched);
+    case 6: return mm16_launch_one<MODE, 6>(0, st, p, launched);
+    case 8: return mm16_launch_one<MODE, 8>(0, st, p, launched);
+    case 10: return mm16_launch_one<MODE, 10>(0, st, p, launched);
+    case 12: return mm16_launch_one<MODE, 12>(0, st, p, launched);
+    case 16: return mm16_launch_one<MODE, 16>(0, st, p, launched);
+  }
+  return fail(ABV_ERR_ARGS, "no packed kernel for K=%d", K);
+}
+
+int mm16_launch(int mode, int K, cudaStream_t st, const Mm16Params &p, int &launched) {
+  if (mode == ABV_GLOBAL) return mm16_launch_mode<GLOBAL>(K, st, p, launched);
+  if (mode == ABV_LOCAL) return mm16_launch_mode<LOCAL>(K, st, p, launched);
+  if (mode == ABV_GLOCAL) return mm16_launch_mode<GLOCAL>(K, st, p, launched);
+  return fail(ABV_ERR_ARGS, "packed kernel does not implement mode %d", mode);
+}
+
+}  // namespace
+
+// =================================================================================================
+// the many-to-many job
+struct abv_job {
+  int mode = 0, n_q = 0, n_t = 0, seed = 0;
+  int alpha = 0, go = 0, ge = 0;
+  double cells = 0;
+  double h2d_bytes = 0;
+  bool want_all_scores = false;
+  // device data
+  DevMem q_codes, q_off, t_codes, t_off, map, matrix, matrix_ext, tp_codes, tp_meta, lists, counters;
+  DevMem best_score, best_idx, all_scores, chunk_scores, border;
+  int tp_stride = 0, n_pairs = 0, a1 = 0, max_lt = 0, max_lq = 0;
+  struct Bucket { int K, n, offset; };
+  std::vector<Bucket> buckets;     // packed-kernel launches (one per K class), lists at `offset`
+  int n_wf32 = 0, wf32_offset = 0; // queries served by the 32-bit kernel, list at `wf32_offset`
+  int n_counters = 0;
+  int launches_per_run = 0;
+  cudaStream_t last_stream = nullptr;
+};
+
+namespace {
+
+// is the packed kernel exact for queries padded to P columns against these targets?
+bool packed_exact(int mode, int P, int max_lt, int maxabs) {
+  const long long bound = (long long)(P + max_lt + 8) * maxabs;
+  return bound <= (mode == ABV_GLOCAL ? p16::P16_LIMIT : 30000);
+}
+
+int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int n_q,
+                const char *t, const long long *t_off, int n_t, const Scoring &sc, int seed, bool all_scores) {
+  int rc;
+  if ((rc = check_scoring(sc))) return rc;
+  int max_lq, min_lq, max_lt, min_lt;
+  if ((rc = check_seqs(q, q_off, n_q, "query", max_lq, min_lq))) return rc;
+  if ((rc = check_seqs(t, t_off, n_t, "target", max_lt, min_lt))) return rc;
+  if (n_q > 0 && n_t > 0 && (rc = check_mode_lengths(mode, min_lq, min_lt))) return rc;
+  if (mode < 0 || mode > 3) return fail(ABV_ERR_ARGS, "unknown mode %d", mode);
+  if ((rc = ctx_init())) return rc;
+  cudaStream_t st = g.stream;
+  J.mode = mode; J.n_q = n_q; J.n_t = n_t; J.seed = seed; J.alpha = sc.alpha; J.go = sc.go; J.ge = sc.ge;
+  J.max_lq = max_lq; J.max_lt = max_lt; J.want_all_scores = all_scores;
+  {
+    double tq = n_q ? (double)(q_off[n_q] - q_off[0]) : 0, tt = n_t ? (double)(t_off[n_t] - t_off[0]) : 0;
+    J.cells = tq * tt;
+  }
+  CU(J.best_score.alloc(sizeof(int) * (size_t)std::max(n_q, 1)));
+  CU(J.best_idx.alloc(sizeof(int) * (size_t)std::max(n_q, 1)));
+  if (all_scores) {
+    if ((long long)n_q * n_t > (1ll << 28)) return fail(ABV_ERR_ARGS, "score matrix of %d x %d is too large", n_q, n_t);
+    CU(J.all_scores.alloc(sizeof(int) * (size_t)std::max<long long>((long long)n_q * n_t, 1)));
+  }
+  if (n_q == 0) return ABV_OK;
+  if ((rc = upload_encoded(q, q_off, n_q, sc, st, J.q_codes, J.q_off, J.map, J.h2d_bytes))) return rc;
+  if ((rc = upload_encoded(t, t_off, n_t, sc, st, J.t_codes, J.t_off, J.map, J.h2d_bytes))) return rc;
+  CU(J.matrix.alloc(sizeof(int) * sc.alpha * sc.alpha));
+  CU(cudaMemcpyAsync(J.matrix.p, sc.matrix, sizeof(int) * sc.alpha * sc.alpha, cudaMemcpyHostToDevice, st));
+  J.h2d_bytes += sizeof(int) * sc.alpha * sc.alpha;
+
+  // ---- which queries can take the packed kernel ------------------------------------------------
+  int maxabs = std::max(std::abs(sc.go), std::abs(sc.ge));
+  for (int i = 0; i < sc.alpha * sc.alpha; ++i) maxabs = std::max(maxabs, std::abs(sc.matrix[i]));
+  maxabs = std::max(maxabs, 1);
+  const int a1 = sc.alpha + 1;
+  bool packed_ok = g.opt.path != ABV_PATH_WF32 && n_t > 0 && a1 * a1 <= 64 &&
+                   (mode == ABV_GLOBAL || mode == ABV_LOCAL || mode == ABV_GLOCAL);
+  const int tp_stride = (max_lt + 15) & ~15;
+  std::vector<std::vector<int>> lists(MM16_NK);
+  std::vector<int> wf32_list;
+  for (int i = 0; i < n_q; ++i) {
+    const int lq = (int)(q_off[i + 1] - q_off[i]);
+    int slot = -1;
+    if (packed_ok) {
+      for (int k = 0; k < MM16_NK; ++k)
+        if (32 * MM16_KS[k] >= lq) { slot = k; break; }
+      if (slot >= 0) {
+        const int K = MM16_KS[slot];
+        if (!packed_exact(mode, 32 * K, tp_stride, maxabs)) slot = -1;
+        else if (mm16_smem_layout(K, a1, tp_stride).total > 100 * 1024) slot = -1;
+      }
+    }
+    if (slot >= 0) lists[slot].push_back(i); else wf32_list.push_back(i);
+  }
+  if (g.opt.path == ABV_PATH_PACKED && !wf32_list.empty())
+    return fail(ABV_ERR_ARGS, "packed path forced but %zu queries are not eligible for it", wf32_list.size());
+
+  std::vector<int> flat;
+  for (int k = 0; k < MM16_NK; ++k)
+    if (!lists[k].empty()) {
+      J.buckets.push_back({MM16_KS[k], (int)lists[k].size(), (int)flat.size()});
+      flat.insert(flat.end(), lists[k].begin(), lists[k].end());
+    }
+  J.wf32_offset = (int)flat.size();
+  J.n_wf32 = (int)wf32_list.size();
+  flat.insert(flat.end(), wf32_list.begin(), wf32_list.end());
+  CU(J.lists.alloc(sizeof(int) * std::max<size_t>(flat.size(), 1)));
+  CU(cudaMemcpyAsync(J.lists.p, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  J.h2d_bytes += sizeof(int) * flat.size();
+  J.n_counters = (int)J.buckets.size() + 64;
+  CU(J.counters.alloc(sizeof(unsigned long long) * J.n_counters));
+
+  // ---- target pairs for the packed kernel: sort by length, pair neighbours ----------------------
+  if (!J.buckets.empty()) {
+    std::vector<int> order(n_t);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+      return (t_off[x + 1] - t_off[x]) > (t_off[y + 1] - t_off[y]);
+    });
+    const int n_pairs = (n_t + 1) / 2;
+    unsigned char ident[256];
+    const unsigned char *m = sc.map256;
+    if (!m) { for (int i = 0; i < 256; ++i) ident[i] = (unsigned char)i; m = ident; }
+    std::vector<unsigned char> codes((size_t)n_pairs * tp_stride);
+    std::vector<int> meta((size_t)n_pairs * 4);
+    const int pad = sc.alpha;
+    for (int pi = 0; pi < n_pairs; ++pi) {
+      const int i1 = order[2 * pi], i2 = (2 * pi + 1 < n_t) ? order[2 * pi + 1] : -1;
+      const int l1 = (int)(t_off[i1 + 1] - t_off[i1]), l2 = i2 >= 0 ? (int)(t_off[i2 + 1] - t_off[i2]) : 0;
+      const unsigned char *s1 = (const unsigned char *)t + t_off[i1];
+      const unsigned char *s2 = i2 >= 0 ? (const unsigned char *)t + t_off[i2] : nullptr;
+      unsigned char *row = codes.data() + (size_t)pi * tp_stride;
+      for (int r = 0; r < tp_stride; ++r) {
+        const int a = r < l1 ? std::min<int>(m[s1[r]], sc.alpha - 1) : pad;
+        const int b = r < l2 ? std::min<int>(m[s2[r]], sc.alpha - 1) : pad;
+        row[r] = (unsigned char)(a * a1 + b);
+      }
+      meta[4 * pi] = l1; meta[4 * pi + 1] = l2; meta[4 * pi + 2] = i1; meta[4 * pi + 3] = i2;
+    }
+    std::vector<int> mext((size_t)a1 * a1, 0);
+    for (int x = 0; x < sc.alpha; ++x)
+      for (int y = 0; y < sc.alpha; ++y) mext[x * a1 + y] = sc.matrix[x * sc.alpha + y];
+    CU(J.tp_codes.alloc(codes.size()));
+    CU(J.tp_meta.alloc(sizeof(int) * meta.size()));
+    CU(J.matrix_ext.alloc(sizeof(int) * mext.size()));
+    CU(cudaMemcpyAsync(J.tp_codes.p, codes.data(), codes.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(J.tp_meta.p, meta.data(), sizeof(int) * meta.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(J.matrix_ext.p, mext.data(), sizeof(int) * mext.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    J.h2d_bytes += codes.size() + sizeof(int) * (meta.size() + mext.size());
+    J.tp_stride = tp_stride; J.n_pairs = n_pairs; J.a1 = a1;
+  }
+
+  // ---- scratch of the 32-bit path ----------------------------------------------------------------
+  if (J.n_wf32 > 0 && n_t > 0) {
+    const long long max_chunk_scores = 32ll << 20;
+    long long rows = std::max<long long>(1, std::min<long long>(J.n_wf32, max_chunk_scores / n_t));
+    if (!all_scores) CU(J.chunk_scores.alloc(sizeof(int) * (size_t)(rows * n_t)));
+    const int grid = wf32_grid(rows * n_t, 0);
+    CU(J.border.alloc(sizeof(int) * 2 * (size_t)max_lt * grid * WF32_WARPS));
+  }
+  CU(cudaStreamSynchronize(st));
+  // launches per run: counter memset is not a kernel
+  J.launches_per_run = (int)J.buckets.size();
+  if (J.n_wf32 > 0 && n_t > 0) {
+    const long long max_chunk_scores = 32ll << 20;
+    long long rows = std::max<long long>(1, std::min<long long>(J.n_wf32, max_chunk_scores / n_t));
+    long long chunks = (J.n_wf32 + rows - 1) / rows;
+    J.launches_per_run += (int)chunks * 2;
+  }
+  return ABV_OK;
+}
+
+int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) {
+  int rc;
+  if ((rc = ctx_init())) return rc;
+  if (!st) st = g.stream;
+  J.last_stream = st;
+  if (!d_best_score) d_best_score = J.best_score.as<int>();
+  if (!d_best_idx) d_best_idx = J.best_idx.as<int>();
+  if (J.n_q == 0) return ABV_OK;
+  if (J.n_t == 0) {   // nothing can beat the seed
+    std::vector<int> s(J.n_q, J.seed), i(J.n_q, -1);
+    CU(cudaMemcpyAsync(d_best_score, s.data(), sizeof(int) * J.n_q, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_best_idx, i.data(), sizeof(int) * J.n_q, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    return ABV_OK;
+  }
+  CU(cudaMemsetAsync(J.counters.p, 0, sizeof(unsigned long long) * J.n_counters, st));
+  int launched = 0;
+  int ci = 0;
+  for (const auto &b : J.buckets) {
+    Mm16Params p{};
+    p.q = J.q_codes.as<uint8_t>(); p.q_off = J.q_off.as<long long>();
+    p.q_list = J.lists.as<int>() + b.offset; p.n_list = b.n;
+    p.tp_codes = J.tp_codes.as<uint8_t>(); p.tp_stride = J.tp_stride;
+    p.tp_meta = J.tp_meta.as<int4>(); p.n_pairs = J.n_pairs;
+    p.matrix_ext = J.matrix_ext.as<int>(); p.a1 = J.a1;
+    p.go = J.go; p.ge = J.ge; p.seed = J.seed;
+    p.best_score = d_best_score; p.best_idx = d_best_idx;
+    p.all_scores = J.want_all_scores ? J.all_scores.as<int>() : nullptr; p.n_t = J.n_t;
+    p.q_counter = reinterpret_cast<unsigned int *>(J.counters.as<unsigned long long>() + ci++);
+    if ((rc = mm16_launch(J.mode, b.K, st, p, launched))) return rc;
+  }
+  if (J.n_wf32 > 0) {
+    const long long max_chunk_scores = 32ll << 20;
+    const long long rows_per = std::max<long long>(1, std::min<long long>(J.n_wf32, max_chunk_scores / J.n_t));
+    const int grid = wf32_grid(rows_per * J.n_t, 0);
+    int chunk = 0;
+    for (long long base = 0; base < J.n_wf32; base += rows_per, ++chunk) {
+      const long long rows = std::min<long long>(rows_per, J.n_wf32 - base);
+      Wf32Params p{};
+      p.a = J.q_codes.as<uint8_t>(); p.a_off = J.q_off.as<long long>();
+      p.b = J.t_codes.as<uint8_t>(); p.b_off = J.t_off.as<long long>();
+      p.n_pairs = rows * J.n_t; p.n_t = J.n_t; p.q_base = base;
+      p.q_list = J.lists.as<int>() + J.wf32_offset;
+      p.matrix = J.matrix.as<int>(); p.alpha = J.alpha; p.go = J.go; p.ge = J.ge;
+      p.border = J.border.as<int>(); p.border_len = J.max_lt;
+      if (ci >= J.n_counters) {   // counters exhausted: reset and reuse (launches are stream-ordered)
+        CU(cudaMemsetAsync(J.counters.p, 0, sizeof(unsigned long long) * J.n_counters, st));
+        ci = 0;
+      }
+      p.pair_counter = J.counters.as<unsigned long long>() + ci++;
+      // full-matrix requests write scores[query*n_t + target]; otherwise a dense chunk in row order
+      p.scores = J.want_all_scores ? J.all_scores.as<int>() : J.chunk_scores.as<int>();
+      p.score_rows_by_query = J.want_all_scores ? 1 : 0;
+      wf32_dispatch<false>(J.mode, std::min<long long>(grid, (p.n_pairs + WF32_WARPS - 1) / WF32_WARPS), st, p);
+      CU(cudaGetLastError());
+      ++launched;
+      const int wpb = 8;
+      argmax_rows_kernel<<<(int)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+          p.scores, (int)rows, J.n_t, J.seed, d_best_score, d_best_idx, base,
+          J.lists.as<int>() + J.wf32_offset, J.want_all_scores ? 1 : 0);
+      CU(cudaGetLastError());
+      ++launched;
+    }
+  }
+  J.launches_per_run = launched;
+  return ABV_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int abv_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int abv_set_device(int ordinal) {
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  if (g.inited && g.device != ordinal) return fail(ABV_ERR_ARGS, "device already initialised as %d", g.device);
+  if (ordinal < 0) return fail(ABV_ERR_ARGS, "negative device ordinal");
+  g.device = ordinal;
+  return ctx_init();
+}
+
+int abv_get_device(void) { return g.device; }
+const char *abv_last_error(void) { return t_err.c_str(); }
+const char *abv_version(void) { return "ambivert-b200 0.1 (sm_100a)"; }
+
+int abv_set_option(const char *key, int value) {
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  if (!key) return fail(ABV_ERR_ARGS, "NULL key");
+  if (!strcmp(key, "path")) { if (value < 0 || value > 2) return fail(ABV_ERR_ARGS, "bad path"); g.opt.path = value; return ABV_OK; }
+  if (!strcmp(key, "wf32_blocks_per_sm")) { g.opt.wf32_blocks_per_sm = std::max(1, std::min(value, 8)); return ABV_OK; }
+  if (!strcmp(key, "mm16_blocks_per_sm")) { g.opt.mm16_blocks_per_sm = std::max(0, std::min(value, 8)); return ABV_OK; }
+  return fail(ABV_ERR_ARGS, "unknown option %s", key);
+}
+
+abv_job *abv_best_hits_prepare(int mode, const char *q, const long long *q_off, int n_q,
+                               const char *t, const long long *t_off, int n_t,
+                               int alpha_len, const unsigned char *map256, const int *score_matrix,
+                               int gap_open, int gap_extend, int seed_score) {
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  abv_job *J = new abv_job();
+  Scoring sc{alpha_len, gap_open, gap_extend, map256, score_matrix};
+  if (job_prepare(*J, mode, q, q_off, n_q, t, t_off, n_t, sc, seed_score, false) != ABV_OK) { delete J; return nullptr; }
+  return J;
+}
+
+int abv_best_hits_launch(abv_job *job, void *stream, int *d_best_score, int *d_best_idx) {
+  if (!job) return fail(ABV_ERR_ARGS, "NULL job");
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  return job_launch(*job, (cudaStream_t)stream, d_best_score, d_best_idx);
+}
+
+int abv_best_hits_fetch(abv_job *job, int *best_score, int *best_idx) {
+  if (!job) return fail(ABV_ERR_ARGS, "NULL job");
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  cudaStream_t st = job->last_stream ? job->last_stream : g.stream;
+  if (job->n_q == 0) return ABV_OK;
+  if (best_score) CU(cudaMemcpyAsync(best_score, job->best_score.p, sizeof(int) * job->n_q, cudaMemcpyDeviceToHost, st));
+  if (best_idx) CU(cudaMemcpyAsync(best_idx, job->best_idx.p, sizeof(int) * job->n_q, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return ABV_OK;
+}
+
+double abv_job_cells(const abv_job *job) { return job ? job->cells : 0; }
+int abv_job_kernel_launches(const abv_job *job) { return job ? job->launches_per_run : 0; }
+void abv_job_free(abv_job *job) {
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  delete job;
+}
+
+static int best_hits_impl(int mode, const char *q, const long long *q_off, int n_q,
+                          const char *t, const long long *t_off, int n_t,
+                          int alpha_len, const unsigned char *map256, const int *score_matrix,
+                          int gap_open, int gap_extend, int seed_score,
+                          int *best_score, int *best_idx, int *scores) {
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  int rc;
+  if ((rc = ctx_init())) return rc;
+  for (double &v : t_timing) v = 0;
+  abv_job J;
+  Scoring sc{alpha_len, gap_open, gap_extend, map256, score_matrix};
+  CU(cudaEventRecord(g.ev[0], g.stream));
+  if ((rc = job_prepare(J, mode, q, q_off, n_q, t, t_off, n_t, sc, seed_score, scores != nullptr))) return rc;
+  CU(cudaEventRecord(g.ev[1], g.stream));
+  if ((rc = job_launch(J, g.stream, nullptr, nullptr))) return rc;
+  CU(cudaEventRecord(g.ev[2], g.stream));
+  double d2h = 0;
+  if (n_q > 0) {
+    if (best_score) { CU(cudaMemcpyAsync(best_score, J.best_score.p, sizeof(int) * n_q, cudaMemcpyDeviceToHost, g.stream)); d2h += sizeof(int) * (double)n_q; }
+    if (best_idx) { CU(cudaMemcpyAsync(best_idx, J.best_idx.p, sizeof(int) * n_q, cudaMemcpyDeviceToHost, g.stream)); d2h += sizeof(int) * (double)n_q; }
+    if (scores && n_t > 0) {
+      CU(cudaMemcpyAsync(scores, J.all_scores.p, sizeof(int) * (size_t)n_q * n_t, cudaMemcpyDeviceToHost, g.stream));
+      d2h += sizeof(int) * (double)n_q * n_t;
+    }
+  }
+  CU(cudaEventRecord(g.ev[3], g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  float a = 0, b = 0, c = 0;
+  cudaEventElapsedTime(&a, g.ev[0], g.ev[1]);
+  cudaEventElapsedTime(&b, g.ev[1], g.ev[2]);
+  cudaEventElapsedTime(&c, g.ev[2], g.ev[3]);
+  t_timing[0] = a; t_timing[1] = b; t_timing[2] = c; t_timing[3] = J.cells; t_timing[4] = J.launches_per_run;
+  t_timing[5] = J.h2d_bytes; t_timing[6] = d2h; t_timing[7] = b;
+  return ABV_OK;
+}
+
+int abv_best_hits(int mode, const char *q, const long long *q_off, int n_q,
+                  const char *t, const long long *t_off, int n_t,
+                  int alpha_len, const unsigned char *map256, const int *score_matrix,
+                  int gap_open, int gap_extend, int seed_score, int *best_score, int *best_idx) {
+  if (n_q > 0 && (!best_score || !best_idx)) return fail(ABV_ERR_ARGS, "NULL output");
+  return best_hits_impl(mode, q, q_off, n_q, t, t_off, n_t, alpha_len, map256, score_matrix, gap_open, gap_extend,
+                        seed_score, best_score, best_idx, nullptr);
+}
+
+int abv_score_matrix(int mode, const char *q, const long long *q_off, int n_q,
+                     const char *t, const long long *t_off, int n_t,
+                     int alpha_len, const unsigned char *map256, const int *score_matrix,
+                     int gap_open, int gap_extend, int *scores) {
+  if (n_q > 0 && n_t > 0 && !scores) return fail(ABV_ERR_ARGS, "NULL output");
+  return best_hits_impl(mode, q, q_off, n_q, t, t_off, n_t, alpha_len, map256, score_matrix, gap_open, gap_extend,
+                        INT_MIN, nullptr, nullptr, scores);
+}
+
+// -------------------------------------------------------------------------------------------------
+int abv_align_pairs(int mode, const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
+                    int alpha_len, const unsigned char *map256, const int *score_matrix,
+                    int gap_open, int gap_extend,
+                    int *scores, long long *frag_start, int *frag_count,
+                    abv_frag *frags, long long frag_cap, long long *frag_total) {
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  int rc;
+  Scoring sc{alpha_len, gap_open, gap_extend, map256, score_matrix};
+  if ((rc = check_scoring(sc))) return rc;
+  int max_la, min_la, max_lb, min_lb;
+  if ((rc = check_seqs(a, a_off, n, "sequence a", max_la, min_la))) return rc;
+  if ((rc = check_seqs(b, b_off, n, "sequence b", max_lb, min_lb))) return rc;
+  if (mode < 0 || mode > 3) return fail(ABV_ERR_ARGS, "unknown mode %d", mode);
+  if (n > 0 && (rc = check_mode_lengths(mode, min_la, min_lb))) return rc;
+  if (frag_cap < 0 || (frag_cap > 0 && !frags)) return fail(ABV_ERR_ARGS, "bad fragment pool");
+  if (frag_total) *frag_total = 0;
+  if (n == 0) return ABV_OK;
+  if (!scores || !frag_start || !frag_count) return fail(ABV_ERR_ARGS, "NULL output");
+  if ((rc = ctx_init())) return rc;
+  for (double &v : t_timing) v = 0;
+  cudaStream_t st = g.stream;
+  CU(cudaEventRecord(g.ev[0], st));
+  double h2d = 0;
+  DevMem da, da_off, db, db_off, dmap, dmatrix;
+  if ((rc = upload_encoded(a, a_off, n, sc, st, da, da_off, dmap, h2d))) return rc;
+  if ((rc = upload_encoded(b, b_off, n, sc, st, db, db_off, dmap, h2d))) return rc;
+  CU(dmatrix.alloc(sizeof(int) * alpha_len * alpha_len));
+  CU(cudaMemcpyAsync(dmatrix.p, score_matrix, sizeof(int) * alpha_len * alpha_len, cudaMemcpyHostToDevice, st));
+
+  const long long dwords = dir_words(max_la, max_lb);
+  const int tmp_cap = max_la + max_lb + 2;
+  const size_t per_warp = (size_t)dwords * 4 + (size_t)tmp_cap * sizeof(FragOut) + (size_t)max_lb * 8;
+  const int grid = wf32_grid(n, per_warp);
+  const long long warps = (long long)grid * WF32_WARPS;
+  const long long pool = std::min<long long>(frag_cap, (long long)n * (max_la + max_lb + 1));
+  DevMem ddir, dtmp, dborder, dscores, dstart, dcount, dfrags, dcounters;
+  CU(ddir.alloc((size_t)dwords * 4 * warps));
+  CU(dtmp.alloc((size_t)tmp_cap * sizeof(FragOut) * warps));
+  CU(dborder.alloc((size_t)max_lb * 8 * warps));
+  CU(dscores.alloc(sizeof(int) * (size_t)n));
+  CU(dstart.alloc(sizeof(long long) * (size_t)n));
+  CU(dcount.alloc(sizeof(int) * (size_t)n));
+  CU(dfrags.alloc(sizeof(FragOut) * (size_t)std::max<long long>(pool, 1)));
+  CU(dcounters.alloc(16));
+  CU(cudaMemsetAsync(dcounters.p, 0, 16, st));
+  CU(cudaEventRecord(g.ev[1], st));
+
+  Wf32Params p{};
+  p.a = da.as<uint8_t>(); p.a_off = da_off.as<long long>();
+  p.b = db.as<uint8_t>(); p.b_off = db_off.as<long long>();
+  p.n_pairs = n; p.n_t = 0; p.q_base = 0; p.q_list = nullptr;
+  p.matrix = dmatrix.as<int>(); p.alpha = alpha_len; p.go = gap_open; p.ge = gap_extend;
+  p.scores = dscores.as<int>(); p.score_rows_by_query = 0;
+  p.dir = ddir.as<uint32_t>(); p.dir_words_per_warp = dwords;
+  p.frag_tmp = dtmp.as<FragOut>(); p.frag_tmp_cap = tmp_cap;
+  p.frags = dfrags.as<FragOut>(); p.frag_cap = pool;
+  p.frag_total = dcounters.as<unsigned long long>() + 1;
+  p.frag_start = dstart.as<long long>(); p.frag_count = dcount.as<int>();
+  p.border = dborder.as<int>(); p.border_len = max_lb;
+  p.pair_counter = dcounters.as<unsigned long long>();
+  wf32_dispatch<true>(mode, grid, st, p);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(g.ev[2], st));
+
+  unsigned long long total = 0;
+  CU(cudaMemcpyAsync(scores, dscores.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(frag_start, dstart.p, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(frag_count, dcount.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&total, p.frag_total, sizeof total, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  double d2h = 16.0 * n + 8;
+  const long long ncopy = std::min<long long>((long long)total, pool);
+  if (ncopy > 0) {
+    CU(cudaMemcpyAsync(frags, dfrags.p, sizeof(FragOut) * (size_t)ncopy, cudaMemcpyDeviceToHost, st));
+    d2h += 16.0 * ncopy;
+  }
+  CU(cudaEventRecord(g.ev[3], st));
+  CU(cudaStreamSynchronize(st));
+  if (frag_total) *frag_total = (long long)total;
+  float t0 = 0, t1 = 0, t2 = 0;
+  cudaEventElapsedTime(&t0, g.ev[0], g.ev[1]);
+  cudaEventElapsedTime(&t1, g.ev[1], g.ev[2]);
+  cudaEventElapsedTime(&t2, g.ev[2], g.ev[3]);
+  double cells = 0;
+  for (int i = 0; i < n; ++i) cells += (double)(a_off[i + 1] - a_off[i]) * (double)(b_off[i + 1] - b_off[i]);
+  t_timing[0] = t0; t_timing[1] = t1; t_timing[2] = t2; t_timing[3] = cells; t_timing[4] = 3;
+  t_timing[5] = h2d; t_timing[6] = d2h; t_timing[7] = t1;
+  if ((long long)total > frag_cap)
+    return fail(ABV_ERR_FRAG_CAP, "fragment pool of %lld entries is too small, %llu needed", frag_cap, total);
+  return ABV_OK;
+}
+
+int abv_get_timing(double *out, int n) {
+  if (!out || n <= 0) return 0;
+  n = std::min(n, 8);
+  for (int i = 0; i < n; ++i) out[i] = t_timing[i];
+  return n;
+}
+
+int abv_int_peak(int which, int iters, double *lane_ops_per_s, double *sm_clock_mhz) {
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  int rc;
+  if ((rc = ctx_init())) return rc;
+  if (which < 0 || which > 7 || iters <= 0) return fail(ABV_ERR_ARGS, "bad microbenchmark arguments");
+  const int threads = 256, grid = g.sms * 8;
+  DevMem out;
+  CU(out.alloc(sizeof(uint32_t) * (size_t)grid * threads));
+  auto run = [&](int it) {
+    switch (which) {
+      case 0: int_peak_kernel<0><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
+      case 1: int_peak_kernel<1><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
+      case 2: int_peak_kernel<2><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
+      case 3: int_peak_kernel<3><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
+      case 4: int_peak_kernel<4><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
+      case 5: int_peak_kernel<5><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
+      case 6: int_peak_kernel<6><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
+      default: int_peak_kernel<7><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
+    }
+  };
+  run(std::max(1, iters / 10));   // warm-up
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(g.ev[4], g.stream));
+  run(iters);
+  CU(cudaEventRecord(g.ev[5], g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  CU(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, g.ev[4], g.ev[5]);
+  const double ops = (double)grid * threads * INT_PEAK_CHAINS * INT_PEAK_OPS[which] * (double)iters;
+  if (lane_ops_per_s) *lane_ops_per_s = ops / (ms * 1e-3);
+  if (sm_clock_mhz) {
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g.device);
+    *sm_clock_mhz = khz / 1000.0;
+  }
+  return ABV_OK;
+}
+
+// =================================================================================================
+// Part 1: the reference's own ABI (lib/align/align.h:43-125)
+
+int align_frag_count(AlignFrag *f) {
+  int i = 0;
+  for (; f; f = f->next) ++i;
+  return i;
+}
+
+void align_frag_free(AlignFrag *f) {
+  while (f) {
+    AlignFrag *nx = f->next;
+    free(f);
+    f = nx;
+  }
+}
+
+void alignment_free(Alignment *alignment) {
+  if (!alignment) return;     // the reference would crash here (alignment.c:36-39); harmless superset
+  align_frag_free(alignment->align_frag);
+  free(alignment);
+}
+
+Alignment *alignment_new(AlignFrag *align_frag, int score) {
+  Alignment *al = (Alignment *)malloc(sizeof(Alignment));
+  if (al) {
+    al->align_frag = align_frag;
+    al->frag_count = align_frag_count(align_frag);
+    al->score = score;
+  }
+  return al;
+}
+
+static Alignment *legacy_align(int mode, const char *sa, int la, const char *sb, int lb, int alpha_len,
+                               const unsigned char *map, int *matrix, int go, int ge, bool need_map) {
+  // global_align.c:118-122, :241-243
+  if (la <= 0 || lb <= 0 || !sa || !sb || !matrix || go > 0 || ge > 0) return nullptr;
+  if (need_map && !map) return nullptr;
+  const long long a_off[2] = {0, la}, b_off[2] = {0, lb};
+  const long long cap = (long long)la + lb + 2;
+  std::vector<abv_frag> frags((size_t)cap);
+  int score = 0, count = 0;
+  long long start = 0, total = 0;
+  int rc = abv_align_pairs(mode, sa, a_off, sb, b_off, 1, alpha_len, need_map ? map : nullptr, matrix, go, ge,
+                           &score, &start, &count, frags.data(), cap, &total);
+  if (rc != ABV_OK) return nullptr;
+  AlignFrag *head = nullptr;
+  for (int i = count - 1; i >= 0; --i) {
+    AlignFrag *f = (AlignFrag *)malloc(sizeof(AlignFrag));
+    if (!f) { align_frag_free(head); return nullptr; }
+    const abv_frag &s = frags[(size_t)start + i];
+    f->next = head; f->type = (FragType)s.type; f->sa_start = s.sa_start; f->sb_start = s.sb_start; f->hsp_len = s.hsp_len;
+    head = f;
+  }
+  Alignment *al = alignment_new(head, score);
+  if (!al) align_frag_free(head);
+  return al;
+}
+
+#define ABV_LEGACY(NAME, MODE)                                                                                     \
+  Alignment *NAME##_raw(const unsigned char *sa, int sa_len, const unsigned char *sb, int sb_len, int alpha_len,   \
+                        int *score_matrix, int gap_open, int gap_extend) {                                         \
+    return legacy_align(MODE, (const char *)sa, sa_len, (const char *)sb, sb_len, alpha_len, nullptr, score_matrix, \
+                        gap_open, gap_extend, false);                                                              \
+  }                                                                                                                \
+  Alignment *NAME(const char *seqa, int sa_len, const char *seqb, int sb_len, int alpha_len,                       \
+                  const unsigned char *map, int *score_matrix, int gap_open, int gap_extend) {                     \
+    return legacy_align(MODE, seqa, sa_len, seqb, sb_len, alpha_len, map, score_matrix, gap_open, gap_extend, true); \
+  }
+
+ABV_LEGACY(align, ABV_OVERLAP)
+ABV_LEGACY(local_align, ABV_LOCAL)
+ABV_LEGACY(global_align, ABV_GLOBAL)
+ABV_LEGACY(glocal_align, ABV_GLOCAL)
+
+}  // extern "C"

@@ -1,0 +1,311 @@
+// dp_core.cuh -- the per-cell recurrences, direction encoding and traceback walk shared by the
+// sm_100a kernels (kernels.cu).  Everything here is a small __host__ __device__ inline function so
+// that tests/emu can drive the very same cell logic lane by lane on a CPU and compare it with the
+// oracle before any GPU time is spent; the shipped library only ever runs it on the device.
+//
+// Notation follows the reference: sa = query, indexed by col; sb = target,
+// indexed by row; H = cell score; F = gap running down a column (consumes sb, A_GAP); E = gap
+// running along a row (consumes sa, B_GAP).  Reference recurrences:
+//   lib/align/global_align.c:136-217, local_align.c:119-214, glocal_align.c:115-191, align.c:109-232.
+#pragma once
+#include <limits.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ABV_HD __host__ __device__ __forceinline__
+#else
+#define ABV_HD inline
+#endif
+
+namespace abv {
+
+enum Mode { OVERLAP = 0, LOCAL = 1, GLOBAL = 2, GLOCAL = 3 };
+enum { FRAG_A_GAP = 0, FRAG_B_GAP = 1, FRAG_MATCH = 2 };
+
+constexpr int NEG_HALF = INT_MIN / 2;   // glocal_align.c:120-122 "minus infinity"
+
+// ---------------------------------------------------------------------------------------------
+// Direction nibble.  The reference stores a jump length per cell (0 diag, <0 A_GAP length,
+// >0 B_GAP length, INT_MIN local stop; e.g. local_align.c:183-197).  The jump length of a gap
+// is "distance back to where that gap state was last opened", so it is recoverable from one
+// open/extend bit per gap state per cell: 4 bits per cell instead of 32.
+constexpr unsigned SRC_DIAG = 0, SRC_F = 1, SRC_E = 2, SRC_STOP = 3, SRC_MASK = 3;
+constexpr unsigned BIT_FOPEN = 4;   // after this cell the column gap restarts here (vgap_pos = row)
+constexpr unsigned BIT_EOPEN = 8;   // after this cell the row gap restarts here    (hgap_pos = col)
+
+// End-cell candidate of one lane (one column).  Cross-lane order is (score, col): the reference
+// scans column-major with '>=' so among equal maxima the last scanned cell wins.
+struct EndCell {
+  int score, col, row;
+};
+
+ABV_HD bool end_better(const EndCell &a, const EndCell &b) {   // a replaces b ?
+  return a.score > b.score || (a.score == b.score && a.col > b.col);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One cell of the 32-bit wavefront kernel.
+//   c,r      : column (query position) and row (target position)
+//   sub      : score_matrix[sa[c]*alpha + sb[r]]
+//   hdiag    : H[c-1][r-1] as handed over by the left neighbour (for c==0 the caller passes the
+//              mode's virtual column -1); row 0 is overridden here where the mode defines it
+//   e_in     : E[r] entering column c
+//   F        : column gap state entering row r (lane-resident, updated in place)
+//   h,e_out  : H[c][r] and E[r] leaving column c
+//   cand     : lane's end-cell candidate (updated per the mode's rule)
+// returns the direction nibble.
+template <int MODE>
+ABV_HD unsigned wf32_cell(int c, int r, int la, int lb, int sub, int hdiag, int e_in, int &F,
+                          int go, int ge, int &h, int &e_out, EndCell &cand) {
+  unsigned nib;
+  if (MODE == GLOBAL) {
+    if (r == 0) {                       // global_align.c:145-148
+      hdiag = c ? go + ge * (c - 1) : 0;
+      F = 2 * go + ge * c;
+    }
+  } else if (MODE == LOCAL) {
+    if (r == 0) {                       // local_align.c:134-137
+      hdiag = 0;
+      F = go;
+    }
+  } else if (MODE == GLOCAL) {
+    if (r == 0) {                       // first target row: forced match (glocal_align.c:128-136)
+      h = sub;
+      F = h + go;
+      e_out = e_in;
+      return SRC_DIAG | BIT_FOPEN;
+    }
+    if (r == lb - 1) {                  // last target row: forced match (glocal_align.c:172-183)
+      h = hdiag + sub;
+      e_out = e_in;
+      if (h >= 0) { cand.score = h; cand.col = c; cand.row = r; }
+      return SRC_DIAG;
+    }
+  } else {                              // OVERLAP
+    if (c == 0) {                       // first column (align.c:114-125)
+      h = sub;
+      e_out = h + go;
+      if (r == lb - 1) { cand.score = h; cand.col = c; cand.row = r; }
+      return SRC_DIAG | BIT_EOPEN;
+    }
+    if (r == 0) {                       // top cell of later columns (align.c:135-138, :185-192)
+      h = sub;
+      F = h + go;
+      e_out = e_in;
+      if (c == la - 1 || lb == 1) { cand.score = h; cand.col = c; cand.row = 0; }
+      return SRC_DIAG | BIT_FOPEN;
+    }
+  }
+
+  // the common choice: diagonal wins ties over F, both win ties over E (global_align.c:180-192)
+  int s = hdiag + sub;
+  unsigned src = SRC_DIAG;
+  if (s < F) { s = F; src = SRC_F; }
+  if (s < e_in) { s = e_in; src = SRC_E; }
+
+  if (MODE == LOCAL) {
+    if (s < 0) { s = 0; src = SRC_STOP; }                       // local_align.c:150-152
+    else if (s >= cand.score) { cand.score = s; cand.col = c; cand.row = r; }   // :156-160
+  }
+  if (MODE == OVERLAP) {
+    if (c == la - 1) {                                          // align.c:211-215
+      if (s >= cand.score) { cand.score = s; cand.col = c; cand.row = r; }
+    } else if (r == lb - 1) {                                   // align.c:172-176
+      cand.score = s; cand.col = c; cand.row = r;
+    }
+  }
+
+  // gap state updates: opening wins ties over extending (global_align.c:198-209)
+  bool fo = (s + go >= F + ge), eo = (s + go >= e_in + ge);
+  if (MODE == OVERLAP && c < la - 1) {                          // guarded re-open (align.c:157, :164)
+    fo = fo && (src != SRC_F);
+    eo = eo && (src != SRC_E);
+  }
+  F = fo ? s + go : F + ge;
+  e_out = eo ? s + go : e_in + ge;
+  h = s;
+  nib = src | (fo ? BIT_FOPEN : 0u) | (eo ? BIT_EOPEN : 0u);
+  return nib;
+}
+
+// virtual column -1 handed to column 0: H[-1][r] and E[r] entering column 0
+template <int MODE>
+ABV_HD void wf32_virtual_column(int r, int go, int ge, int &h_left, int &e_in) {
+  if (MODE == GLOBAL) { h_left = go + ge * r; e_in = h_left + go; }        // global_align.c:136-140
+  else if (MODE == LOCAL) { h_left = 0; e_in = go; }                       // local_align.c:123-128
+  else if (MODE == GLOCAL) { h_left = NEG_HALF; e_in = NEG_HALF; }         // glocal_align.c:119-123
+  else { h_left = 0; e_in = 0; }                                           // overlap: column 0 ignores both
+}
+
+template <int MODE>
+ABV_HD EndCell wf32_initial_candidate() {
+  EndCell e;
+  e.score = (MODE == OVERLAP) ? INT_MIN : -1;   // local/glocal: -1 = "no cell reached best >= 0"
+  e.col = -1;
+  e.row = -1;
+  return e;
+}
+
+// final (score, end cell) of a pair from the warp-wide best candidate / the corner cell
+template <int MODE>
+ABV_HD void wf32_finish(const EndCell &best, int corner_h, int la, int lb, int &score, int &ec, int &er) {
+  if (MODE == GLOBAL) { score = corner_h; ec = la - 1; er = lb - 1; }      // global_align.c:217
+  else if (MODE == OVERLAP) { score = best.score; ec = best.col; er = best.row; }
+  else if (best.score < 0 || best.col < 0) { score = 0; ec = 0; er = 0; }  // max starts at 0,(0,0)
+  else { score = best.score; ec = best.col; er = best.row; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Direction matrix layout of the wavefront kernel: the query is cut into blocks of 32 columns,
+// lane t owns column 32*b+t and at step s works on row s-t.  Each lane packs the nibbles of 8
+// consecutive steps into one 32-bit word, so a warp writes one coalesced 128-byte line per 8
+// steps:   word(b, s, t) = (b*steps8 + s/8)*32 + t ,  nibble s%8.
+ABV_HD int dir_steps8(int lb) { return (lb + 31 + 7) >> 3; }
+ABV_HD long long dir_words(int la, int lb) { return (long long)((la + 31) >> 5) * dir_steps8(lb) * 32; }
+
+struct DirReader {
+  const uint32_t *w;
+  int steps8;
+  ABV_HD unsigned get(int col, int row) const {
+    int b = col >> 5, t = col & 31, s = row + t;
+    uint32_t v = w[((long long)b * steps8 + (s >> 3)) * 32 + t];
+    return (v >> ((s & 7) * 4)) & 15u;
+  }
+};
+
+struct FragOut {
+  int type, sa_start, sb_start, hsp_len;
+};
+
+// Traceback (global_align.c:25-92, local_align.c:23-72, glocal_align.c:25-70, align.c:25-65).
+// Writes fragments in REVERSE sequence order into out[0..cap) and returns how many there are
+// (which may exceed cap; the excess is counted but not stored).
+template <int MODE, class Reader>
+ABV_HD int walk_back(const Reader &rd, int col, int row, FragOut *out, int cap) {
+  int n = 0;
+  while (col >= 0 && row >= 0) {
+    unsigned nib = rd.get(col, row);
+    unsigned src = nib & SRC_MASK;
+    if (MODE == LOCAL && src == SRC_STOP) break;
+    FragOut f;
+    if (src == SRC_F) {              // jump = -(row - vgap_pos): back to where F was last opened
+      int p = row - 1;
+      while (p >= 0 && !(rd.get(col, p) & BIT_FOPEN)) --p;
+      f.type = FRAG_A_GAP; f.hsp_len = row - p;
+      row = p;
+    } else if (src == SRC_E) {       // jump = col - hgap_pos[row]
+      int p = col - 1;
+      while (p >= 0 && !(rd.get(p, row) & BIT_EOPEN)) --p;
+      f.type = FRAG_B_GAP; f.hsp_len = col - p;
+      col = p;
+    } else {                         // diagonal run
+      int run = 0;
+      do { --col; --row; ++run; }
+      while (col >= 0 && row >= 0 && (rd.get(col, row) & SRC_MASK) == SRC_DIAG);
+      f.type = FRAG_MATCH; f.hsp_len = run;
+    }
+    f.sa_start = col + 1; f.sb_start = row + 1;
+    if (n < cap) out[n] = f;
+    ++n;
+  }
+  if (MODE == GLOBAL && (col >= 0 || row >= 0)) {   // leading end gap (global_align.c:69-86)
+    FragOut f; f.sa_start = 0; f.sb_start = 0;
+    if (col >= 0) { f.type = FRAG_B_GAP; f.hsp_len = col + 1; }
+    else          { f.type = FRAG_A_GAP; f.hsp_len = row + 1; }
+    if (n < cap) out[n] = f;
+    ++n;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packed 16-bit arithmetic of the many-to-many score-only kernel: each 32-bit word carries the
+// same DP cell of TWO alignments (one query against two targets).  On sm_100a these are single
+// instructions (VIADD.16x2, VIMNMX.S16x2, VIMNMX3.S16x2, VIADDMNMX.S16x2[.RELU]).
+namespace p16 {
+
+ABV_HD uint32_t pack(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+ABV_HD int lo(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
+ABV_HD int hi(uint32_t v) { return (int)(int16_t)(v >> 16); }
+
+#if defined(__CUDA_ARCH__)
+ABV_HD uint32_t add(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+ABV_HD uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+ABV_HD uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+ABV_HD uint32_t max3_relu(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2_relu(a, b, c); }
+ABV_HD uint32_t addmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }   // max(a+b, c)
+#else
+ABV_HD int16_t w16(int v) { return (int16_t)(uint16_t)(v & 0xffff); }   // wrap like the hardware
+ABV_HD uint32_t add(uint32_t a, uint32_t b) { return pack(w16(lo(a) + lo(b)), w16(hi(a) + hi(b))); }
+ABV_HD int mx(int a, int b) { return a > b ? a : b; }
+ABV_HD uint32_t max2(uint32_t a, uint32_t b) { return pack(mx(lo(a), lo(b)), mx(hi(a), hi(b))); }
+ABV_HD uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return max2(max2(a, b), c); }
+ABV_HD uint32_t max3_relu(uint32_t a, uint32_t b, uint32_t c) { return max2(max3(a, b, c), 0u); }
+ABV_HD uint32_t addmax(uint32_t a, uint32_t b, uint32_t c) { return max2(add(a, b), c); }
+#endif
+
+// "minus infinity" of the packed kernel and the bound that makes it exact: every true DP value v
+// of a pair satisfies |v| <= P16_LIMIT, so NEG16 + anything reachable never wins a max against a
+// true value and never wraps.
+constexpr int NEG16 = -16000;
+constexpr int P16_LIMIT = 8000;
+
+}  // namespace p16
+
+// Layout of the per-query substitution profile in shared memory.  Lane t of the warp owns query
+// columns [t*K, (t+1)*K).  Its K packed substitution scores for one target-pair symbol are read
+// with K/V vector loads of V words; chunk i of lane t sits at word (i*32 + t)*V, so the 8 (V=4)
+// or 16 (V=2) lanes of one shared-memory phase touch 32 consecutive banks whatever symbol each
+// lane is looking up (the row stride 32*K words is a multiple of 32 banks).
+template <int K, int V>
+ABV_HD int lut_pos(int c) {   // c = t*K + k
+  int t = c / K, k = c % K;
+  return ((k / V) * 32 + t) * V + (k % V);
+}
+
+// One row of one lane of the packed kernel, plain Gotoh form (5 packed ops per cell pair):
+//   d   : in  H[c0-1][r-1]                          (diag of the lane's first column)
+//   e   : in  E[r] entering c0; out E[r] leaving the strip
+//   Hp  : in  H[.][r-1]; out H[.][r]
+//   F   : column gap states
+//   S   : packed substitution scores of the K columns for this row's target symbols
+template <int K, bool RELU, bool TRACK_MAX>
+ABV_HD void mm16_row(uint32_t d, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], const uint32_t (&S)[K],
+                     uint32_t go2, uint32_t ge2, uint32_t &best) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    uint32_t dd = p16::add(d, S[k]);
+    d = Hp[k];
+    uint32_t h = RELU ? p16::max3_relu(dd, e, F[k]) : p16::max3(dd, e, F[k]);
+    uint32_t hg = p16::add(h, go2);
+    e = p16::addmax(e, ge2, hg);
+    F[k] = p16::addmax(F[k], ge2, hg);
+    Hp[k] = h;
+    if (TRACK_MAX) best = p16::max2(best, h);
+  }
+}
+
+// glocal rows on which at least one half is on its last target row: that half takes the forced
+// diagonal (glocal_align.c:172-176), the other half the plain update.  `last_mask` has 0xffff in
+// the halves that are on their last row.  colmask[k] is 0xffff.. for real query columns.
+template <int K>
+ABV_HD void mm16_row_glocal_last(uint32_t d, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], const uint32_t (&S)[K],
+                                 uint32_t go2, uint32_t ge2, uint32_t last_mask, int c0, int lq, uint32_t &best) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    uint32_t dd = p16::add(d, S[k]);
+    d = Hp[k];
+    uint32_t hn = p16::max3(dd, e, F[k]);
+    uint32_t h = (dd & last_mask) | (hn & ~last_mask);
+    uint32_t hg = p16::add(h, go2);
+    e = p16::addmax(e, ge2, hg);
+    F[k] = p16::addmax(F[k], ge2, hg);
+    Hp[k] = h;
+    if (c0 + k < lq) {   // only real query columns may end the alignment
+      uint32_t cand = (h & last_mask) | (p16::pack(p16::NEG16, p16::NEG16) & ~last_mask);
+      best = p16::max2(best, cand);
+    }
+  }
+}
+
+}  // namespace abv

@@ -1,0 +1,524 @@
+// kernels.cuh -- hand-written sm_100a kernels of the AmBiVErT alignment backend.
+//
+//   encode_kernel        to_raw (lib/align/helpers.h:26-32): bytes -> symbol indices, on the device
+//   wf32_kernel          general kernel: one warp per (sa, sb) pair, 32-bit, anti-diagonal wavefront
+//                        over 32-column blocks with shuffle exchange; all four modes; optional
+//                        4-bit direction matrix + traceback (bit-exact fragment lists)
+//   mm16_kernel          many-to-many score-only kernel: one warp per (query, target PAIR), packed
+//                        16x2 DPX arithmetic, per-query substitution profile in shared memory,
+//                        target symbols staged by bulk async copies (TMA 1-D), fused per-query arg-max
+//   argmax_rows_kernel   per-query first-maximum selection over a score matrix (general path)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dp_core.cuh"
+
+namespace abv {
+
+#define ABV_FULL 0xffffffffu
+
+// ---------------------------------------------------------------------------------------------
+__global__ void encode_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, long long n,
+                              const uint8_t *__restrict__ map256) {
+  __shared__ uint8_t m[256];
+  if (threadIdx.x < 256) m[threadIdx.x] = map256[threadIdx.x];
+  __syncthreads();
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = m[in[i]];
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Wf32Params {
+  const uint8_t *a; const long long *a_off;      // encoded sa sequences (queries)
+  const uint8_t *b; const long long *b_off;      // encoded sb sequences (targets)
+  long long n_pairs;                             // pairs of this launch
+  int n_t;                                       // 0: pair p = (a[p], b[p]); >0: p -> (row q_base + p / n_t, p % n_t)
+  long long q_base;
+  const int *q_list;                             // optional: query of a row = q_list[row]
+  int score_rows_by_query;                       // many-to-many: scores[query*n_t + target] instead of scores[p]
+  const int *matrix; int alpha, go, ge;
+  int *scores;                                   // [n_pairs]
+  // traceback (TRACE only)
+  uint32_t *dir; long long dir_words_per_warp;   // per-warp direction scratch
+  FragOut *frag_tmp; int frag_tmp_cap;           // per-warp reversed fragment scratch
+  FragOut *frags; long long frag_cap;            // output pool
+  unsigned long long *frag_total;
+  long long *frag_start; int *frag_count;
+  // column-block border hand-over (queries longer than 32): 2*border_len ints per warp
+  int *border; int border_len;
+  unsigned long long *pair_counter;
+};
+
+constexpr int WF32_WARPS = 8;
+constexpr int WF32_MAX_SMEM_ALPHA = 48;
+
+template <int MODE, bool TRACE>
+__global__ void __launch_bounds__(WF32_WARPS * 32) wf32_kernel(Wf32Params p) {
+  __shared__ int s_matrix[WF32_MAX_SMEM_ALPHA * WF32_MAX_SMEM_ALPHA];
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const long long gwarp = (long long)blockIdx.x * WF32_WARPS + warp_in_block;
+  const int alpha = p.alpha, go = p.go, ge = p.ge;
+  const bool smem_matrix = alpha <= WF32_MAX_SMEM_ALPHA;
+  if (smem_matrix)
+    for (int i = threadIdx.x; i < alpha * alpha; i += blockDim.x) s_matrix[i] = p.matrix[i];
+  __syncthreads();
+  const int *M = smem_matrix ? s_matrix : p.matrix;
+
+  uint32_t *dir = TRACE ? p.dir + gwarp * p.dir_words_per_warp : nullptr;
+  int *borderH = p.border + gwarp * 2 * (long long)p.border_len;
+  int *borderE = borderH + p.border_len;
+
+  for (;;) {
+    unsigned long long pidx = 0;
+    if (lane == 0) pidx = atomicAdd(p.pair_counter, 1ull);
+    pidx = __shfl_sync(ABV_FULL, pidx, 0);
+    if ((long long)pidx >= p.n_pairs) break;
+    long long ia, ib, out_idx = (long long)pidx;
+    if (p.n_t > 0) {
+      const long long row = p.q_base + (long long)(pidx / (unsigned)p.n_t);
+      ia = p.q_list ? (long long)p.q_list[row] : row;
+      ib = (long long)(pidx % (unsigned)p.n_t);
+      if (p.score_rows_by_query) out_idx = ia * p.n_t + ib;
+    } else { ia = (long long)pidx; ib = (long long)pidx; }
+    const uint8_t *sa = p.a + p.a_off[ia];
+    const uint8_t *sb = p.b + p.b_off[ib];
+    const int la = (int)(p.a_off[ia + 1] - p.a_off[ia]);
+    const int lb = (int)(p.b_off[ib + 1] - p.b_off[ib]);
+    const int nblk = (la + 31) >> 5;
+    const int steps8 = dir_steps8(lb);
+
+    EndCell wbest = wf32_initial_candidate<MODE>();
+    int corner = 0;
+
+    for (int b = 0; b < nblk; ++b) {
+      const int c = (b << 5) + lane;
+      const bool colvalid = c < la;
+      const int qa = colvalid ? (int)sa[c] * alpha : 0;
+      int F = 0, hleft_prev = 0, h_out = 0, e_out = 0;
+      EndCell cand = wf32_initial_candidate<MODE>();
+      uint32_t acc = 0;
+      const int lanes_used = min(32, la - (b << 5));
+      const int nsteps = lb + lanes_used - 1;
+      for (int s = 0; s < nsteps; ++s) {
+        int h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
+        int e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+        const int r = s - lane;
+        if (lane == 0 && s < lb) {
+          if (b == 0) wf32_virtual_column<MODE>(s, go, ge, h_sh, e_sh);
+          else { h_sh = borderH[s]; e_sh = borderE[s]; }
+        }
+        unsigned nib = 0;
+        if (r >= 0 && r < lb && colvalid) {
+          const int sub = M[qa + (int)sb[r]];
+          int h, eo;
+          nib = wf32_cell<MODE>(c, r, la, lb, sub, hleft_prev, e_sh, F, go, ge, h, eo, cand);
+          hleft_prev = h_sh;
+          h_out = h;
+          e_out = eo;
+          if (MODE == GLOBAL && c == la - 1 && r == lb - 1) corner = h;
+          if (lane == 31 && b + 1 < nblk) { borderH[r] = h; borderE[r] = eo; }
+        }
+        if (TRACE) {
+          acc |= nib << ((s & 7) * 4);
+          if ((s & 7) == 7 || s == nsteps - 1) {
+            dir[((long long)b * steps8 + (s >> 3)) * 32 + lane] = acc;
+            acc = 0;
+          }
+        }
+      }
+      // best end cell of this block, then fold into the running best (later blocks win ties)
+      for (int off = 16; off > 0; off >>= 1) {
+        EndCell o;
+        o.score = __shfl_xor_sync(ABV_FULL, cand.score, off);
+        o.col = __shfl_xor_sync(ABV_FULL, cand.col, off);
+        o.row = __shfl_xor_sync(ABV_FULL, cand.row, off);
+        if (end_better(o, cand)) cand = o;
+      }
+      if (cand.col >= 0 && cand.score >= wbest.score) wbest = cand;
+      __syncwarp();
+    }
+    if (MODE == GLOBAL) corner = __shfl_sync(ABV_FULL, corner, (la - 1) & 31);
+    int score, ec, er;
+    wf32_finish<MODE>(wbest, corner, la, lb, score, ec, er);
+    if (lane == 0) p.scores[out_idx] = score;
+
+    if (TRACE) {
+      __syncwarp();
+      FragOut *tmp = p.frag_tmp + gwarp * (long long)p.frag_tmp_cap;
+      int n = 0;
+      unsigned long long base = 0;
+      if (lane == 0) {
+        DirReader rd; rd.w = dir; rd.steps8 = steps8;
+        n = walk_back<MODE>(rd, ec, er, tmp, p.frag_tmp_cap);
+        base = atomicAdd(p.frag_total, (unsigned long long)n);
+        p.frag_start[pidx] = (long long)base;
+        p.frag_count[pidx] = n;
+      }
+      n = __shfl_sync(ABV_FULL, n, 0);
+      base = __shfl_sync(ABV_FULL, base, 0);
+      __syncwarp();
+      for (int i = lane; i < n; i += 32)
+        if ((long long)(base + i) < p.frag_cap) p.frags[base + i] = tmp[n - 1 - i];
+      __syncwarp();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-query selection over a score matrix: strict '>' in target order from the seed
+// (ambivert.py:478-485): first maximum wins; idx -1 when nothing beats the seed.
+__global__ void argmax_rows_kernel(const int *__restrict__ scores, int n_rows, int n_t, int seed,
+                                   int *__restrict__ best_score, int *__restrict__ best_idx, long long row_base,
+                                   const int *__restrict__ row_map, int rows_by_query) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const long long qi = row_map ? (long long)row_map[row_base + row] : row_base + row;
+  const int *s = scores + (rows_by_query ? qi : (long long)row) * n_t;
+  int bs = INT_MIN, bi = INT_MAX;
+  for (int j = lane; j < n_t; j += 32) {
+    int v = s[j];
+    if (v > bs) { bs = v; bi = j; }       // ascending j within a lane: first maximum kept
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    int os = __shfl_xor_sync(ABV_FULL, bs, off), oi = __shfl_xor_sync(ABV_FULL, bi, off);
+    if (os > bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+  }
+  if (lane == 0) {
+    bool hit = n_t > 0 && bs > seed;
+    best_score[qi] = hit ? bs : seed;
+    best_idx[qi] = hit ? bi : -1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bulk async copy (TMA 1-D: SASS UBLKCP) global -> shared with mbarrier completion
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  } while (!ok);
+}
+
+struct Mm16Params {
+  const uint8_t *q; const long long *q_off;   // encoded queries
+  const int *q_list; int n_list;              // the queries of this launch (one K bucket)
+  const uint8_t *tp_codes; int tp_stride;     // target-pair symbol rows (bytes, stride multiple of 16)
+  const int4 *tp_meta;                        // {len1, len2, idx1, idx2}; idx2 = -1: single target
+  int n_pairs;
+  const int *matrix_ext;                      // (alpha+1)^2, last row/col (the pad symbol) zero
+  int a1;                                     // alpha + 1
+  int go, ge, seed;
+  int *best_score, *best_idx;                 // indexed by query
+  int *all_scores; int n_t;                   // optional full score matrix [query*n_t + target]
+  unsigned int *q_counter;
+};
+
+constexpr int MM16_WARPS = 8;
+
+template <int K>
+struct Mm16Cfg {
+  static constexpr int V = (K % 4 == 0) ? 4 : 2;     // words per shared-memory vector load
+  static constexpr int P = 32 * K;                   // profile row length in words
+  static constexpr int MIN_BLOCKS = K <= 8 ? 4 : (K <= 12 ? 3 : 2);
+};
+
+template <int K>
+__device__ __forceinline__ void mm16_load_S(const uint32_t *lut_row, int lane, uint32_t (&S)[K]) {
+  if (Mm16Cfg<K>::V == 4) {
+    const uint4 *rp = reinterpret_cast<const uint4 *>(lut_row) + lane;
+#pragma unroll
+    for (int i = 0; i < K / 4; ++i) {
+      uint4 v = rp[i * 32];
+      S[4 * i] = v.x; S[4 * i + 1] = v.y; S[4 * i + 2] = v.z; S[4 * i + 3] = v.w;
+    }
+  } else {
+    const uint2 *rp = reinterpret_cast<const uint2 *>(lut_row) + lane;
+#pragma unroll
+    for (int i = 0; i < K / 2; ++i) {
+      uint2 v = rp[i * 32];
+      S[2 * i] = v.x; S[2 * i + 1] = v.y;
+    }
+  }
+}
+
+template <int K>
+__device__ __forceinline__ uint32_t mm16_pick(const uint32_t (&Hp)[K], int kstar) {
+  uint32_t v = Hp[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) v = (k == kstar) ? Hp[k] : v;
+  return v;
+}
+
+__device__ __forceinline__ uint32_t warp_max2(uint32_t v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = p16::max2(v, __shfl_xor_sync(ABV_FULL, v, off));
+  return v;
+}
+
+// dynamic shared memory layout of mm16_kernel (offsets in bytes); host and device agree through this
+struct Mm16Smem {
+  int lut, qcodes, mext, tbuf, mbar, wres, misc, total;
+};
+__host__ __device__ inline Mm16Smem mm16_smem_layout(int K, int a1, int tp_stride) {
+  Mm16Smem L;
+  int off = 0;
+  L.lut = off; off += a1 * a1 * 32 * K * 4;
+  L.tbuf = off; off += MM16_WARPS * 2 * tp_stride;
+  L.mbar = off; off += MM16_WARPS * 2 * 8;
+  L.mext = off; off += a1 * a1 * 4;
+  L.wres = off; off += MM16_WARPS * 2 * 4;
+  L.misc = off; off += 16;
+  L.qcodes = off; off += 32 * K;
+  L.total = (off + 15) & ~15;
+  return L;
+}
+
+template <int MODE, int K>
+__global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16_kernel(Mm16Params p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int P = Mm16Cfg<K>::P;
+  constexpr int V = Mm16Cfg<K>::V;
+  const Mm16Smem L = mm16_smem_layout(K, p.a1, p.tp_stride);
+  uint32_t *lut = reinterpret_cast<uint32_t *>(smem + L.lut);
+  uint8_t *qcodes = smem + L.qcodes;
+  int *mext = reinterpret_cast<int *>(smem + L.mext);
+  int *wres = reinterpret_cast<int *>(smem + L.wres);
+  int *misc = reinterpret_cast<int *>(smem + L.misc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t *tbuf0 = smem + L.tbuf + warp * 2 * p.tp_stride;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.mbar) + warp * 2;
+
+  const int a1 = p.a1, ncodes = a1 * a1;
+  const int go = p.go, ge = p.ge;
+  const uint32_t go2 = p16::pack(go, go), ge2 = p16::pack(ge, ge);
+  const uint32_t NEG2 = p16::pack(p16::NEG16, p16::NEG16);
+
+  for (int i = threadIdx.x; i < ncodes; i += blockDim.x) mext[i] = p.matrix_ext[i];
+  if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+  mbar_fence_init();
+  uint32_t phase0 = 0, phase1 = 0;
+  __syncthreads();
+
+  for (;;) {
+    if (threadIdx.x == 0) misc[0] = (int)atomicAdd(p.q_counter, 1u);
+    __syncthreads();
+    const int li = misc[0];
+    if (li >= p.n_list) break;
+    const int qi = p.q_list[li];
+    const uint8_t *qs = p.q + p.q_off[qi];
+    const int lq = (int)(p.q_off[qi + 1] - p.q_off[qi]);
+    for (int c = threadIdx.x; c < P; c += blockDim.x) qcodes[c] = c < lq ? qs[c] : (uint8_t)(a1 - 1);
+    __syncthreads();
+    // per-query profile: lut[code][pos(c)] = (S(q[c], a), S(q[c], b)), code = a*a1 + b
+    for (int idx = threadIdx.x; idx < ncodes * P; idx += blockDim.x) {
+      const int code = idx / P, pos = idx - code * P;
+      const int j = pos % V, it = pos / V, t = it & 31, i = it >> 5;
+      const int c = t * K + i * V + j;
+      const int qa = qcodes[c] * a1;
+      const int a = code / a1, bsym = code - a * a1;
+      lut[idx] = p16::pack(mext[qa + a], mext[qa + bsym]);
+    }
+    __syncthreads();
+
+    const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;
+    const int c0 = lane * K;
+    int wbest = INT_MIN, widx = INT_MAX;
+
+    int pi = warp;
+    if (pi < p.n_pairs && lane == 0) bulk_load(tbuf0, p.tp_codes + (long long)pi * p.tp_stride, p.tp_stride, &bar[0]);
+    int it = 0;
+    for (; pi < p.n_pairs; pi += MM16_WARPS, ++it) {
+      const int cur = it & 1;
+      const int pn = pi + MM16_WARPS;
+      __syncwarp();
+      if (pn < p.n_pairs && lane == 0)
+        bulk_load(tbuf0 + (cur ^ 1) * p.tp_stride, p.tp_codes + (long long)pn * p.tp_stride, p.tp_stride, &bar[cur ^ 1]);
+      const int4 meta = p.tp_meta[pi];
+      if (cur == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
+      else { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
+      const uint8_t *tb = tbuf0 + cur * p.tp_stride;
+      const int L1m1 = meta.x - 1, L2m1 = meta.y - 1;
+      const int lmax = max(meta.x, meta.y);
+
+      uint32_t Hp[K], F[K], S[K];
+      uint32_t hleft_prev, h_out = 0, e_out = 0, best2 = 0;
+      int cap1 = 0, cap2 = 0;
+      int sc1, sc2;
+
+      if (MODE == GLOBAL) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int v = go + ge * (c0 + k);            // H[c][-1]  (global_align.c:148)
+          Hp[k] = p16::pack(v, v);
+          F[k] = p16::pack(v + go, v + go);            // F entering row 0 (global_align.c:146)
+        }
+        { const int v = c0 ? go + ge * (c0 - 1) : 0; hleft_prev = p16::pack(v, v); }
+        int vcol = go;                                 // H[-1][r] of the virtual column, r = s on lane 0
+        const int nsteps = lmax + tstar;
+        for (int s = 0; s < nsteps; ++s) {
+          uint32_t h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
+          uint32_t e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+          if (lane == 0) { h_sh = p16::pack(vcol, vcol); e_sh = p16::pack(vcol + go, vcol + go); vcol += ge; }
+          const int r = s - lane;
+          if (r >= 0 && r < lmax && lane <= tstar) {
+            mm16_load_S<K>(lut + (int)tb[r] * P, lane, S);
+            uint32_t e = e_sh;
+            mm16_row<K, false, false>(hleft_prev, e, Hp, F, S, go2, ge2, best2);
+            hleft_prev = h_sh; e_out = e; h_out = Hp[K - 1];
+            if (lane == tstar && (r == L1m1 || r == L2m1)) {
+              const uint32_t hs = mm16_pick<K>(Hp, kstar);
+              if (r == L1m1) cap1 = p16::lo(hs);
+              if (r == L2m1) cap2 = p16::hi(hs);
+            }
+          }
+        }
+        sc1 = __shfl_sync(ABV_FULL, cap1, tstar);
+        sc2 = __shfl_sync(ABV_FULL, cap2, tstar);
+      } else if (MODE == LOCAL) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) { Hp[k] = 0; F[k] = go2; }   // local_align.c:123-135
+        hleft_prev = 0;
+        const int nsteps = lmax + tstar;
+        for (int s = 0; s < nsteps; ++s) {
+          uint32_t h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
+          uint32_t e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+          if (lane == 0) { h_sh = 0; e_sh = go2; }
+          const int r = s - lane;
+          if (r >= 0 && r < lmax && lane <= tstar) {
+            mm16_load_S<K>(lut + (int)tb[r] * P, lane, S);
+            uint32_t e = e_sh;
+            mm16_row<K, true, true>(hleft_prev, e, Hp, F, S, go2, ge2, best2);
+            hleft_prev = h_sh; e_out = e; h_out = Hp[K - 1];
+          }
+        }
+        best2 = warp_max2(best2);
+        sc1 = p16::lo(best2); sc2 = p16::hi(best2);
+      } else {  // GLOCAL
+        // row 0 has no dependencies: H[c][0] = S(q[c], t[0]), F = H + go (glocal_align.c:128-136)
+        mm16_load_S<K>(lut + (int)tb[0] * P, lane, S);
+#pragma unroll
+        for (int k = 0; k < K; ++k) { Hp[k] = S[k]; F[k] = p16::add(S[k], go2); }
+        hleft_prev = __shfl_up_sync(ABV_FULL, Hp[K - 1], 1);
+        if (lane == 0) hleft_prev = NEG2;
+        best2 = NEG2;
+        const int nsteps = lmax - 1 + tstar;
+        for (int s = 0; s < nsteps; ++s) {
+          uint32_t h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
+          uint32_t e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+          if (lane == 0) { h_sh = NEG2; e_sh = NEG2; }
+          const int r = 1 + s - lane;
+          if (r >= 1 && r < lmax && lane <= tstar) {
+            mm16_load_S<K>(lut + (int)tb[r] * P, lane, S);
+            uint32_t e = e_sh;
+            const bool l1 = (r == L1m1), l2 = (r == L2m1);
+            if (l1 || l2) {
+              const uint32_t mask = (l1 ? 0x0000ffffu : 0u) | (l2 ? 0xffff0000u : 0u);
+              mm16_row_glocal_last<K>(hleft_prev, e, Hp, F, S, go2, ge2, mask, c0, lq, best2);
+            } else {
+              uint32_t dummy = 0;
+              mm16_row<K, false, false>(hleft_prev, e, Hp, F, S, go2, ge2, dummy);
+            }
+            hleft_prev = h_sh; e_out = e; h_out = Hp[K - 1];
+          }
+        }
+        best2 = warp_max2(best2);
+        sc1 = max(0, p16::lo(best2)); sc2 = max(0, p16::hi(best2));   // max starts at 0 (glocal_align.c:115)
+      }
+
+      // fold this pair's two scores into the warp's running best: higher score, then lower index
+      if (sc1 > wbest || (sc1 == wbest && meta.z < widx)) { wbest = sc1; widx = meta.z; }
+      if (meta.w >= 0 && (sc2 > wbest || (sc2 == wbest && meta.w < widx))) { wbest = sc2; widx = meta.w; }
+      if (p.all_scores && lane == 0) {
+        p.all_scores[(long long)qi * p.n_t + meta.z] = sc1;
+        if (meta.w >= 0) p.all_scores[(long long)qi * p.n_t + meta.w] = sc2;
+      }
+    }
+
+    if (lane == 0) { wres[2 * warp] = wbest; wres[2 * warp + 1] = widx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int bs = INT_MIN, bi = INT_MAX;
+      for (int w = 0; w < MM16_WARPS; ++w) {
+        const int s = wres[2 * w], i = wres[2 * w + 1];
+        if (i != INT_MAX && (s > bs || (s == bs && i < bi))) { bs = s; bi = i; }
+      }
+      const bool hit = bi != INT_MAX && bs > p.seed;     // strict '>' against the seed (ambivert.py:482)
+      p.best_score[qi] = hit ? bs : p.seed;
+      p.best_idx[qi] = hit ? bi : -1;
+    }
+    // the next iteration's first __syncthreads orders these reads before wres/lut are rewritten
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Integer-pipe microbenchmark: register-only dependent chains, UNROLL independent chains per thread.
+template <int WHICH>
+__global__ void int_peak_kernel(uint32_t *out, int iters, uint32_t seed) {
+  constexpr int CH = 8;
+  uint32_t a[CH], b[CH], c[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    a[i] = seed + threadIdx.x * 7 + i;
+    b[i] = seed * 3 + i * 5 + (threadIdx.x & 3);
+    c[i] = seed ^ (i * 0x10001u);
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      if (WHICH == 0) { a[i] = a[i] + b[i]; b[i] = b[i] + c[i]; c[i] = c[i] + a[i]; a[i] += 3; }                   // 4 IADD
+      else if (WHICH == 1) { a[i] = __vimax3_s16x2(a[i], b[i], c[i]); b[i] = __vimax3_s16x2(b[i], c[i], a[i]);
+                             c[i] = __vimax3_s16x2(c[i], a[i], b[i] ^ 1); a[i] = __vimax3_s16x2(a[i], b[i], 0x00010001u); }
+      else if (WHICH == 2) { a[i] = __viaddmax_s16x2(a[i], b[i], c[i]); b[i] = __viaddmax_s16x2(b[i], c[i], a[i]);
+                             c[i] = __viaddmax_s16x2(c[i], a[i], b[i]); a[i] = __viaddmax_s16x2(a[i], 0x00010001u, b[i]); }
+      else if (WHICH == 3) { a[i] = __vadd2(a[i], b[i]); b[i] = __vadd2(b[i], c[i]); c[i] = __vadd2(c[i], a[i]); a[i] = __vadd2(a[i], 0x00030003u); }
+      else if (WHICH == 4) {   // the packed DP cell: 2 add + max3 + 2 addmax   (5 ops)
+        uint32_t dd = __vadd2(a[i], c[i]);
+        uint32_t h = __vimax3_s16x2(dd, b[i], c[i]);
+        uint32_t hg = __vadd2(h, 0xfff9fff9u);
+        b[i] = __viaddmax_s16x2(b[i], 0xffffffffu, hg);
+        c[i] = __viaddmax_s16x2(c[i], 0xffffffffu, hg);
+        a[i] = h;
+      } else if (WHICH == 5) { // the 32-bit DP cell: 2 add + max3 + 2 addmax   (5 ops)
+        int dd = (int)a[i] + (int)c[i];
+        int h = __vimax3_s32(dd, (int)b[i], (int)c[i]);
+        int hg = h - 7;
+        b[i] = (uint32_t)__viaddmax_s32((int)b[i], -1, hg);
+        c[i] = (uint32_t)__viaddmax_s32((int)c[i], -1, hg);
+        a[i] = (uint32_t)h;
+      } else if (WHICH == 6) { a[i] = (uint32_t)__vimax3_s32((int)a[i], (int)b[i], (int)c[i]); b[i] = (uint32_t)__vimax3_s32((int)b[i], (int)c[i], (int)a[i]);
+                               c[i] = (uint32_t)__vimax3_s32((int)c[i], (int)a[i], (int)(b[i] ^ 1)); a[i] = (uint32_t)__vimax3_s32((int)a[i], (int)b[i], 65537); }
+      else {                   // packed cell with plain 32-bit adds (biased-operand variant): 5 ops
+        uint32_t dd = a[i] + c[i];
+        uint32_t h = __vimax3_s16x2(dd, b[i], c[i]);
+        uint32_t hg = h + 0xfff8fff9u;
+        b[i] = __viaddmax_s16x2(b[i], 0xffffffffu, hg);
+        c[i] = __viaddmax_s16x2(c[i], 0xffffffffu, hg);
+        a[i] = h;
+      }
+    }
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) r ^= a[i] ^ b[i] ^ c[i];
+  if (r == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = r;   // keeps the chains live
+}
+constexpr int INT_PEAK_OPS[8] = {4, 4, 4, 4, 5, 5, 4, 5};   // lane-ops per chain per iteration
+constexpr int INT_PEAK_CHAINS = 8;
+
+}  // namespace abv

@@ -1,0 +1,215 @@
+/*
+ * include/ambivert_align.h -- C ABI of the B200 (sm_100a) alignment backend for AmBiVErT.
+ *
+ * The shared object built from ambivert_b200/csrc (align_c.b200.so) is a drop-in for the
+ * reference's `align_c` extension (setup.py:44-50; loaded by ambivert/align/align_ctypes.py:30-35,
+ * which takes the first file in the package directory whose name contains "align_c.").
+ *
+ * Part 1 re-exports, symbol for symbol and struct for struct, the interface of the reference's
+ * lib/align/align.h:29-125 (what align_ctypes.py:60-101 binds).  Part 2 is the batched extension
+ * that the pipeline host calls once per stage instead of once per pair.
+ *
+ * Every entry point computes on the GPU.  There is no CPU fallback: without a usable CUDA device
+ * the legacy symbols return NULL and the batched ones return ABV_ERR_NO_DEVICE.
+ *
+ * All sequence arguments are length-delimited, borrowed for the duration of the call and never
+ * modified.  All arithmetic is 32-bit signed integer; results are bit-exact with the reference.
+ */
+#ifndef AMBIVERT_ALIGN_H
+#define AMBIVERT_ALIGN_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* the library is built with -fvisibility=hidden: only this interface is exported */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+/* ============================ Part 1: the reference's own ABI ================================ */
+
+/* lib/align/align.h:29 */
+typedef enum { A_GAP = 0, B_GAP = 1, MATCH = 2 } FragType;
+
+/* lib/align/align.h:31-35  (24 bytes on LP64) */
+typedef struct AlignFrag {
+  struct AlignFrag *next;
+  FragType type;
+  int sa_start, sb_start, hsp_len;
+} AlignFrag;
+
+/* lib/align/align.h:37-41  (16 bytes on LP64) */
+typedef struct Alignment {
+  AlignFrag *align_frag;
+  int frag_count;
+  int score;
+} Alignment;
+
+/* lib/align/align.h:43-46, alignment.c:22-49.  Callee-allocated (malloc) lists; the caller frees
+ * each Alignment exactly once with alignment_free (ambivert.py:113, :154, :176). */
+int align_frag_count(AlignFrag *f);
+void align_frag_free(AlignFrag *f);
+void alignment_free(Alignment *alignment);
+Alignment *alignment_new(AlignFrag *align_frag, int score);
+
+/* The eight aligners.  `*_raw` take sequences already encoded as symbol indices
+ * (0 <= code < alpha_len); the others take bytes and a 256-entry byte->index map
+ * (helpers.h:26-32 to_raw).  score_matrix is alpha_len*alpha_len ints, row = sa symbol.
+ * gap_open/gap_extend are <= 0; a gap of length L costs gap_open + (L-1)*gap_extend.
+ * Return NULL on sa_len<=0, sb_len<=0, NULL pointers, gap_open>0, gap_extend>0, allocation
+ * failure (global_align.c:118-132), where the reference has undefined behaviour
+ * (glocal with sb_len==1, glocal_align.c:138+172; overlap with sa_len==1, align.c:183), or when
+ * no CUDA device is usable.
+ *
+ *   align_raw / align                 ends-free overlap      lib/align/align.c:68-243, :246-274
+ *   local_align_raw / local_align     Smith-Waterman/Gotoh   lib/align/local_align.c:75-244, :247-275
+ *   global_align_raw / global_align   Needleman-Wunsch/Gotoh lib/align/global_align.c:95-228, :231-260
+ *   glocal_align_raw / glocal_align   sb global, sa local    lib/align/glocal_align.c:73-202, :205-234
+ */
+Alignment *align_raw(const unsigned char *sa, int sa_len, const unsigned char *sb, int sb_len,
+                     int alpha_len, int *score_matrix, int gap_open, int gap_extend);
+Alignment *align(const char *seqa, int sa_len, const char *seqb, int sb_len, int alpha_len,
+                 const unsigned char *map, int *score_matrix, int gap_open, int gap_extend);
+Alignment *local_align_raw(const unsigned char *sa, int sa_len, const unsigned char *sb, int sb_len,
+                           int alpha_len, int *score_matrix, int gap_open, int gap_extend);
+Alignment *local_align(const char *seqa, int sa_len, const char *seqb, int sb_len, int alpha_len,
+                       const unsigned char *map, int *score_matrix, int gap_open, int gap_extend);
+Alignment *global_align_raw(const unsigned char *sa, int sa_len, const unsigned char *sb, int sb_len,
+                            int alpha_len, int *score_matrix, int gap_open, int gap_extend);
+Alignment *global_align(const char *seqa, int sa_len, const char *seqb, int sb_len, int alpha_len,
+                        const unsigned char *map, int *score_matrix, int gap_open, int gap_extend);
+Alignment *glocal_align_raw(const unsigned char *sa, int sa_len, const unsigned char *sb, int sb_len,
+                            int alpha_len, int *score_matrix, int gap_open, int gap_extend);
+Alignment *glocal_align(const char *seqa, int sa_len, const char *seqb, int sb_len, int alpha_len,
+                        const unsigned char *map, int *score_matrix, int gap_open, int gap_extend);
+
+/* ============================ Part 2: batched extension ====================================== */
+
+/* alignment modes (the four aligners above) */
+#define ABV_OVERLAP 0
+#define ABV_LOCAL   1
+#define ABV_GLOBAL  2
+#define ABV_GLOCAL  3
+
+/* status codes (0 = success) */
+#define ABV_OK              0
+#define ABV_ERR_ARGS      (-1)  /* what makes the reference return NULL (global_align.c:118-122) */
+#define ABV_ERR_UNDEFINED (-2)  /* a pair on which the reference has undefined behaviour */
+#define ABV_ERR_CUDA      (-3)  /* CUDA runtime error; text in abv_last_error() */
+#define ABV_ERR_NOMEM     (-4)
+#define ABV_ERR_FRAG_CAP  (-5)  /* fragment pool too small; *frag_total holds the needed size */
+#define ABV_ERR_NO_DEVICE (-6)
+
+/* kernel selection for the many-to-many scorer (abv_set_option("path", ...)) */
+#define ABV_PATH_AUTO    0      /* packed 16-bit kernel when provably exact, else the 32-bit one */
+#define ABV_PATH_WF32    1      /* force the general 32-bit wavefront kernel */
+#define ABV_PATH_PACKED  2      /* force the packed kernel; ABV_ERR_ARGS if it is not applicable */
+
+/* one alignment fragment, the payload of AlignFrag without the link (align.h:31-35) */
+typedef struct abv_frag { int type, sa_start, sb_start, hsp_len; } abv_frag;
+
+typedef struct abv_job abv_job;   /* opaque: a many-to-many job whose inputs are resident in HBM */
+
+/* device management / diagnostics */
+int abv_device_count(void);               /* number of usable CUDA devices (0 if none) */
+int abv_set_device(int ordinal);          /* device used by subsequent calls of this process */
+int abv_get_device(void);
+const char *abv_last_error(void);         /* message of the last failing call of this thread */
+const char *abv_version(void);
+int abv_set_option(const char *key, int value);   /* "path": ABV_PATH_*, "warps_per_sm", ... */
+
+/*
+ * Many-to-many best hit: what ambivert.py:461-485 / :487-511 compute with one ctypes call per
+ * (query, target) pair and a Python arg-max.  For every query i the score of `mode` against every
+ * target j (query = sa, target = sb) is computed and reduced with the reference's selection rule
+ * (strict '>' in target order starting from seed_score: the first maximum wins,
+ * ambivert.py:478-485): best_idx[i] = -1 and best_score[i] = seed_score when no target beats the
+ * seed.
+ *
+ * Sequences are concatenated: sequence i is bytes [off[i], off[i+1]) of the buffer.
+ * map256 != NULL: buffers hold characters, encoded on the device through map256 (to_raw);
+ * map256 == NULL: buffers already hold symbol indices (< alpha_len).
+ */
+int abv_best_hits(int mode,
+                  const char *q, const long long *q_off, int n_q,
+                  const char *t, const long long *t_off, int n_t,
+                  int alpha_len, const unsigned char *map256, const int *score_matrix,
+                  int gap_open, int gap_extend, int seed_score,
+                  int *best_score, int *best_idx);
+
+/* Full n_q x n_t score matrix (row-major, scores[i*n_t + j]); same arguments. */
+int abv_score_matrix(int mode,
+                     const char *q, const long long *q_off, int n_q,
+                     const char *t, const long long *t_off, int n_t,
+                     int alpha_len, const unsigned char *map256, const int *score_matrix,
+                     int gap_open, int gap_extend, int *scores);
+
+/*
+ * The same job split into stages, so that a caller can keep the inputs resident in HBM, launch
+ * on its own stream and hand the per-query results to a collective (one NCCL gather of 8 bytes per
+ * query) without a host round trip.
+ *   prepare : validate, upload and pre-process (encode, length-bucket, pair the targets)
+ *   launch  : enqueue the kernels on `stream` (a cudaStream_t; NULL = the library's stream).
+ *             d_best_score/d_best_idx are DEVICE pointers to n_q ints each, or NULL to use the
+ *             job's own result buffers.  Asynchronous.
+ *   fetch   : wait for the last launch and copy the job's own result buffers to the host
+ *   cells   : sum over all pairs of len(query)*len(target)
+ */
+abv_job *abv_best_hits_prepare(int mode,
+                               const char *q, const long long *q_off, int n_q,
+                               const char *t, const long long *t_off, int n_t,
+                               int alpha_len, const unsigned char *map256, const int *score_matrix,
+                               int gap_open, int gap_extend, int seed_score);
+int abv_best_hits_launch(abv_job *job, void *stream, int *d_best_score, int *d_best_idx);
+int abv_best_hits_fetch(abv_job *job, int *best_score, int *best_idx);
+double abv_job_cells(const abv_job *job);
+int abv_job_kernel_launches(const abv_job *job);   /* kernels one abv_best_hits_launch enqueues */
+void abv_job_free(abv_job *job);
+
+/*
+ * One-to-one alignments with traceback: pair k aligns a[k] (sa) with b[k] (sb); what
+ * ambivert.py:75-155 obtains one ctypes call at a time in merge_overlaps (:320-328) and
+ * align_to_reference (:556-573).
+ *   scores[k]      the alignment score (Alignment.score)
+ *   frag_start[k]  index of pair k's first fragment in frags
+ *   frag_count[k]  number of fragments (Alignment.frag_count); fragments are in sequence order
+ *   frags          caller-allocated pool of frag_cap entries; *frag_total receives the number
+ *                  of entries needed (ABV_ERR_FRAG_CAP if that exceeds frag_cap; scores and
+ *                  frag_count are valid even then)
+ */
+int abv_align_pairs(int mode,
+                    const char *a, const long long *a_off,
+                    const char *b, const long long *b_off, int n,
+                    int alpha_len, const unsigned char *map256, const int *score_matrix,
+                    int gap_open, int gap_extend,
+                    int *scores, long long *frag_start, int *frag_count,
+                    abv_frag *frags, long long frag_cap, long long *frag_total);
+
+/*
+ * Timings of the last batched call of this thread, CUDA events on the library's stream:
+ *   out[0] host->device ms, out[1] kernel ms, out[2] device->host ms, out[3] cells,
+ *   out[4] kernel launches, out[5] bytes host->device, out[6] bytes device->host,
+ *   out[7] ms of the dominant DP kernel alone
+ * Returns the number of values written (<= n).
+ */
+int abv_get_timing(double *out, int n);
+
+/*
+ * Integer-pipe microbenchmark, the measured denominator of the GCUPS roofline:
+ * runs a register-only dependent-chain kernel of the instruction mix `which` on every SM and
+ * reports lane-operations per second.
+ *   which 0: IADD3 (32-bit add)            1: VIMNMX3.S16x2        2: VIADDMNMX.S16x2
+ *         3: VIADD.16x2                    4: the packed DP cell mix (2 add + 1 max3 + 2 addmax)
+ *         5: the 32-bit DP cell mix        6: VIMNMX3 (32-bit)     7: 32-bit add + 16x2 max mix
+ */
+int abv_int_peak(int which, int iters, double *lane_ops_per_s, double *sm_clock_mhz);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMBIVERT_ALIGN_H */

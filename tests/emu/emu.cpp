@@ -1,0 +1,239 @@
+// tests/emu/emu.cpp -- TEST INFRASTRUCTURE ONLY.
+// Drives the device cell logic of ambivert_b200/csrc/dp_core.cuh (the very functions the sm_100a
+// kernels call) lane by lane on the CPU, mirroring the warp loops of kernels.cuh, so that the
+// recurrences, tie rules, direction nibbles, traceback walk and shared-memory layouts can be
+// checked against the oracle in the CPU test suite.  Never linked into the product library.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "../../ambivert_b200/csrc/dp_core.cuh"
+
+using namespace abv;
+
+template <int MODE>
+static int emu_wf32_t(const unsigned char *sa, int la, const unsigned char *sb, int lb, int alpha, const int *M,
+                      int go, int ge, int *score_out, FragOut *frags, int cap) {
+  const int nblk = (la + 31) >> 5, steps8 = dir_steps8(lb);
+  std::vector<uint32_t> dir((size_t)dir_words(la, lb), 0xdeadbeefu);
+  std::vector<int> borderH(lb), borderE(lb);
+  EndCell wbest = wf32_initial_candidate<MODE>();
+  int corner = 0;
+  for (int b = 0; b < nblk; ++b) {
+    int F[32] = {0}, hleft_prev[32] = {0}, h_out[32] = {0}, e_out[32] = {0};
+    uint32_t acc[32] = {0};
+    EndCell cand[32];
+    for (int t = 0; t < 32; ++t) cand[t] = wf32_initial_candidate<MODE>();
+    const int lanes_used = std::min(32, la - (b << 5));
+    const int nsteps = lb + lanes_used - 1;
+    for (int s = 0; s < nsteps; ++s) {
+      int h_sh[32], e_sh[32];
+      for (int t = 0; t < 32; ++t) { h_sh[t] = t ? h_out[t - 1] : h_out[0]; e_sh[t] = t ? e_out[t - 1] : e_out[0]; }
+      std::vector<std::pair<int, std::pair<int, int>>> border_writes;
+      for (int t = 0; t < 32; ++t) {
+        const int c = (b << 5) + t, r = s - t;
+        const bool colvalid = c < la;
+        if (t == 0 && s < lb) {
+          if (b == 0) wf32_virtual_column<MODE>(s, go, ge, h_sh[0], e_sh[0]);
+          else { h_sh[0] = borderH[s]; e_sh[0] = borderE[s]; }
+        }
+        unsigned nib = 0;
+        if (r >= 0 && r < lb && colvalid) {
+          const int sub = M[(int)sa[c] * alpha + (int)sb[r]];
+          int h, eo;
+          nib = wf32_cell<MODE>(c, r, la, lb, sub, hleft_prev[t], e_sh[t], F[t], go, ge, h, eo, cand[t]);
+          hleft_prev[t] = h_sh[t];
+          h_out[t] = h; e_out[t] = eo;
+          if (MODE == GLOBAL && c == la - 1 && r == lb - 1) corner = h;
+          if (t == 31 && b + 1 < nblk) border_writes.push_back({r, {h, eo}});
+        }
+        acc[t] |= nib << ((s & 7) * 4);
+        if ((s & 7) == 7 || s == nsteps - 1) { dir[((long long)b * steps8 + (s >> 3)) * 32 + t] = acc[t]; acc[t] = 0; }
+      }
+      for (auto &w : border_writes) { borderH[w.first] = w.second.first; borderE[w.first] = w.second.second; }
+    }
+    EndCell best = cand[0];
+    // same xor-butterfly order as the kernel
+    EndCell cur[32];
+    for (int t = 0; t < 32; ++t) cur[t] = cand[t];
+    for (int off = 16; off > 0; off >>= 1) {
+      EndCell nxt[32];
+      for (int t = 0; t < 32; ++t) { EndCell o = cur[t ^ off]; nxt[t] = end_better(o, cur[t]) ? o : cur[t]; }
+      for (int t = 0; t < 32; ++t) cur[t] = nxt[t];
+    }
+    best = cur[0];
+    if (best.col >= 0 && best.score >= wbest.score) wbest = best;
+  }
+  int score, ec, er;
+  wf32_finish<MODE>(wbest, corner, la, lb, score, ec, er);
+  *score_out = score;
+  DirReader rd; rd.w = dir.data(); rd.steps8 = steps8;
+  std::vector<FragOut> tmp(la + lb + 2);
+  int n = walk_back<MODE>(rd, ec, er, tmp.data(), (int)tmp.size());
+  for (int i = 0; i < n && i < cap; ++i) frags[i] = tmp[n - 1 - i];
+  return n;
+}
+
+// ---- the packed many-to-many kernel, one (query, target pair) ---------------------------------
+template <int K>
+static void load_S(const uint32_t *lut_row, int lane, uint32_t (&S)[K]) {
+  constexpr int V = (K % 4 == 0) ? 4 : 2;
+  for (int i = 0; i < K / V; ++i)
+    for (int j = 0; j < V; ++j) S[i * V + j] = lut_row[(i * 32 + lane) * V + j];
+}
+
+template <int MODE, int K>
+static void emu_mm16_t(const unsigned char *q, int lq, const unsigned char *t1, int l1, const unsigned char *t2, int l2,
+                       int alpha, const int *M, int go, int ge, int *sc1_out, int *sc2_out) {
+  constexpr int V = (K % 4 == 0) ? 4 : 2, P = 32 * K;
+  const int a1 = alpha + 1, ncodes = a1 * a1;
+  std::vector<int> mext((size_t)a1 * a1, 0);
+  for (int x = 0; x < alpha; ++x) for (int y = 0; y < alpha; ++y) mext[x * a1 + y] = M[x * alpha + y];
+  std::vector<unsigned char> qcodes(P);
+  for (int c = 0; c < P; ++c) qcodes[c] = c < lq ? q[c] : (unsigned char)(a1 - 1);
+  std::vector<uint32_t> lut((size_t)ncodes * P);
+  for (int idx = 0; idx < ncodes * P; ++idx) {
+    const int code = idx / P, pos = idx - code * P;
+    const int j = pos % V, it = pos / V, t = it & 31, i = it >> 5;
+    const int c = t * K + i * V + j;
+    const int qa = qcodes[c] * a1;
+    const int a = code / a1, b = code - a * a1;
+    lut[idx] = p16::pack(mext[qa + a], mext[qa + b]);
+  }
+  const int lmax = std::max(l1, l2);
+  std::vector<unsigned char> tb(lmax + 16);
+  for (int r = 0; r < (int)tb.size(); ++r) {
+    const int a = r < l1 ? t1[r] : alpha, b = r < l2 ? t2[r] : alpha;
+    tb[r] = (unsigned char)(a * a1 + b);
+  }
+  const uint32_t go2 = p16::pack(go, go), ge2 = p16::pack(ge, ge), NEG2 = p16::pack(p16::NEG16, p16::NEG16);
+  const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;
+  const int L1m1 = l1 - 1, L2m1 = l2 - 1;
+  uint32_t Hp[32][K], F[32][K], S[K];
+  uint32_t hleft_prev[32], h_out[32] = {0}, e_out[32] = {0}, best2[32] = {0};
+  int cap1 = 0, cap2 = 0, sc1 = 0, sc2 = 0;
+  if (MODE == GLOBAL) {
+    for (int t = 0; t < 32; ++t) {
+      const int c0 = t * K;
+      for (int k = 0; k < K; ++k) { const int v = go + ge * (c0 + k); Hp[t][k] = p16::pack(v, v); F[t][k] = p16::pack(v + go, v + go); }
+      const int v = c0 ? go + ge * (c0 - 1) : 0; hleft_prev[t] = p16::pack(v, v);
+    }
+    int vcol = go;
+    const int nsteps = lmax + tstar;
+    for (int s = 0; s < nsteps; ++s) {
+      uint32_t h_sh[32], e_sh[32];
+      for (int t = 0; t < 32; ++t) { h_sh[t] = t ? h_out[t - 1] : h_out[0]; e_sh[t] = t ? e_out[t - 1] : e_out[0]; }
+      h_sh[0] = p16::pack(vcol, vcol); e_sh[0] = p16::pack(vcol + go, vcol + go); vcol += ge;
+      for (int t = 0; t < 32; ++t) {
+        const int r = s - t;
+        if (r >= 0 && r < lmax && t <= tstar) {
+          load_S<K>(&lut[(size_t)tb[r] * P], t, S);
+          uint32_t e = e_sh[t], dummy = 0;
+          mm16_row<K, false, false>(hleft_prev[t], e, Hp[t], F[t], S, go2, ge2, dummy);
+          hleft_prev[t] = h_sh[t]; e_out[t] = e; h_out[t] = Hp[t][K - 1];
+          if (t == tstar && (r == L1m1 || r == L2m1)) {
+            const uint32_t hs = Hp[t][kstar];
+            if (r == L1m1) cap1 = p16::lo(hs);
+            if (r == L2m1) cap2 = p16::hi(hs);
+          }
+        }
+      }
+    }
+    sc1 = cap1; sc2 = cap2;
+  } else if (MODE == LOCAL) {
+    for (int t = 0; t < 32; ++t) { for (int k = 0; k < K; ++k) { Hp[t][k] = 0; F[t][k] = go2; } hleft_prev[t] = 0; }
+    const int nsteps = lmax + tstar;
+    for (int s = 0; s < nsteps; ++s) {
+      uint32_t h_sh[32], e_sh[32];
+      for (int t = 0; t < 32; ++t) { h_sh[t] = t ? h_out[t - 1] : h_out[0]; e_sh[t] = t ? e_out[t - 1] : e_out[0]; }
+      h_sh[0] = 0; e_sh[0] = go2;
+      for (int t = 0; t < 32; ++t) {
+        const int r = s - t;
+        if (r >= 0 && r < lmax && t <= tstar) {
+          load_S<K>(&lut[(size_t)tb[r] * P], t, S);
+          uint32_t e = e_sh[t];
+          mm16_row<K, true, true>(hleft_prev[t], e, Hp[t], F[t], S, go2, ge2, best2[t]);
+          hleft_prev[t] = h_sh[t]; e_out[t] = e; h_out[t] = Hp[t][K - 1];
+        }
+      }
+    }
+    uint32_t b = 0;
+    for (int t = 0; t < 32; ++t) b = p16::max2(b, best2[t]);
+    sc1 = p16::lo(b); sc2 = p16::hi(b);
+  } else {
+    for (int t = 0; t < 32; ++t) {
+      load_S<K>(&lut[(size_t)tb[0] * P], t, S);
+      for (int k = 0; k < K; ++k) { Hp[t][k] = S[k]; F[t][k] = p16::add(S[k], go2); }
+      best2[t] = NEG2;
+    }
+    for (int t = 31; t > 0; --t) hleft_prev[t] = Hp[t - 1][K - 1];
+    hleft_prev[0] = NEG2;
+    const int nsteps = lmax - 1 + tstar;
+    for (int s = 0; s < nsteps; ++s) {
+      uint32_t h_sh[32], e_sh[32];
+      for (int t = 0; t < 32; ++t) { h_sh[t] = t ? h_out[t - 1] : h_out[0]; e_sh[t] = t ? e_out[t - 1] : e_out[0]; }
+      h_sh[0] = NEG2; e_sh[0] = NEG2;
+      for (int t = 0; t < 32; ++t) {
+        const int r = 1 + s - t;
+        if (r >= 1 && r < lmax && t <= tstar) {
+          load_S<K>(&lut[(size_t)tb[r] * P], t, S);
+          uint32_t e = e_sh[t];
+          const bool a = (r == L1m1), b = (r == L2m1);
+          if (a || b) {
+            const uint32_t mask = (a ? 0x0000ffffu : 0u) | (b ? 0xffff0000u : 0u);
+            mm16_row_glocal_last<K>(hleft_prev[t], e, Hp[t], F[t], S, go2, ge2, mask, t * K, lq, best2[t]);
+          } else {
+            uint32_t dummy = 0;
+            mm16_row<K, false, false>(hleft_prev[t], e, Hp[t], F[t], S, go2, ge2, dummy);
+          }
+          hleft_prev[t] = h_sh[t]; e_out[t] = e; h_out[t] = Hp[t][K - 1];
+        }
+      }
+    }
+    uint32_t b = NEG2;
+    for (int t = 0; t < 32; ++t) b = p16::max2(b, best2[t]);
+    sc1 = std::max(0, p16::lo(b)); sc2 = std::max(0, p16::hi(b));
+  }
+  *sc1_out = sc1; *sc2_out = sc2;
+}
+
+template <int MODE>
+static int emu_mm16_k(int K, const unsigned char *q, int lq, const unsigned char *t1, int l1, const unsigned char *t2, int l2,
+                      int alpha, const int *M, int go, int ge, int *s1, int *s2) {
+  switch (K) {
+    case 2: emu_mm16_t<MODE, 2>(q, lq, t1, l1, t2, l2, alpha, M, go, ge, s1, s2); return 0;
+    case 4: emu_mm16_t<MODE, 4>(q, lq, t1, l1, t2, l2, alpha, M, go, ge, s1, s2); return 0;
+    case 6: emu_mm16_t<MODE, 6>(q, lq, t1, l1, t2, l2, alpha, M, go, ge, s1, s2); return 0;
+    case 8: emu_mm16_t<MODE, 8>(q, lq, t1, l1, t2, l2, alpha, M, go, ge, s1, s2); return 0;
+    case 10: emu_mm16_t<MODE, 10>(q, lq, t1, l1, t2, l2, alpha, M, go, ge, s1, s2); return 0;
+    case 12: emu_mm16_t<MODE, 12>(q, lq, t1, l1, t2, l2, alpha, M, go, ge, s1, s2); return 0;
+    case 16: emu_mm16_t<MODE, 16>(q, lq, t1, l1, t2, l2, alpha, M, go, ge, s1, s2); return 0;
+  }
+  return -1;
+}
+
+extern "C" {
+
+int emu_wf32(int mode, const unsigned char *sa, int la, const unsigned char *sb, int lb, int alpha, const int *M,
+             int go, int ge, int *score, int *frags /* 4 ints each */, int cap) {
+  FragOut *f = reinterpret_cast<FragOut *>(frags);
+  switch (mode) {
+    case OVERLAP: return emu_wf32_t<OVERLAP>(sa, la, sb, lb, alpha, M, go, ge, score, f, cap);
+    case LOCAL: return emu_wf32_t<LOCAL>(sa, la, sb, lb, alpha, M, go, ge, score, f, cap);
+    case GLOBAL: return emu_wf32_t<GLOBAL>(sa, la, sb, lb, alpha, M, go, ge, score, f, cap);
+    case GLOCAL: return emu_wf32_t<GLOCAL>(sa, la, sb, lb, alpha, M, go, ge, score, f, cap);
+  }
+  return -1;
+}
+
+int emu_mm16(int mode, int K, const unsigned char *q, int lq, const unsigned char *t1, int l1,
+             const unsigned char *t2, int l2, int alpha, const int *M, int go, int ge, int *s1, int *s2) {
+  if (32 * K < lq) return -1;
+  switch (mode) {
+    case LOCAL: return emu_mm16_k<LOCAL>(K, q, lq, t1, l1, t2, l2, alpha, M, go, ge, s1, s2);
+    case GLOBAL: return emu_mm16_k<GLOBAL>(K, q, lq, t1, l1, t2, l2, alpha, M, go, ge, s1, s2);
+    case GLOCAL: return emu_mm16_k<GLOCAL>(K, q, lq, t1, l1, t2, l2, alpha, M, go, ge, s1, s2);
+  }
+  return -1;
+}
+}

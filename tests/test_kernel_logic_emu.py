@@ -1,0 +1,148 @@
+"""CPU tests of the DEVICE cell logic (ambivert_b200/csrc/dp_core.cuh).
+
+tests/emu/emu.cpp includes the very header the sm_100a kernels are built from and drives its
+__host__ __device__ functions lane by lane, mirroring the kernels' warp loops.  This pins the
+recurrences, tie rules, direction nibbles, traceback walk and the packed 16-bit arithmetic against the
+oracle without a GPU.  It is a test of the kernel source, not a product path.
+"""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle as O
+from util import as_result, case_scoring, golden
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "emu")
+MODES = [O.OVERLAP, O.LOCAL, O.GLOBAL, O.GLOCAL]
+KS = [2, 4, 6, 8, 10, 12, 16]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(EMU_DIR, "libemu.so")
+    src = os.path.join(EMU_DIR, "emu.cpp")
+    hdr = os.path.join(os.path.dirname(HERE), "ambivert_b200", "csrc", "dp_core.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.emu_wf32.restype = C.c_int
+    lib.emu_mm16.restype = C.c_int
+    return lib
+
+
+def emu_align(lib, mode, sa, sb, alpha, M, go, ge):
+    M = np.ascontiguousarray(M, dtype=np.int32)
+    cap = len(sa) + len(sb) + 2
+    fr = np.zeros(cap * 4, np.int32)
+    sc = C.c_int(0)
+    n = lib.emu_wf32(C.c_int(mode), sa, C.c_int(len(sa)), sb, C.c_int(len(sb)), C.c_int(alpha),
+                     M.ctypes.data_as(C.c_void_p), C.c_int(go), C.c_int(ge), C.byref(sc),
+                     fr.ctypes.data_as(C.c_void_p), C.c_int(cap))
+    assert 0 <= n <= cap
+    return sc.value, [tuple(int(x) for x in fr[4 * i:4 * i + 4]) for i in range(n)]
+
+
+def emu_pair_scores(lib, mode, K, q, t1, t2, alpha, M, go, ge):
+    M = np.ascontiguousarray(M, dtype=np.int32)
+    s1, s2 = C.c_int(0), C.c_int(0)
+    rc = lib.emu_mm16(C.c_int(mode), C.c_int(K), q, C.c_int(len(q)), t1, C.c_int(len(t1)), t2, C.c_int(len(t2)),
+                      C.c_int(alpha), M.ctypes.data_as(C.c_void_p), C.c_int(go), C.c_int(ge), C.byref(s1), C.byref(s2))
+    assert rc == 0
+    return s1.value, s2.value
+
+
+def undefined(mode, sa, sb):
+    return (mode == O.GLOCAL and len(sb) < 2) or (mode == O.OVERLAP and len(sa) < 2)
+
+
+def test_wf32_logic_golden_vectors(emu, oracle_port):
+    g = golden("fuzz_ref_vectors.json")
+    n = 0
+    for c in g["cases"]:
+        alpha, mp, M = case_scoring(c)
+        sa, sb = O.encode(c["a"], mp), O.encode(c["b"], mp)
+        for m in MODES:
+            want = as_result(c["modes"][O.MODE_NAMES[m]])
+            if isinstance(want, int):
+                continue
+            assert emu_align(emu, m, sa, sb, alpha, M, c["go"], c["ge"]) == want, (c["kind"], O.MODE_NAMES[m], c["a"], c["b"])
+            n += 1
+    assert n > 1500
+    for c in golden("kat_reference_tests.json"):
+        for m in MODES:
+            want = as_result(c["modes"][O.MODE_NAMES[m]])
+            if isinstance(want, int):
+                continue
+            got = emu_align(emu, m, O.encode(c["s1"]), O.encode(c["s2"].upper()), 5, O.DNA_SCORE, -7, -1)
+            assert got == want, (c["name"], O.MODE_NAMES[m])
+
+
+def test_wf32_logic_fuzz_vs_oracle(emu, oracle_port):
+    rng = random.Random(4242)
+    chk = oracle_port
+    for it in range(2500):
+        m = rng.choice(MODES)
+        alpha = rng.choice([2, 4, 5, 5, 5, 7, 24])
+        la = rng.choice([1, 2, 3, 31, 32, 33, 64, 65, rng.randint(1, 100), rng.randint(1, 100)])
+        sa = bytes(rng.randrange(alpha) for _ in range(la))
+        if rng.random() < 0.55:
+            sb = bytearray(sa)
+            for _ in range(rng.randint(0, 6)):
+                if len(sb) > 2 and rng.random() < 0.5:
+                    p = rng.randrange(len(sb)); del sb[p:p + rng.randint(1, 6)]
+                else:
+                    p = rng.randrange(len(sb) + 1); sb[p:p] = bytes(rng.randrange(alpha) for _ in range(rng.randint(1, 6)))
+            sb = bytes(sb) or b"\x00"
+        else:
+            sb = bytes(rng.randrange(alpha) for _ in range(rng.choice([1, 2, 3, rng.randint(1, 100)])))
+        if undefined(m, sa, sb):
+            continue
+        if alpha == 5 and rng.random() < 0.6:
+            M = O.DNA_SCORE
+        else:
+            M = np.array([rng.randint(-5, 5) for _ in range(alpha * alpha)], np.int32)
+        go, ge = (-7, -1) if rng.random() < 0.5 else (-rng.randint(0, 9), -rng.randint(0, 3))
+        assert emu_align(emu, m, sa, sb, alpha, M, go, ge) == chk.align_raw(m, sa, sb, alpha, M, go, ge), (it, m, sa, sb, go, ge)
+
+
+def test_packed_logic_vs_oracle(emu, oracle_port):
+    """the packed 16x2 rows (global, local, glocal): two targets per word, every K, ragged lengths"""
+    rng = random.Random(99)
+    chk = oracle_port
+    for it in range(700):
+        m = rng.choice([O.GLOBAL, O.LOCAL, O.GLOCAL])
+        K = rng.choice(KS)
+        lq = rng.randint(max(1, 32 * K - 70), 32 * K) if rng.random() < 0.7 else rng.randint(1, 32 * K)
+        alpha = 5
+        q = bytes(rng.choice([0, 1, 2, 3, 0, 1, 2, 3, 4]) for _ in range(lq))
+
+        def target():
+            if rng.random() < 0.6:
+                t = bytearray(q)
+                for _ in range(rng.randint(0, 5)):
+                    if len(t) > 4 and rng.random() < 0.5:
+                        p = rng.randrange(len(t)); del t[p:p + rng.randint(1, 5)]
+                    else:
+                        p = rng.randrange(len(t) + 1); t[p:p] = bytes(rng.randrange(4) for _ in range(rng.randint(1, 5)))
+                if rng.random() < 0.3:
+                    t = t[rng.randint(0, len(t) // 3):]
+                t = bytes(t)
+            else:
+                t = bytes(rng.randrange(5) for _ in range(rng.randint(2, 300)))
+            return t if len(t) >= 2 else b"\x00\x01"
+        t1 = target()
+        t2 = target() if rng.random() < 0.85 else b""
+        if rng.random() < 0.7:
+            M, go, ge = O.DNA_SCORE, -7, -1
+        else:
+            M = np.array([rng.randint(-4, 4) for _ in range(25)], np.int32)
+            go, ge = -rng.randint(0, 8), -rng.randint(0, 3)
+        s1, s2 = emu_pair_scores(emu, m, K, q, t1, t2, alpha, M, go, ge)
+        assert s1 == chk.align_raw(m, q, t1, alpha, M, go, ge)[0], (it, m, K, lq, len(t1), len(t2))
+        if t2:
+            assert s2 == chk.align_raw(m, q, t2, alpha, M, go, ge)[0], (it, m, K, lq, len(t1), len(t2))
