@@ -1,0 +1,228 @@
+"""numpy-facing wrappers of the batched C ABI (include/ambivert_align.h, part 2).
+
+Sequences go in as lists of `bytes`/`str` (or pre-packed (buffer, offsets) pairs) and results come
+back as numpy arrays.  All computation happens in the CUDA library; a failing call raises
+`AlignError` with the library's message -- nothing here computes an alignment on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .align.align_ctypes import DNA_MAP, DNA_SCORE, align_c as _lib
+
+OVERLAP, LOCAL, GLOBAL, GLOCAL = 0, 1, 2, 3
+MODE_BY_NAME = {"overlap": OVERLAP, "local": LOCAL, "global": GLOBAL, "glocal": GLOCAL}
+A_GAP, B_GAP, MATCH = 0, 1, 2
+OK, ERR_ARGS, ERR_UNDEFINED, ERR_CUDA, ERR_NOMEM, ERR_FRAG_CAP, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5, -6
+PATH_AUTO, PATH_WF32, PATH_PACKED = 0, 1, 2
+
+# scoring used at every pipeline call site (ambivert.py:86-89, :127-130, :170-173)
+GAP_OPEN, GAP_EXTEND = -7, -1
+SEED_GLOBAL = -1000000   # ambivert.py:478
+SEED_LOCAL = 0           # ambivert.py:504
+
+_vp = C.c_void_p
+_lib.abv_device_count.restype = C.c_int
+_lib.abv_set_device.argtypes = [C.c_int]
+_lib.abv_get_device.restype = C.c_int
+_lib.abv_last_error.restype = C.c_char_p
+_lib.abv_version.restype = C.c_char_p
+_lib.abv_set_option.argtypes = [C.c_char_p, C.c_int]
+_MM = [C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int]
+_lib.abv_best_hits.argtypes = _MM + [C.c_int, _vp, _vp]
+_lib.abv_score_matrix.argtypes = _MM + [_vp]
+_lib.abv_best_hits_prepare.argtypes = _MM + [C.c_int]
+_lib.abv_best_hits_prepare.restype = _vp
+_lib.abv_best_hits_launch.argtypes = [_vp, _vp, _vp, _vp]
+_lib.abv_best_hits_fetch.argtypes = [_vp, _vp, _vp]
+_lib.abv_job_cells.argtypes = [_vp]
+_lib.abv_job_cells.restype = C.c_double
+_lib.abv_job_kernel_launches.argtypes = [_vp]
+_lib.abv_job_free.argtypes = [_vp]
+_lib.abv_job_free.restype = None
+_lib.abv_align_pairs.argtypes = [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int,
+                                 _vp, _vp, _vp, _vp, C.c_longlong, _vp]
+_lib.abv_get_timing.argtypes = [_vp, C.c_int]
+_lib.abv_int_peak.argtypes = [C.c_int, C.c_int, _vp, _vp]
+
+
+class AlignError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("ambivert_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+def _check(rc):
+    if rc != OK:
+        raise AlignError(rc, (_lib.abv_last_error() or b"").decode("utf-8", "replace"))
+
+
+def device_count():
+    return int(_lib.abv_device_count())
+
+
+def set_device(ordinal):
+    _check(_lib.abv_set_device(int(ordinal)))
+
+
+def version():
+    return _lib.abv_version().decode()
+
+
+def set_option(key, value):
+    _check(_lib.abv_set_option(key.encode(), int(value)))
+
+
+def pack(seqs):
+    """list of bytes/str -> (uint8 buffer, int64 offsets[n+1]); (buffer, offsets) passes through"""
+    if isinstance(seqs, tuple) and len(seqs) == 2 and isinstance(seqs[1], np.ndarray):
+        buf, off = seqs
+        return np.ascontiguousarray(buf, dtype=np.uint8), np.ascontiguousarray(off, dtype=np.int64)
+    bs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    if bs:
+        np.cumsum([len(b) for b in bs], out=off[1:])
+    buf = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs else np.zeros(0, np.uint8)
+    return buf, off
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _scoring(alpha_len, map256, matrix):
+    if map256 is None:
+        mp = None
+    else:
+        mp = np.ascontiguousarray(np.frombuffer(bytes(bytearray(map256)), dtype=np.uint8)) if not isinstance(map256, np.ndarray) \
+            else np.ascontiguousarray(map256, dtype=np.uint8)
+        assert mp.size == 256
+    m = np.ascontiguousarray(np.array(list(matrix), dtype=np.int32) if not isinstance(matrix, np.ndarray) else matrix, dtype=np.int32)
+    assert m.size == alpha_len * alpha_len, "score matrix must be alpha_len x alpha_len"
+    return mp, m
+
+
+def timing():
+    """timings of the last batched call: dict(h2d_ms, kernel_ms, d2h_ms, cells, launches, h2d_bytes, d2h_bytes, dp_ms)"""
+    out = np.zeros(8, np.float64)
+    _lib.abv_get_timing(out.ctypes.data_as(_vp), 8)
+    keys = ["h2d_ms", "kernel_ms", "d2h_ms", "cells", "launches", "h2d_bytes", "d2h_bytes", "dp_ms"]
+    return dict(zip(keys, out.tolist()))
+
+
+def best_hits(queries, targets, mode=GLOBAL, seed=SEED_GLOBAL, alpha_len=DNA_MAP[0], map256=DNA_MAP[1],
+              matrix=DNA_SCORE, gap_open=GAP_OPEN, gap_extend=GAP_EXTEND):
+    """For every query the best-scoring target under the reference's selection rule
+    (ambivert.py:478-485): -> (best_score int32[n_q], best_idx int32[n_q]); idx -1 = nothing beat `seed`."""
+    q, qo = pack(queries)
+    t, to = pack(targets)
+    mp, m = _scoring(alpha_len, map256, matrix)
+    n_q, n_t = len(qo) - 1, len(to) - 1
+    bs = np.empty(n_q, np.int32)
+    bi = np.empty(n_q, np.int32)
+    _check(_lib.abv_best_hits(mode, _ptr(q), _ptr(qo), n_q, _ptr(t), _ptr(to), n_t, alpha_len,
+                              _ptr(mp), _ptr(m), gap_open, gap_extend, seed, _ptr(bs), _ptr(bi)))
+    return bs, bi
+
+
+def score_matrix(queries, targets, mode=GLOBAL, alpha_len=DNA_MAP[0], map256=DNA_MAP[1], matrix=DNA_SCORE,
+                 gap_open=GAP_OPEN, gap_extend=GAP_EXTEND):
+    """all n_q x n_t scores (int32)"""
+    q, qo = pack(queries)
+    t, to = pack(targets)
+    mp, m = _scoring(alpha_len, map256, matrix)
+    n_q, n_t = len(qo) - 1, len(to) - 1
+    out = np.empty((n_q, n_t), np.int32)
+    _check(_lib.abv_score_matrix(mode, _ptr(q), _ptr(qo), n_q, _ptr(t), _ptr(to), n_t, alpha_len,
+                                 _ptr(mp), _ptr(m), gap_open, gap_extend, _ptr(out)))
+    return out
+
+
+class BestHitsJob:
+    """A many-to-many job whose inputs stay resident in HBM (abv_best_hits_prepare/launch/fetch)."""
+
+    def __init__(self, queries, targets, mode=GLOBAL, seed=SEED_GLOBAL, alpha_len=DNA_MAP[0], map256=DNA_MAP[1],
+                 matrix=DNA_SCORE, gap_open=GAP_OPEN, gap_extend=GAP_EXTEND):
+        q, qo = pack(queries)
+        t, to = pack(targets)
+        mp, m = _scoring(alpha_len, map256, matrix)
+        self.n_q, self.n_t = len(qo) - 1, len(to) - 1
+        self._h = _lib.abv_best_hits_prepare(mode, _ptr(q), _ptr(qo), self.n_q, _ptr(t), _ptr(to), self.n_t, alpha_len,
+                                             _ptr(mp), _ptr(m), gap_open, gap_extend, seed)
+        if not self._h:
+            raise AlignError(ERR_ARGS, (_lib.abv_last_error() or b"").decode("utf-8", "replace"))
+        self.cells = float(_lib.abv_job_cells(self._h))
+
+    def launch(self, stream=None, d_best_score=None, d_best_idx=None):
+        """enqueue the kernels; stream = raw cudaStream_t (int) or None; outputs = device pointers (int) or None"""
+        _check(_lib.abv_best_hits_launch(self._h, _vp(stream) if stream else None,
+                                         _vp(d_best_score) if d_best_score else None,
+                                         _vp(d_best_idx) if d_best_idx else None))
+
+    def kernel_launches(self):
+        return int(_lib.abv_job_kernel_launches(self._h))
+
+    def fetch(self):
+        bs = np.empty(self.n_q, np.int32)
+        bi = np.empty(self.n_q, np.int32)
+        _check(_lib.abv_best_hits_fetch(self._h, _ptr(bs), _ptr(bi)))
+        return bs, bi
+
+    def close(self):
+        if self._h:
+            _lib.abv_job_free(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def align_pairs(seqs_a, seqs_b, mode, alpha_len=DNA_MAP[0], map256=DNA_MAP[1], matrix=DNA_SCORE,
+                gap_open=GAP_OPEN, gap_extend=GAP_EXTEND, frag_cap=None):
+    """One-to-one alignments with traceback.
+    -> (scores int32[n], frag_start int64[n], frag_count int32[n], frags int32[total, 4])
+    frags rows are (type, sa_start, sb_start, hsp_len); pair k owns rows frag_start[k] .. +frag_count[k]."""
+    a, ao = pack(seqs_a)
+    b, bo = pack(seqs_b)
+    n = len(ao) - 1
+    assert len(bo) - 1 == n, "align_pairs needs as many b sequences as a sequences"
+    mp, m = _scoring(alpha_len, map256, matrix)
+    scores = np.empty(n, np.int32)
+    start = np.empty(n, np.int64)
+    count = np.empty(n, np.int32)
+    cap = int(frag_cap) if frag_cap is not None else max(1024, 24 * n)
+    for _ in range(2):
+        frags = np.empty((cap, 4), np.int32)
+        total = C.c_longlong(0)
+        rc = _lib.abv_align_pairs(mode, _ptr(a), _ptr(ao), _ptr(b), _ptr(bo), n, alpha_len,
+                                  _ptr(mp), _ptr(m), gap_open, gap_extend,
+                                  _ptr(scores), _ptr(start), _ptr(count), _ptr(frags), cap, C.byref(total))
+        if rc == ERR_FRAG_CAP and frag_cap is None:
+            cap = int(total.value)      # retry once with the exact size the library reported
+            continue
+        _check(rc)
+        return scores, start, count, frags[:total.value]
+    _check(rc)
+
+
+def fragments(k, start, count, frags):
+    """pair k's fragment list as tuples, the shape the oracle returns"""
+    s = int(start[k])
+    return [tuple(int(x) for x in frags[s + i]) for i in range(int(count[k]))]
+
+
+def int_peak(which, iters=20000):
+    """integer-pipe microbenchmark -> (lane-ops per second, nominal SM clock MHz)"""
+    ops = C.c_double(0)
+    mhz = C.c_double(0)
+    _check(_lib.abv_int_peak(int(which), int(iters), C.byref(ops), C.byref(mhz)))
+    return ops.value, mhz.value

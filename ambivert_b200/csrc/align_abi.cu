@@ -259,15 +259,21 @@ bool packed_exact(int mode, int P, int max_lt, int maxabs) {
   return bound <= (mode == ABV_GLOCAL ? p16::P16_LIMIT : 30000);
 }
 
-int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int n_q,
-                const char *t, const long long *t_off, int n_t, const Scoring &sc, int seed, bool all_scores) {
-  int rc;
+int mm_validate(int mode, const char *q, const long long *q_off, int n_q, const char *t, const long long *t_off, int n_t,
+                const Scoring &sc, int &max_lq, int &max_lt) {
+  int rc, min_lq, min_lt;
   if ((rc = check_scoring(sc))) return rc;
-  int max_lq, min_lq, max_lt, min_lt;
+  if (mode < 0 || mode > 3) return fail(ABV_ERR_ARGS, "unknown mode %d", mode);
   if ((rc = check_seqs(q, q_off, n_q, "query", max_lq, min_lq))) return rc;
   if ((rc = check_seqs(t, t_off, n_t, "target", max_lt, min_lt))) return rc;
   if (n_q > 0 && n_t > 0 && (rc = check_mode_lengths(mode, min_lq, min_lt))) return rc;
-  if (mode < 0 || mode > 3) return fail(ABV_ERR_ARGS, "unknown mode %d", mode);
+  return ABV_OK;
+}
+
+int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int n_q,
+                const char *t, const long long *t_off, int n_t, const Scoring &sc, int seed, bool all_scores) {
+  int rc, max_lq, max_lt;
+  if ((rc = mm_validate(mode, q, q_off, n_q, t, t_off, n_t, sc, max_lq, max_lt))) return rc;
   if ((rc = ctx_init())) return rc;
   cudaStream_t st = g.stream;
   J.mode = mode; J.n_q = n_q; J.n_t = n_t; J.seed = seed; J.alpha = sc.alpha; J.go = sc.go; J.ge = sc.ge;
@@ -535,10 +541,11 @@ static int best_hits_impl(int mode, const char *q, const long long *q_off, int n
                           int *best_score, int *best_idx, int *scores) {
   std::lock_guard<std::recursive_mutex> lk(g.mu);
   int rc;
+  Scoring sc{alpha_len, gap_open, gap_extend, map256, score_matrix};
+  { int a, b; if ((rc = mm_validate(mode, q, q_off, n_q, t, t_off, n_t, sc, a, b))) return rc; }
   if ((rc = ctx_init())) return rc;
   for (double &v : t_timing) v = 0;
   abv_job J;
-  Scoring sc{alpha_len, gap_open, gap_extend, map256, score_matrix};
   CU(cudaEventRecord(g.ev[0], g.stream));
   if ((rc = job_prepare(J, mode, q, q_off, n_q, t, t_off, n_t, sc, seed_score, scores != nullptr))) return rc;
   CU(cudaEventRecord(g.ev[1], g.stream));
