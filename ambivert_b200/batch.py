@@ -38,6 +38,7 @@ _lib.abv_best_hits_fetch.argtypes = [_vp, _vp, _vp]
 _lib.abv_job_cells.argtypes = [_vp]
 _lib.abv_job_cells.restype = C.c_double
 _lib.abv_job_kernel_launches.argtypes = [_vp]
+_lib.abv_job_profile.argtypes = [_vp, _vp, C.c_int]
 _lib.abv_job_free.argtypes = [_vp]
 _lib.abv_job_free.restype = None
 _lib.abv_align_pairs.argtypes = [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int,
@@ -161,6 +162,12 @@ class BestHitsJob:
 
     def kernel_launches(self):
         return int(_lib.abv_job_kernel_launches(self._h))
+
+    def profile(self):
+        """per packed-kernel launch of the last launch(): list of dict(K, queries, cells, ms)"""
+        out = np.zeros((16, 4), np.float64)
+        n = _lib.abv_job_profile(self._h, out.ctypes.data_as(_vp), 16)
+        return [dict(K=int(r[0]), queries=int(r[1]), cells=float(r[2]), ms=float(r[3])) for r in out[:n]]
 
     def fetch(self):
         bs = np.empty(self.n_q, np.int32)

@@ -243,8 +243,9 @@ struct abv_job {
   DevMem q_codes, q_off, t_codes, t_off, map, matrix, matrix_ext, tp_codes, tp_meta, lists, counters;
   DevMem best_score, best_idx, all_scores, chunk_scores, border;
   int tp_stride = 0, n_pairs = 0, a1 = 0, max_lt = 0, max_lq = 0;
-  struct Bucket { int K, n, offset; };
+  struct Bucket { int K, n, offset; double cells; cudaEvent_t e0, e1; };
   std::vector<Bucket> buckets;     // packed-kernel launches (one per K class), lists at `offset`
+  ~abv_job() { for (auto &b : buckets) { if (b.e0) cudaEventDestroy(b.e0); if (b.e1) cudaEventDestroy(b.e1); } }
   int n_wf32 = 0, wf32_offset = 0; // queries served by the 32-bit kernel, list at `wf32_offset`
   int n_counters = 0;
   int launches_per_run = 0;
@@ -325,7 +326,12 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   std::vector<int> flat;
   for (int k = 0; k < MM16_NK; ++k)
     if (!lists[k].empty()) {
-      J.buckets.push_back({MM16_KS[k], (int)lists[k].size(), (int)flat.size()});
+      double qlen = 0;
+      for (int i : lists[k]) qlen += (double)(q_off[i + 1] - q_off[i]);
+      abv_job::Bucket b{MM16_KS[k], (int)lists[k].size(), (int)flat.size(), qlen * (double)(t_off[n_t] - t_off[0]), nullptr, nullptr};
+      CU(cudaEventCreate(&b.e0));
+      CU(cudaEventCreate(&b.e1));
+      J.buckets.push_back(b);
       flat.insert(flat.end(), lists[k].begin(), lists[k].end());
     }
   J.wf32_offset = (int)flat.size();
@@ -428,7 +434,9 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
     p.best_score = d_best_score; p.best_idx = d_best_idx;
     p.all_scores = J.want_all_scores ? J.all_scores.as<int>() : nullptr; p.n_t = J.n_t;
     p.q_counter = reinterpret_cast<unsigned int *>(J.counters.as<unsigned long long>() + ci++);
+    CU(cudaEventRecord(b.e0, st));
     if ((rc = mm16_launch(J.mode, b.K, st, p, launched))) return rc;
+    CU(cudaEventRecord(b.e1, st));
   }
   if (J.n_wf32 > 0) {
     const long long max_chunk_scores = 32ll << 20;
@@ -528,6 +536,20 @@ int abv_best_hits_fetch(abv_job *job, int *best_score, int *best_idx) {
 }
 
 double abv_job_cells(const abv_job *job) { return job ? job->cells : 0; }
+
+int abv_job_profile(abv_job *job, double *out, int max_rows) {
+  if (!job || !out) return 0;
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  int n = 0;
+  for (const auto &b : job->buckets) {
+    if (n >= max_rows) break;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, b.e0, b.e1) != cudaSuccess) { cudaGetLastError(); ms = -1; }
+    out[4 * n] = b.K; out[4 * n + 1] = b.n; out[4 * n + 2] = b.cells; out[4 * n + 3] = ms;
+    ++n;
+  }
+  return n;
+}
 int abv_job_kernel_launches(const abv_job *job) { return job ? job->launches_per_run : 0; }
 void abv_job_free(abv_job *job) {
   std::lock_guard<std::recursive_mutex> lk(g.mu);

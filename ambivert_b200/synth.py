@@ -1,0 +1,97 @@
+"""Synthetic amplicon data of the shapes BASELINE.json names.  Seeded and
+deterministic, so every rank of a multi-GPU run builds the same set and takes its own shard."""
+import numpy as np
+
+_ACGT = np.frombuffer(b"ACGT", np.uint8)
+_IUPAC = b"NRYSWKM"
+_COMP = bytes.maketrans(b"ACGTNacgtn", b"TGCANtgcan")
+
+
+def reverse_complement(seq):
+    return seq.translate(_COMP)[::-1]
+
+
+def _random_dna(rng, n):
+    return _ACGT[rng.integers(0, 4, int(n))].tobytes()
+
+
+def panel_targets(n_targets=2000, lo=200, hi=260, probe=27, seed=0xC4):
+    """manifest-style targets: upper-case core with lower-case primer flanks, as
+    truseq_manifest.make_sequences(with_probes, softmask_probes) produces (truseq_manifest.py:148-152)"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for L in rng.integers(lo, hi + 1, n_targets):
+        s = _random_dna(rng, L)
+        out.append(s[:probe].lower() + s[probe:len(s) - probe] + s[len(s) - probe:].lower())
+    return out
+
+
+def panel_queries(targets, n_queries=100000, seed=0xC4 + 1, snv_mean=1.5, p_indel=0.10, p_iupac=0.005, p_unrelated=0.01):
+    """unique amplicons: mutated copies of uniformly chosen targets (upper-cased), k~Poisson SNVs, an
+    occasional 1-5 bp indel, a rare IUPAC/N base, 1 % unrelated sequences; de-duplicated.
+    -> (queries, source target index or -1)"""
+    rng = np.random.default_rng(seed)
+    up = [t.upper() for t in targets]
+    seen = set()
+    queries, source = [], []
+    while len(queries) < n_queries:
+        m = n_queries - len(queries)
+        src = rng.integers(0, len(up), m)
+        nsnv = rng.poisson(snv_mean, m)
+        indel = rng.random(m) < p_indel
+        iupac = rng.random(m) < p_iupac
+        unrelated = rng.random(m) < p_unrelated
+        for i in range(m):
+            if unrelated[i]:
+                s = bytearray(_random_dna(rng, len(up[src[i]])))
+                origin = -1
+            else:
+                s = bytearray(up[src[i]])
+                origin = int(src[i])
+                for p in rng.integers(0, len(s), int(nsnv[i])):
+                    s[p] = b"ACGT"[int(rng.integers(0, 4))]
+                if indel[i]:
+                    p = int(rng.integers(1, len(s) - 6))
+                    n = int(rng.integers(1, 6))
+                    if rng.random() < 0.5:
+                        del s[p:p + n]
+                    else:
+                        s[p:p] = _random_dna(rng, n)
+                if iupac[i]:
+                    s[int(rng.integers(0, len(s)))] = _IUPAC[int(rng.integers(0, len(_IUPAC)))]
+            b = bytes(s)
+            if b in seen:
+                continue
+            seen.add(b)
+            queries.append(b)
+            source.append(origin)
+    return queries, np.asarray(source, np.int64)
+
+
+def fasta_targets(n_targets=10000, length=250, seed=0xD5):
+    rng = np.random.default_rng(seed)
+    return [_random_dna(rng, length) for _ in range(n_targets)]
+
+
+def read_pairs(n_pairs=1000000, read_len=150, seed=0xA3B1, p_sub=0.005, p_n=0.001, p_unrelated=0.02):
+    """forward / reverse read pairs of amplicons 170..280 bp (overlap 20..130 bp): F = first 150 bases,
+    R = reverse complement of the last 150; per-base substitutions and N calls; 2 % of pairs carry an
+    unrelated reverse read (the `unmergable` path, ambivert.py:324-325).  -> (fwd, rev) as sequenced"""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(read_len + 20, 2 * read_len - 19, n_pairs)
+    unrelated = rng.random(n_pairs) < p_unrelated
+    fwd, rev = [], []
+    for i in range(n_pairs):
+        amp = _ACGT[rng.integers(0, 4, int(lens[i]))]
+        f = amp[:read_len].copy()
+        r = (_ACGT[rng.integers(0, 4, read_len)] if unrelated[i] else amp[-read_len:].copy())
+        for a in (f, r):
+            nsub = rng.binomial(read_len, p_sub)
+            if nsub:
+                a[rng.integers(0, read_len, nsub)] = _ACGT[rng.integers(0, 4, nsub)]
+            nn = rng.binomial(read_len, p_n)
+            if nn:
+                a[rng.integers(0, read_len, nn)] = ord("N")
+        fwd.append(f.tobytes())
+        rev.append(reverse_complement(r.tobytes()))
+    return fwd, rev

@@ -165,6 +165,10 @@ int abv_best_hits_launch(abv_job *job, void *stream, int *d_best_score, int *d_b
 int abv_best_hits_fetch(abv_job *job, int *best_score, int *best_idx);
 double abv_job_cells(const abv_job *job);
 int abv_job_kernel_launches(const abv_job *job);   /* kernels one abv_best_hits_launch enqueues */
+/* Per packed-kernel launch of the LAST abv_best_hits_launch (call after it completed): rows of
+ * 4 doubles {K = packed columns per lane, queries, cells, milliseconds by CUDA events on the
+ * launch stream}.  Returns the number of rows written (<= max_rows). */
+int abv_job_profile(abv_job *job, double *out, int max_rows);
 void abv_job_free(abv_job *job);
 
 /*
