@@ -1,0 +1,246 @@
+"""Host side of the hot path: the three pipeline stages of the reference's AmpliconData that call
+the aligner, re-hosted so that each stage makes ONE batched call into the CUDA library instead of one
+ctypes call per pair.
+
+  merge_overlaps      ambivert/ambivert.py:301-331   local alignment + traceback of every unique F/R pair
+  match_to_reference  ambivert/ambivert.py:365-541   every merged amplicon x every target -> hash table
+  align_to_reference  ambivert/ambivert.py:543-574   final global/local alignment to the chosen target
+
+The functions take any object with the reference AmpliconData's attributes (`data`, `merged`,
+`unmergable`, `reference`, `reference_sequences`, `aligned`, `location`, `potential_variants`,
+`threshold`), so they can be bound onto the reference class
+(`ambivert.ambivert.AmpliconData.match_to_reference = ambivert_b200.host.match_to_reference`) or used
+through the small `AmpliconData` below.  Names, argument meaning, result containers, iteration order
+and error behaviour follow the reference, including its quirks.
+"""
+import hashlib
+import logging
+import pickle
+import warnings
+from collections import defaultdict
+
+from . import batch as B
+
+_COMP = {ord(a): b for a, b in zip("acgtACGT-.nNUMRWSYKVHDBumrwsykvhdb", "tgcaTGCA-.nNAKYWSRMBDHVakywsrmbdhv")}
+_IUPAC = {"AG": "R", "CT": "Y", "CG": "S", "AT": "W", "GT": "K", "AC": "M",
+          "CGT": "B", "AGT": "D", "ACT": "H", "ACG": "V", "ACGT": "N"}
+
+
+class _CompTable(dict):
+    def __missing__(self, key):
+        return "n"
+
+
+_COMP_TABLE = _CompTable(_COMP)
+
+
+def complement(seq):
+    """case-sensitive IUPAC complement; unknown characters become 'n' (sequence_utilities.py:96-119)"""
+    return seq.translate(_COMP_TABLE)
+
+
+def reverse_complement(seq):
+    return complement(seq)[::-1]
+
+
+def encode_ambiguous(bases):
+    """IUPAC symbol of a set of bases; N if any is N (sequence_utilities.py:130-156)"""
+    s = "".join(sorted(set(b.upper() for b in bases)))
+    if len(s) == 1:
+        return s
+    if "N" in s:
+        return "N"
+    return _IUPAC[s]          # KeyError for non-ACGT input, as in the reference
+
+
+def flatten_paired_alignment(seq1, seq2, gap="-"):
+    """merge two gapped rows: a gap takes the other base, a disagreement its IUPAC code
+    (sequence_utilities.py:158-169)"""
+    out = []
+    for a, b in zip(seq1, seq2):
+        if a == gap:
+            out.append(b)
+        elif b == gap or a == b:
+            out.append(a)
+        else:
+            out.append(encode_ambiguous((a, b)))
+    return "".join(out)
+
+
+def gapped_strings(seq1, seq2, frags):
+    """fragment list -> the two gapped rows, as ambivert.py:95-111 / :136-152 build them
+    (slices of seq2 keep seq2's own case)"""
+    r1, r2 = [], []
+    for typ, sa, sb, n in frags:
+        if typ == B.MATCH:
+            r1.append(seq1[sa:sa + n]); r2.append(seq2[sb:sb + n])
+        elif typ == B.A_GAP:
+            r1.append("-" * n); r2.append(seq2[sb:sb + n])
+        elif typ == B.B_GAP:
+            r1.append(seq1[sa:sa + n]); r2.append("-" * n)
+    a, b = "".join(r1), "".join(r2)
+    assert len(a) == len(b)
+    return a, b
+
+
+def _ascii(seqs):
+    return [bytes(s, "ascii") for s in seqs]       # same conversion (and same UnicodeEncodeError) as ambivert.py:84
+
+
+def batched_pairwise(seqs1, seqs2, local):
+    """smith_waterman (local=True, ambivert.py:75-114) / needleman_wunsch (ambivert.py:116-155) for a
+    whole batch: -> list of (align_seq1, align_seq2, start_seq1, start_seq2)."""
+    for s1, s2 in zip(seqs1, seqs2):
+        if "-" in s1 or "-" in s2:
+            raise RuntimeError("Aligning Sequences with gaps is not supported", s1, s2)
+    try:
+        sc, st, cn, fr = B.align_pairs(_ascii(seqs1), _ascii(s.upper() for s in seqs2), B.LOCAL if local else B.GLOBAL)
+    except B.AlignError as e:
+        if e.code in (B.ERR_ARGS, B.ERR_UNDEFINED):
+            raise ValueError("NULL pointer access") from e     # what ctypes raises on the reference's NULL result
+        raise
+    out = []
+    for k, (s1, s2) in enumerate(zip(seqs1, seqs2)):
+        frags = B.fragments(k, st, cn, fr)
+        if local:
+            if not frags:
+                raise ValueError("NULL pointer access")        # alignment.contents.align_frag.contents on an empty list
+            start1, start2 = frags[0][1], frags[0][2]
+        else:
+            start1 = start2 = 0
+        a1, a2 = gapped_strings(s1, s2, frags)
+        out.append((a1, a2, start1, start2))
+    return out
+
+
+def smith_waterman(seq1, seq2):
+    return batched_pairwise([seq1], [seq2], True)[0]
+
+
+def needleman_wunsch(seq1, seq2):
+    return batched_pairwise([seq1], [seq2], False)[0]
+
+
+def get_above_threshold(self, threshold=1):
+    return [x for x in self.data if len(self.data[x]) > threshold]
+
+
+def merge_overlaps(self, threshold=0, minimum_overlap=10):
+    """ambivert.py:301-331 with one batched local alignment for all unique pairs above threshold"""
+    self.threshold = threshold
+    keys = get_above_threshold(self, threshold)
+    logging.info("Merging overlaps for {0} unique pairs".format(len(keys)))
+    fwds = [self.data[k][0][0][1] for k in keys]
+    revs = [reverse_complement(self.data[k][0][1][1]) for k in keys]
+    for key, fwd, rev, (fa, ra, fstart, rstart) in zip(keys, fwds, revs, batched_pairwise(fwds, revs, True)):
+        if len(fa) < minimum_overlap:
+            self.unmergable.append(key)
+        else:
+            self.merged[key] = fwd[:fstart] + flatten_paired_alignment(fa, ra) + rev[rstart + len(ra.replace("-", "")):]
+    logging.info("\nSuccessfully merged {0} reads. {1} reads could not be merged".format(len(self.merged), len(self.unmergable)))
+
+
+def match_to_reference(self, min_score=0.1, trim_primers=0, global_align=True, show_progress=False, threads=1):
+    """ambivert.py:365-541: the exact-match hash table.  Every merged amplicon that is not already
+    in the table is scored against every reference target (global alignment in both settings of
+    `global_align` -- the reference's calculate_local_score calls global_align too, ambivert.py:190; the
+    settings differ by the arg-max seed, 0 vs -1000000) and keeps the first best-scoring target if its
+    score exceeds min_score.  `threads` is accepted for signature compatibility; the GPU does the work."""
+    keys = [k for k in self.merged if k not in self.reference]
+    ref_keys = list(self.reference_sequences)
+    if not keys:
+        return
+    seqs = [self.merged[k][trim_primers:-trim_primers] if trim_primers else self.merged[k] for k in keys]
+    targets = [self.reference_sequences[x].upper() for x in ref_keys]
+    seed = B.SEED_GLOBAL if global_align else B.SEED_LOCAL
+    logging.info("Matching read bins to references - {0} amplicons x {1} targets on the GPU".format(len(keys), len(ref_keys)))
+    try:
+        best_score, best_idx = B.best_hits(_ascii(seqs), _ascii(targets), B.GLOBAL, seed)
+    except B.AlignError as e:
+        if e.code in (B.ERR_ARGS, B.ERR_UNDEFINED):
+            raise ValueError("NULL pointer access") from e
+        raise
+    for key, score, idx in zip(keys, best_score.tolist(), best_idx.tolist()):
+        best_hit = ref_keys[idx] if idx >= 0 else ""
+        if best_hit and score > min_score:
+            self.reference[key] = best_hit
+        else:
+            logging.warning("\nWARNING NO MATCH FOR {0}\n Use ambivert --fastqamplicon {1} to retrieve reads from this amplicon".format(
+                self.merged[key], key))
+
+
+def align_to_reference(self, global_align=True):
+    """ambivert.py:543-574 with one batched alignment (+ traceback) for all matched amplicons"""
+    keys = [k for k in self.reference if k in self.merged]
+    queries, refs = [], []
+    for k in keys:
+        ref_key = self.reference[k]
+        if ref_key[-1] == "-":          # minus-strand probe: both sequences to the plus strand
+            queries.append(reverse_complement(self.merged[k]))
+            refs.append(reverse_complement(self.reference_sequences[ref_key]))
+        else:
+            queries.append(self.merged[k])
+            refs.append(self.reference_sequences[ref_key])
+    if not keys:
+        return
+    for k, (sample, ref, _s, ref_start) in zip(keys, batched_pairwise(queries, refs, not global_align)):
+        if ref.upper() != sample:
+            self.potential_variants.append(k)
+        self.aligned[k] = (sample, ref)
+        rk = self.reference[k]
+        self.location[k] = (rk[1], int(rk[2]), int(rk[3]), ref_start)
+
+
+def _reference_sha224(self):
+    return hashlib.sha224(repr(sorted(self.reference_sequences)).encode("latin-1")).hexdigest()
+
+
+def save_hash_table(self, newhashfile):
+    """the on-disk product of match_to_reference, byte-compatible with ambivert.py:608-619"""
+    with newhashfile as outfile:
+        table = {k: self.reference[k] for k in self.reference if k not in self.potential_variants}
+        pickle.dump((_reference_sha224(self), table), outfile)
+
+
+def load_hash_table(self, hashfile):
+    """ambivert.py:621-637"""
+    with hashfile as infile:
+        sha, table = pickle.load(infile)
+        if sha == _reference_sha224(self):
+            self.reference = table
+        else:
+            warnings.warn("WARNING: loaded read to reference hash library does not match reference sequences\n"
+                          "I really hope you know what you are doing... Check and if in doubt use --savehashtable\n"
+                          "without specifying an existing hash file.", UserWarning)
+
+
+class AmpliconData(object):
+    """The state the hot path reads and writes (ambivert.py:202-228) with the on-path stages bound to
+    the batched GPU implementations.  Parsing, variant calling and output stay with the reference."""
+
+    def __init__(self, trim5=None, trim3=None):
+        self.data = defaultdict(list)      # {md5hexdigest: [((f_name, f_seq, f_qual), (r_name, r_seq, r_qual)), ...]}
+        self.merged = {}
+        self.unmergable = []
+        self.aligned = {}
+        self.location = {}
+        self.reference = {}
+        self.reference_sequences = {}      # {(name, chromosome, start, end, strand): sequence}
+        self.potential_variants = []
+        self.trim5 = trim5
+        self.trim3 = None if trim3 is None else -1 * abs(trim3)
+        self.threshold = 0
+        self.readpairs = 0
+
+    def add_reads(self, f_name, f_seq, f_qual, r_name, r_seq, r_qual):
+        """the cluster key is the md5 of the (trimmed) forward + reverse read (ambivert.py:259)"""
+        key = hashlib.md5(bytes(f_seq[self.trim5:self.trim3] + r_seq[self.trim5:self.trim3], "ascii")).hexdigest()
+        self.data[key].append(((f_name, f_seq, f_qual), (r_name, r_seq, r_qual)))
+        self.readpairs += 1
+
+    get_above_threshold = get_above_threshold
+    merge_overlaps = merge_overlaps
+    match_to_reference = match_to_reference
+    align_to_reference = align_to_reference
+    save_hash_table = save_hash_table
+    load_hash_table = load_hash_table
