@@ -44,6 +44,7 @@ struct Options {
   int path = ABV_PATH_AUTO;
   int wf32_blocks_per_sm = 4;
   int mm16_blocks_per_sm = 0;   // 0 = what the occupancy query returns
+  int global_v1 = 0;            // 1 = use the first-generation packed kernel for global mode too
 };
 
 struct Ctx {
@@ -208,6 +209,35 @@ int mm16_launch_one(int grid_cap, cudaStream_t st, const Mm16Params &p, int &lau
   return ABV_OK;
 }
 
+template <int K>
+int mm16g_launch_one(cudaStream_t st, const Mm16Params &p, int &launched) {
+  const Mm16gSmem L = mm16g_smem_layout(K, p.a1, p.tp_stride);
+  auto kern = mm16g_kernel<K>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MM16_WARPS * 32, L.total));
+  if (per_sm < 1) return fail(ABV_ERR_CUDA, "mm16g kernel K=%d does not fit (smem %d)", K, L.total);
+  if (g.opt.mm16_blocks_per_sm > 0) per_sm = std::min(per_sm, g.opt.mm16_blocks_per_sm);
+  const int grid = std::min(p.n_list, g.sms * per_sm);
+  kern<<<grid, MM16_WARPS * 32, L.total, st>>>(p);
+  CU(cudaGetLastError());
+  ++launched;
+  return ABV_OK;
+}
+
+int mm16g_launch(int K, cudaStream_t st, const Mm16Params &p, int &launched) {
+  switch (K) {
+    case 2: return mm16g_launch_one<2>(st, p, launched);
+    case 4: return mm16g_launch_one<4>(st, p, launched);
+    case 6: return mm16g_launch_one<6>(st, p, launched);
+    case 8: return mm16g_launch_one<8>(st, p, launched);
+    case 10: return mm16g_launch_one<10>(st, p, launched);
+    case 12: return mm16g_launch_one<12>(st, p, launched);
+    case 16: return mm16g_launch_one<16>(st, p, launched);
+  }
+  return fail(ABV_ERR_ARGS, "no packed kernel for K=%d", K);
+}
+
 template <int MODE>
 int mm16_launch_mode(int K, cudaStream_t st, const Mm16Params &p, int &launched) {
   switch (K) {
@@ -222,7 +252,8 @@ int mm16_launch_mode(int K, cudaStream_t st, const Mm16Params &p, int &launched)
   return fail(ABV_ERR_ARGS, "no packed kernel for K=%d", K);
 }
 
-int mm16_launch(int mode, int K, cudaStream_t st, const Mm16Params &p, int &launched) {
+int mm16_launch(int mode, int K, bool streaming, cudaStream_t st, const Mm16Params &p, int &launched) {
+  if (mode == ABV_GLOBAL && streaming) return mm16g_launch(K, st, p, launched);
   if (mode == ABV_GLOBAL) return mm16_launch_mode<GLOBAL>(K, st, p, launched);
   if (mode == ABV_LOCAL) return mm16_launch_mode<LOCAL>(K, st, p, launched);
   if (mode == ABV_GLOCAL) return mm16_launch_mode<GLOCAL>(K, st, p, launched);
@@ -243,7 +274,7 @@ struct abv_job {
   DevMem q_codes, q_off, t_codes, t_off, map, matrix, matrix_ext, tp_codes, tp_meta, lists, counters;
   DevMem best_score, best_idx, all_scores, chunk_scores, border;
   int tp_stride = 0, n_pairs = 0, a1 = 0, max_lt = 0, max_lq = 0;
-  struct Bucket { int K, n, offset; double cells; cudaEvent_t e0, e1; };
+  struct Bucket { int K, n, offset; double cells; cudaEvent_t e0, e1; bool streaming; };
   std::vector<Bucket> buckets;     // packed-kernel launches (one per K class), lists at `offset`
   ~abv_job() { for (auto &b : buckets) { if (b.e0) cudaEventDestroy(b.e0); if (b.e1) cudaEventDestroy(b.e1); } }
   int n_wf32 = 0, wf32_offset = 0; // queries served by the 32-bit kernel, list at `wf32_offset`
@@ -269,6 +300,10 @@ int mm_validate(int mode, const char *q, const long long *q_off, int n_q, const 
   if ((rc = check_seqs(t, t_off, n_t, "target", max_lt, min_lt))) return rc;
   if (n_q > 0 && n_t > 0 && (rc = check_mode_lengths(mode, min_lq, min_lt))) return rc;
   return ABV_OK;
+}
+
+bool packed_exact_streaming(int P, int max_lt, int maxabs) {
+  return (long long)(P + max_lt + 8) * maxabs <= b16::LIMIT;
 }
 
 int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int n_q,
@@ -303,7 +338,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   const int a1 = sc.alpha + 1;
   bool packed_ok = g.opt.path != ABV_PATH_WF32 && n_t > 0 && a1 * a1 <= 64 &&
                    (mode == ABV_GLOBAL || mode == ABV_LOCAL || mode == ABV_GLOCAL);
-  const int tp_stride = (max_lt + 15) & ~15;
+  const int tp_stride = std::max(32, (max_lt + 15) & ~15);   // >= 32: the streaming kernel sweeps at least 32 rows per pair
   std::vector<std::vector<int>> lists(MM16_NK);
   std::vector<int> wf32_list;
   for (int i = 0; i < n_q; ++i) {
@@ -315,7 +350,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
       if (slot >= 0) {
         const int K = MM16_KS[slot];
         if (!packed_exact(mode, 32 * K, tp_stride, maxabs)) slot = -1;
-        else if (mm16_smem_layout(K, a1, tp_stride).total > 100 * 1024) slot = -1;
+        else if (std::max(mm16_smem_layout(K, a1, tp_stride).total, mm16g_smem_layout(K, a1, tp_stride).total) > 100 * 1024) slot = -1;
       }
     }
     if (slot >= 0) lists[slot].push_back(i); else wf32_list.push_back(i);
@@ -328,7 +363,8 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
     if (!lists[k].empty()) {
       double qlen = 0;
       for (int i : lists[k]) qlen += (double)(q_off[i + 1] - q_off[i]);
-      abv_job::Bucket b{MM16_KS[k], (int)lists[k].size(), (int)flat.size(), qlen * (double)(t_off[n_t] - t_off[0]), nullptr, nullptr};
+      abv_job::Bucket b{MM16_KS[k], (int)lists[k].size(), (int)flat.size(), qlen * (double)(t_off[n_t] - t_off[0]), nullptr, nullptr,
+                        mode == ABV_GLOBAL && !g.opt.global_v1 && packed_exact_streaming(32 * MM16_KS[k], tp_stride, maxabs)};
       CU(cudaEventCreate(&b.e0));
       CU(cudaEventCreate(&b.e1));
       J.buckets.push_back(b);
@@ -435,7 +471,7 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
     p.all_scores = J.want_all_scores ? J.all_scores.as<int>() : nullptr; p.n_t = J.n_t;
     p.q_counter = reinterpret_cast<unsigned int *>(J.counters.as<unsigned long long>() + ci++);
     CU(cudaEventRecord(b.e0, st));
-    if ((rc = mm16_launch(J.mode, b.K, st, p, launched))) return rc;
+    if ((rc = mm16_launch(J.mode, b.K, b.streaming, st, p, launched))) return rc;
     CU(cudaEventRecord(b.e1, st));
   }
   if (J.n_wf32 > 0) {
@@ -503,6 +539,7 @@ int abv_set_option(const char *key, int value) {
   if (!key) return fail(ABV_ERR_ARGS, "NULL key");
   if (!strcmp(key, "path")) { if (value < 0 || value > 2) return fail(ABV_ERR_ARGS, "bad path"); g.opt.path = value; return ABV_OK; }
   if (!strcmp(key, "wf32_blocks_per_sm")) { g.opt.wf32_blocks_per_sm = std::max(1, std::min(value, 8)); return ABV_OK; }
+  if (!strcmp(key, "global_v1")) { g.opt.global_v1 = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "mm16_blocks_per_sm")) { g.opt.mm16_blocks_per_sm = std::max(0, std::min(value, 8)); return ABV_OK; }
   return fail(ABV_ERR_ARGS, "unknown option %s", key);
 }

@@ -308,4 +308,50 @@ ABV_HD void mm16_row_glocal_last(uint32_t d, uint32_t &e, uint32_t (&Hp)[K], uin
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Biased packed form used by the streaming global kernel (mm16g_kernel).  Every score-like value
+// (H, E, F) is stored as true + BIAS in each half, so both halves are always positive.  Then
+//   * adding a small signed term to both halves is ONE ordinary 32-bit add of the "arithmetically
+//     packed" addend hi*65536 + lo: no borrow can cross the half boundary because the low half stays
+//     in [0, 65535].  Plain IADD/IMAD can issue on the FMA pipe, leaving the half-rate ALU/DPX pipe
+//     to the three max-type instructions of a cell;
+//   * max-type DPX instructions compare the biased halves as signed 16-bit (all in [0, 32767]).
+namespace b16 {
+constexpr int BIAS = 16384;
+constexpr int LIMIT = 16000;      // |true value| bound that keeps every biased half in [384, 32384]
+ABV_HD uint32_t biased(int lo, int hi) { return p16::pack(lo + BIAS, hi + BIAS); }
+ABV_HD uint32_t addend(int lo, int hi) { return (uint32_t)(hi * 65536 + lo); }
+ABV_HD int lo(uint32_t v) { return p16::lo(v) - BIAS; }
+ABV_HD int hi(uint32_t v) { return p16::hi(v) - BIAS; }
+}  // namespace b16
+
+// One row of one lane, biased form.  S[] holds the addend-packed substitution scores on entry and is
+// used as scratch: the K diagonal sums depend only on the previous row, so they are formed first
+// (independent 32-bit adds), then the dependent chain runs: max3, +go, and the two add-max updates.
+//   hleft : H[c0-1][r-1]       e : in E[r] entering the strip, out E[r] leaving it
+//   gow   : addend(go, go)     ge2 : p16::pack(ge, ge)
+template <int K>
+ABV_HD void mm16b_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], uint32_t (&S)[K],
+                      uint32_t gow, uint32_t ge2) {
+#pragma unroll
+  for (int k = K - 1; k >= 1; --k) S[k] += Hp[k - 1];
+  S[0] += hleft;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const uint32_t h = p16::max3(S[k], e, F[k]);
+    const uint32_t hg = h + gow;
+    e = p16::addmax(e, ge2, hg);
+    F[k] = p16::addmax(F[k], ge2, hg);
+    Hp[k] = h;
+  }
+}
+
+// pair-row bookkeeping of the streaming kernel, shared by the kernel and its CPU mirror
+constexpr int MM16G_MIN_ROWS = 32;   // every pair occupies at least 32 steps: lane t switches pair t steps after lane 0
+ABV_HD int mm16g_rows(int l1, int l2) {
+  int m = l1 > l2 ? l1 : l2;
+  return m < MM16G_MIN_ROWS ? MM16G_MIN_ROWS : m;
+}
+
 }  // namespace abv

@@ -467,6 +467,194 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16_
 }
 
 // ---------------------------------------------------------------------------------------------
+// mm16g_kernel: the GLOBAL many-to-many scorer, second generation.  Same data layout and arithmetic
+// idea as mm16_kernel, plus:
+//   * target pairs STREAM through the lane pipeline back to back: lane t switches to the next pair
+//     t steps after lane 0, so there is no ramp-up/ramp-down per pair and all 32 lanes work in every
+//     step (mm16_kernel: 25 of 32 on 240-column queries);
+//   * biased operands (dp_core.cuh, namespace b16): the two adds of a cell are plain 32-bit adds that
+//     can issue on the FMA pipe; the half-rate ALU/DPX pipe only sees max3 + 2 add-max per cell pair;
+//   * the hot loop has no per-step predicates: pair switches happen in the first 32 steps of a pair
+//     (one lane per step), corner captures at warp-uniform steps outside the inner loop;
+//   * three row buffers per warp; the copy for pair i+2 is issued once every lane has left pair i-1.
+struct Mm16gSmem {
+  int lut, tbuf, mbar, mext, wres, misc, zero, qcodes, total;
+};
+__host__ __device__ inline Mm16gSmem mm16g_smem_layout(int K, int a1, int tp_stride) {
+  Mm16gSmem L;
+  int off = 0;
+  L.lut = off; off += a1 * a1 * 32 * K * 4;
+  L.tbuf = off; off += MM16_WARPS * 3 * tp_stride;
+  L.mbar = off; off += MM16_WARPS * 3 * 8;
+  L.mext = off; off += a1 * a1 * 4;
+  L.wres = off; off += MM16_WARPS * 2 * 4;
+  L.misc = off; off += 16;
+  L.zero = off; off += 64;
+  L.qcodes = off; off += 32 * K;
+  L.total = (off + 15) & ~15;
+  return L;
+}
+
+template <int K>
+__global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g_kernel(Mm16Params p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int P = Mm16Cfg<K>::P;
+  constexpr int V = Mm16Cfg<K>::V;
+  constexpr int W = MM16_WARPS;
+  const Mm16gSmem L = mm16g_smem_layout(K, p.a1, p.tp_stride);
+  uint32_t *lut = reinterpret_cast<uint32_t *>(smem + L.lut);
+  uint8_t *qcodes = smem + L.qcodes;
+  int *mext = reinterpret_cast<int *>(smem + L.mext);
+  int *wres = reinterpret_cast<int *>(smem + L.wres);
+  int *misc = reinterpret_cast<int *>(smem + L.misc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tbuf0 = L.tbuf + warp * 3 * p.tp_stride;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.mbar) + warp * 3;
+  const int a1 = p.a1, ncodes = a1 * a1;
+  const int go = p.go, ge = p.ge;
+  const uint32_t gow = b16::addend(go, go), gew = b16::addend(ge, ge), ge2 = p16::pack(ge, ge);
+
+  for (int i = threadIdx.x; i < ncodes; i += blockDim.x) mext[i] = p.matrix_ext[i];
+  if (threadIdx.x < 16) reinterpret_cast<uint32_t *>(smem + L.zero)[threadIdx.x] = 0u;
+  if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1); }
+  mbar_fence_init();
+  uint32_t phbits = 0;
+  __syncthreads();
+
+  for (;;) {
+    if (threadIdx.x == 0) misc[0] = (int)atomicAdd(p.q_counter, 1u);
+    __syncthreads();
+    const int li = misc[0];
+    if (li >= p.n_list) break;
+    const int qi = p.q_list[li];
+    const uint8_t *qs = p.q + p.q_off[qi];
+    const int lq = (int)(p.q_off[qi + 1] - p.q_off[qi]);
+    for (int c = threadIdx.x; c < P; c += blockDim.x) qcodes[c] = c < lq ? qs[c] : (uint8_t)(a1 - 1);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ncodes * P; idx += blockDim.x) {
+      const int code = idx / P, pos = idx - code * P;
+      const int j = pos % V, it = pos / V, t = it & 31, i = it >> 5;
+      const int c = t * K + i * V + j;
+      const int qa = qcodes[c] * a1;
+      const int a = code / a1, bsym = code - a * a1;
+      lut[idx] = b16::addend(mext[qa + a], mext[qa + bsym]);
+    }
+    __syncthreads();
+
+    const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;
+    const int c0 = lane * K;
+    const uint32_t hinit0 = b16::biased(go + ge * c0, go + ge * c0);                 // H[c0][-1]  (global_align.c:148)
+    const uint32_t hl_init = c0 ? b16::biased(go + ge * (c0 - 1), go + ge * (c0 - 1)) : b16::biased(0, 0);
+    const uint32_t v0 = b16::biased(go, go);                                         // H[-1][0]   (global_align.c:137)
+    const int n_i = warp < p.n_pairs ? (p.n_pairs - warp + W - 1) / W : 0;
+    int wbest = INT_MIN, widx = INT_MAX;
+
+    if (n_i > 0) {
+      if (lane == 0) {
+        bulk_load(smem + tbuf0, p.tp_codes + (long long)warp * p.tp_stride, p.tp_stride, &bar[0]);
+        if (n_i > 1) bulk_load(smem + tbuf0 + p.tp_stride, p.tp_codes + (long long)(warp + W) * p.tp_stride, p.tp_stride, &bar[1]);
+      }
+      uint32_t Hp[K], F[K], S[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) { Hp[k] = b16::biased(0, 0); F[k] = b16::biased(0, 0); }
+      uint32_t hleft = b16::biased(0, 0), h_out = b16::biased(0, 0), e_out = b16::biased(0, 0), vh = v0;
+      int tb_off = L.zero + 32 - lane;           // before its first pair a lane sweeps zero (valid) symbols
+      int prev_rows = 0;
+      int pend_s1 = -1, pend_s2 = -1, pend_i1 = -1, pend_i2 = -1;
+      int4 meta_next = p.tp_meta[warp];
+
+      auto step = [&](int s) {
+        uint32_t h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
+        uint32_t e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+        if (lane == 0) { h_sh = vh; e_sh = vh + gow; }
+        vh += gew;
+        const int code = smem[tb_off + s];
+        mm16_load_S<K>(lut + code * P, lane, S);
+        uint32_t e = e_sh;
+        mm16b_row<K>(hleft, e, Hp, F, S, gow, ge2);
+        hleft = h_sh; e_out = e; h_out = Hp[K - 1];
+      };
+      auto capture = [&](int half, int idx) {
+        if (lane == tstar) {
+          const uint32_t hs = mm16_pick<K>(Hp, kstar);
+          const int sc = half ? b16::hi(hs) : b16::lo(hs);
+          if (sc > wbest || (sc == wbest && idx < widx)) { wbest = sc; widx = idx; }
+          if (p.all_scores) p.all_scores[(long long)qi * p.n_t + idx] = sc;
+        }
+      };
+
+      for (int i = 0; i <= n_i; ++i) {
+        const bool real = i < n_i;
+        int4 meta = make_int4(0, 0, -1, -1);
+        int rows = MM16G_MIN_ROWS, bufoff = L.zero + 32;
+        if (real) {
+          meta = meta_next;
+          if (i + 1 < n_i) meta_next = p.tp_meta[warp + (i + 1) * W];
+          rows = mm16g_rows(meta.x, meta.y);
+          const int b = i % 3;
+          bufoff = tbuf0 + b * p.tp_stride;
+          mbar_wait(&bar[b], (phbits >> b) & 1u);
+          phbits ^= 1u << b;
+        }
+        const int cs1 = real ? meta.x - 1 + tstar : -1;
+        const int cs2 = (real && meta.w >= 0) ? meta.y - 1 + tstar : -1;
+        tb_off += prev_rows;
+        vh = v0;
+        // the first 32 steps: lane s switches to this pair at step s
+        for (int s = 0; s < MM16G_MIN_ROWS; ++s) {
+          if (lane == s) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+              Hp[k] = hinit0 + (uint32_t)k * gew;
+              F[k] = Hp[k] + gow;                    // F entering row 0 (global_align.c:146)
+            }
+            hleft = hl_init;
+            tb_off = bufoff - lane;
+          }
+          step(s);
+          if (s == pend_s1) capture(0, pend_i1);
+          if (s == pend_s2) capture(1, pend_i2);
+          if (s == cs1) capture(0, meta.z);
+          if (s == cs2) capture(1, meta.w);
+        }
+        // every lane has left pair i-1: its buffer can take pair i+2
+        __syncwarp();
+        if (lane == 0 && i + 2 < n_i) {
+          const int b2 = (i + 2) % 3;
+          bulk_load(smem + tbuf0 + b2 * p.tp_stride, p.tp_codes + (long long)(warp + (i + 2) * W) * p.tp_stride, p.tp_stride, &bar[b2]);
+        }
+        // steady state
+        int s = MM16G_MIN_ROWS;
+        while (s < rows) {
+          int stop = rows;
+          if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
+          if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
+          for (; s < stop; ++s) step(s);
+          if (s - 1 == cs1) capture(0, meta.z);
+          if (s - 1 == cs2) capture(1, meta.w);
+        }
+        pend_s1 = cs1 >= rows ? cs1 - rows : -1; pend_i1 = meta.z;
+        pend_s2 = cs2 >= rows ? cs2 - rows : -1; pend_i2 = meta.w;
+        prev_rows = rows;
+      }
+    }
+
+    if (lane == tstar) { wres[2 * warp] = wbest; wres[2 * warp + 1] = widx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int bs = INT_MIN, bi = INT_MAX;
+      for (int w = 0; w < W; ++w) {
+        const int s = wres[2 * w], i = wres[2 * w + 1];
+        if (i != INT_MAX && (s > bs || (s == bs && i < bi))) { bs = s; bi = i; }
+      }
+      const bool hit = bi != INT_MAX && bs > p.seed;
+      p.best_score[qi] = hit ? bs : p.seed;
+      p.best_idx[qi] = hit ? bi : -1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Integer-pipe microbenchmark: register-only dependent chains, UNROLL independent chains per thread.
 template <int WHICH>
 __global__ void int_peak_kernel(uint32_t *out, int iters, uint32_t seed) {

@@ -237,3 +237,124 @@ int emu_mm16(int mode, int K, const unsigned char *q, int lq, const unsigned cha
   return -1;
 }
 }
+
+// ---- the streaming global kernel (mm16g_kernel): ONE warp sweeping a list of target pairs -------
+// Mirrors the control flow of the kernel: three row buffers, 32 switch steps per pair, pending corner
+// captures, the zero-symbol prefix before the first pair and the dummy pair that drains the pipeline.
+template <int K>
+static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsigned char *const *t1s, const int *l1s,
+                        const unsigned char *const *t2s, const int *l2s, int alpha, const int *M, int go, int ge,
+                        int *sc1_out, int *sc2_out) {
+  constexpr int V = (K % 4 == 0) ? 4 : 2, P = 32 * K;
+  const int a1 = alpha + 1, ncodes = a1 * a1;
+  std::vector<int> mext((size_t)a1 * a1, 0);
+  for (int x = 0; x < alpha; ++x) for (int y = 0; y < alpha; ++y) mext[x * a1 + y] = M[x * alpha + y];
+  std::vector<unsigned char> qcodes(P);
+  for (int c = 0; c < P; ++c) qcodes[c] = c < lq ? q[c] : (unsigned char)(a1 - 1);
+  std::vector<uint32_t> lut((size_t)ncodes * P);
+  for (int idx = 0; idx < ncodes * P; ++idx) {
+    const int code = idx / P, pos = idx - code * P;
+    const int j = pos % V, it = pos / V, t = it & 31, i = it >> 5;
+    const int c = t * K + i * V + j;
+    const int qa = qcodes[c] * a1;
+    const int a = code / a1, b = code - a * a1;
+    lut[idx] = b16::addend(mext[qa + a], mext[qa + b]);
+  }
+  int max_lt = 1;
+  for (int i = 0; i < n_pairs; ++i) max_lt = std::max(max_lt, std::max(l1s[i], l2s[i]));
+  const int stride = std::max(32, (max_lt + 15) & ~15);
+  // "shared memory": [zero 64][buf0][buf1][buf2]; anything else poisons the LUT index
+  std::vector<unsigned char> sm(64 + 3 * stride, 0);
+  const int zero = 0, tbuf0 = 64;
+  auto fill = [&](int buf, int pi) {
+    for (int r = 0; r < stride; ++r) {
+      const int a = r < l1s[pi] ? t1s[pi][r] : alpha, b = r < l2s[pi] ? t2s[pi][r] : alpha;
+      sm[tbuf0 + buf * stride + r] = (unsigned char)(a * a1 + b);
+    }
+  };
+  const uint32_t gow = b16::addend(go, go), gew = b16::addend(ge, ge), ge2 = p16::pack(ge, ge);
+  const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;
+  const uint32_t v0 = b16::biased(go, go);
+  uint32_t Hp[32][K], F[32][K], S[K], hleft[32], h_out[32], e_out[32], vh = v0, hinit0[32], hl_init[32];
+  int tb_off[32];
+  for (int t = 0; t < 32; ++t) {
+    const int c0 = t * K;
+    for (int k = 0; k < K; ++k) { Hp[t][k] = b16::biased(0, 0); F[t][k] = b16::biased(0, 0); }
+    hleft[t] = h_out[t] = e_out[t] = b16::biased(0, 0);
+    hinit0[t] = b16::biased(go + ge * c0, go + ge * c0);
+    hl_init[t] = c0 ? b16::biased(go + ge * (c0 - 1), go + ge * (c0 - 1)) : b16::biased(0, 0);
+    tb_off[t] = zero + 32 - t;
+  }
+  const int n_i = n_pairs;
+  if (n_i > 0) fill(0, 0);
+  if (n_i > 1) fill(1, 1);
+  int prev_rows = 0, pend_s1 = -1, pend_s2 = -1, pend_i1 = -1, pend_i2 = -1;
+  auto step = [&](int s) {
+    uint32_t h_sh[32], e_sh[32];
+    for (int t = 0; t < 32; ++t) { h_sh[t] = t ? h_out[t - 1] : h_out[0]; e_sh[t] = t ? e_out[t - 1] : e_out[0]; }
+    h_sh[0] = vh; e_sh[0] = vh + gow;
+    vh += gew;
+    for (int t = 0; t < 32; ++t) {
+      const int code = sm.at(tb_off[t] + s);
+      if (code >= ncodes) throw 1;
+      load_S<K>(&lut[(size_t)code * P], t, S);
+      uint32_t e = e_sh[t];
+      mm16b_row<K>(hleft[t], e, Hp[t], F[t], S, gow, ge2);
+      hleft[t] = h_sh[t]; e_out[t] = e; h_out[t] = Hp[t][K - 1];
+    }
+  };
+  auto capture = [&](int half, int idx) {
+    const uint32_t hs = Hp[tstar][kstar];
+    (half ? sc2_out : sc1_out)[idx] = half ? b16::hi(hs) : b16::lo(hs);
+  };
+  for (int i = 0; i <= n_i; ++i) {
+    const bool real = i < n_i;
+    int l1 = 0, l2 = 0, has2 = 0, rows = MM16G_MIN_ROWS, bufoff = zero + 32;
+    if (real) { l1 = l1s[i]; l2 = l2s[i]; has2 = l2 > 0; rows = mm16g_rows(l1, l2); bufoff = tbuf0 + (i % 3) * stride; }
+    const int cs1 = real ? l1 - 1 + tstar : -1, cs2 = (real && has2) ? l2 - 1 + tstar : -1;
+    for (int t = 0; t < 32; ++t) tb_off[t] += prev_rows;
+    vh = v0;
+    for (int s = 0; s < MM16G_MIN_ROWS; ++s) {
+      const int t = s;
+      for (int k = 0; k < K; ++k) { Hp[t][k] = hinit0[t] + (uint32_t)k * gew; F[t][k] = Hp[t][k] + gow; }
+      hleft[t] = hl_init[t];
+      tb_off[t] = bufoff - t;
+      step(s);
+      if (s == pend_s1) capture(0, pend_i1);
+      if (s == pend_s2) capture(1, pend_i2);
+      if (s == cs1) capture(0, i);
+      if (s == cs2) capture(1, i);
+    }
+    if (i + 2 < n_i) fill((i + 2) % 3, i + 2);
+    int s = MM16G_MIN_ROWS;
+    while (s < rows) {
+      int stop = rows;
+      if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
+      if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
+      for (; s < stop; ++s) step(s);
+      if (s - 1 == cs1) capture(0, i);
+      if (s - 1 == cs2) capture(1, i);
+    }
+    pend_s1 = cs1 >= rows ? cs1 - rows : -1; pend_i1 = i;
+    pend_s2 = cs2 >= rows ? cs2 - rows : -1; pend_i2 = i;
+    prev_rows = rows;
+  }
+}
+
+extern "C" int emu_mm16g(int K, const unsigned char *q, int lq, int n_pairs, const unsigned char *const *t1s, const int *l1s,
+                         const unsigned char *const *t2s, const int *l2s, int alpha, const int *M, int go, int ge,
+                         int *sc1, int *sc2) {
+  if (32 * K < lq) return -1;
+  try {
+    switch (K) {
+      case 2: emu_mm16g_t<2>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+      case 4: emu_mm16g_t<4>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+      case 6: emu_mm16g_t<6>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+      case 8: emu_mm16g_t<8>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+      case 10: emu_mm16g_t<10>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+      case 12: emu_mm16g_t<12>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+      case 16: emu_mm16g_t<16>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    }
+  } catch (...) { return -2; }   // an out-of-range symbol read: a pointer bookkeeping error
+  return -1;
+}

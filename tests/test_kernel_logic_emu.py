@@ -146,3 +146,49 @@ def test_packed_logic_vs_oracle(emu, oracle_port):
         assert s1 == chk.align_raw(m, q, t1, alpha, M, go, ge)[0], (it, m, K, lq, len(t1), len(t2))
         if t2:
             assert s2 == chk.align_raw(m, q, t2, alpha, M, go, ge)[0], (it, m, K, lq, len(t1), len(t2))
+
+
+def test_streaming_global_logic_vs_oracle(emu, oracle_port):
+    """mm16g_kernel's pipeline: pairs streaming back to back through the lanes, biased operands,
+    pending corner captures, tiny targets (< 32 rows), single (unpaired) last target"""
+    rng = random.Random(2024)
+    chk = oracle_port
+    for it in range(120):
+        K = rng.choice(KS)
+        lq = rng.randint(max(1, 32 * K - 70), 32 * K) if rng.random() < 0.7 else rng.randint(1, 32 * K)
+        q = bytes(rng.choice([0, 1, 2, 3, 0, 1, 2, 3, 4]) for _ in range(lq))
+        n_pairs = rng.choice([1, 2, 3, 4, 7])
+        lens = sorted([rng.choice([1, 2, 5, 31, 32, 33, rng.randint(1, 300), rng.randint(150, 300)]) for _ in range(2 * n_pairs)], reverse=True)
+        if rng.random() < 0.5:
+            lens[-1] = 0                                     # odd number of targets: the last pair is single
+        targets = []
+        for L in lens:
+            if L and rng.random() < 0.5 and L <= lq:
+                st = rng.randint(0, lq - L)
+                t = bytearray(q[st:st + L])
+                for _ in range(rng.randint(0, 3)):
+                    t[rng.randrange(L)] = rng.randrange(5)
+                targets.append(bytes(t))
+            else:
+                targets.append(bytes(rng.randrange(5) for _ in range(L)))
+        if rng.random() < 0.7:
+            M, go, ge = O.DNA_SCORE, -7, -1
+        else:
+            M = np.array([rng.randint(-4, 4) for _ in range(25)], np.int32)
+            go, ge = -rng.randint(0, 8), -rng.randint(0, 3)
+        M = np.ascontiguousarray(M, dtype=np.int32)
+        t1 = [targets[2 * i] for i in range(n_pairs)]
+        t2 = [targets[2 * i + 1] for i in range(n_pairs)]
+        arr = lambda xs: (C.c_char_p * len(xs))(*xs)
+        l1 = np.array([len(x) for x in t1], np.int32)
+        l2 = np.array([len(x) for x in t2], np.int32)
+        s1 = np.full(n_pairs, -99999, np.int32)
+        s2 = np.full(n_pairs, -99999, np.int32)
+        rc = emu.emu_mm16g(C.c_int(K), q, C.c_int(lq), C.c_int(n_pairs), arr(t1), l1.ctypes.data_as(C.c_void_p), arr(t2),
+                           l2.ctypes.data_as(C.c_void_p), C.c_int(5), M.ctypes.data_as(C.c_void_p), C.c_int(go), C.c_int(ge),
+                           s1.ctypes.data_as(C.c_void_p), s2.ctypes.data_as(C.c_void_p))
+        assert rc == 0, (it, rc)
+        for i in range(n_pairs):
+            assert s1[i] == chk.align_raw(O.GLOBAL, q, t1[i], 5, M, go, ge)[0], (it, K, lq, i, list(l1), list(l2))
+            if len(t2[i]):
+                assert s2[i] == chk.align_raw(O.GLOBAL, q, t2[i], 5, M, go, ge)[0], (it, K, lq, i, list(l1), list(l2))
