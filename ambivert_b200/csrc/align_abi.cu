@@ -302,8 +302,9 @@ int mm_validate(int mode, const char *q, const long long *q_off, int n_q, const 
   return ABV_OK;
 }
 
-bool packed_exact_streaming(int P, int max_lt, int maxabs) {
-  return (long long)(P + max_lt + 8) * maxabs <= b16::LIMIT;
+// drift-normalised values carry an extra |ge| per column and row (dp_core.cuh, mm16d_row)
+bool packed_exact_streaming(int P, int max_lt, int maxabs, int ge) {
+  return (long long)(P + max_lt + 12) * (maxabs + std::abs(ge)) <= b16::LIMIT;
 }
 
 int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int n_q,
@@ -364,7 +365,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
       double qlen = 0;
       for (int i : lists[k]) qlen += (double)(q_off[i + 1] - q_off[i]);
       abv_job::Bucket b{MM16_KS[k], (int)lists[k].size(), (int)flat.size(), qlen * (double)(t_off[n_t] - t_off[0]), nullptr, nullptr,
-                        mode == ABV_GLOBAL && !g.opt.global_v1 && packed_exact_streaming(32 * MM16_KS[k], tp_stride, maxabs)};
+                        mode == ABV_GLOBAL && !g.opt.global_v1 && packed_exact_streaming(32 * MM16_KS[k], tp_stride, maxabs, sc.ge)};
       CU(cudaEventCreate(&b.e0));
       CU(cudaEventCreate(&b.e1));
       J.buckets.push_back(b);

@@ -326,23 +326,28 @@ ABV_HD int lo(uint32_t v) { return p16::lo(v) - BIAS; }
 ABV_HD int hi(uint32_t v) { return p16::hi(v) - BIAS; }
 }  // namespace b16
 
-// One row of one lane, biased form.  S[] holds the addend-packed substitution scores on entry and is
-// used as scratch: the K diagonal sums depend only on the previous row, so they are formed first
-// (independent 32-bit adds), then the dependent chain runs: max3, +go, and the two add-max updates.
-//   hleft : H[c0-1][r-1]       e : in E[r] entering the strip, out E[r] leaving it
-//   gow   : addend(go, go)     ge2 : p16::pack(ge, ge)
+// Drift-normalised recurrences of the streaming global kernel.  With g = gap_extend, every value of
+// cell (c, r) is stored minus g*(c + r):  H~ = H - g(c+r), E~ = E - g(c+r), F~ = F - g(c+r).  Moving one
+// cell right or down changes the offset by exactly g, which cancels the "+ gap_extend" of a gap
+// extension, and a diagonal move changes it by 2g, which is folded into the substitution profile:
+//     H~[c][r]   = max(H~[c-1][r-1] + (S - 2g), E~[c][r], F~[c][r])
+//     E~[c+1][r] = max(E~[c][r], H~[c][r] + (go - g))          F~[c][r+1] likewise
+// One ordinary add and three DPX instructions per cell pair instead of two adds and three DPX, and a
+// two-instruction dependent chain.  The global boundary becomes constant: H~[c][-1] = H~[-1][r] = go + g,
+// F~[c][0] = E~[0][r] = 2go, H~[-1][-1] = 2g (from global_align.c:136-148).
+//   S[]   : in  addend-packed (S - 2g) of this row's symbols; scratch
+//   hleft : H~[c0-1][r-1]       e : in E~[r] entering the strip, out E~[r] leaving it
+//   gop2  : p16::pack(go - g, go - g)
 template <int K>
-ABV_HD void mm16b_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], uint32_t (&S)[K],
-                      uint32_t gow, uint32_t ge2) {
+ABV_HD void mm16d_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], uint32_t (&S)[K], uint32_t gop2) {
 #pragma unroll
   for (int k = K - 1; k >= 1; --k) S[k] += Hp[k - 1];
   S[0] += hleft;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const uint32_t h = p16::max3(S[k], e, F[k]);
-    const uint32_t hg = h + gow;
-    e = p16::addmax(e, ge2, hg);
-    F[k] = p16::addmax(F[k], ge2, hg);
+    e = p16::addmax(h, gop2, e);
+    F[k] = p16::addmax(h, gop2, F[k]);
     Hp[k] = h;
   }
 }

@@ -512,7 +512,10 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.mbar) + warp * 3;
   const int a1 = p.a1, ncodes = a1 * a1;
   const int go = p.go, ge = p.ge;
-  const uint32_t gow = b16::addend(go, go), gew = b16::addend(ge, ge), ge2 = p16::pack(ge, ge);
+  const uint32_t gop2 = p16::pack(go - ge, go - ge);
+  const uint32_t Hc = b16::biased(go + ge, go + ge);      // H~ of the virtual row/column (see mm16d_row)
+  const uint32_t Ec = b16::biased(2 * go, 2 * go);        // E~ entering column 0, F~ entering row 0
+  const uint32_t H00 = b16::biased(2 * ge, 2 * ge);       // H~[-1][-1]
 
   for (int i = threadIdx.x; i < ncodes; i += blockDim.x) mext[i] = p.matrix_ext[i];
   if (threadIdx.x < 16) reinterpret_cast<uint32_t *>(smem + L.zero)[threadIdx.x] = 0u;
@@ -537,15 +540,12 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
       const int c = t * K + i * V + j;
       const int qa = qcodes[c] * a1;
       const int a = code / a1, bsym = code - a * a1;
-      lut[idx] = b16::addend(mext[qa + a], mext[qa + bsym]);
+      lut[idx] = b16::addend(mext[qa + a] - 2 * ge, mext[qa + bsym] - 2 * ge);
     }
     __syncthreads();
 
     const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;
-    const int c0 = lane * K;
-    const uint32_t hinit0 = b16::biased(go + ge * c0, go + ge * c0);                 // H[c0][-1]  (global_align.c:148)
-    const uint32_t hl_init = c0 ? b16::biased(go + ge * (c0 - 1), go + ge * (c0 - 1)) : b16::biased(0, 0);
-    const uint32_t v0 = b16::biased(go, go);                                         // H[-1][0]   (global_align.c:137)
+    const uint32_t hl_init = lane ? Hc : H00;
     const int n_i = warp < p.n_pairs ? (p.n_pairs - warp + W - 1) / W : 0;
     int wbest = INT_MIN, widx = INT_MAX;
 
@@ -557,27 +557,26 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
       uint32_t Hp[K], F[K], S[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) { Hp[k] = b16::biased(0, 0); F[k] = b16::biased(0, 0); }
-      uint32_t hleft = b16::biased(0, 0), h_out = b16::biased(0, 0), e_out = b16::biased(0, 0), vh = v0;
+      uint32_t hleft = b16::biased(0, 0), h_out = b16::biased(0, 0), e_out = b16::biased(0, 0);
       int tb_off = L.zero + 32 - lane;           // before its first pair a lane sweeps zero (valid) symbols
       int prev_rows = 0;
-      int pend_s1 = -1, pend_s2 = -1, pend_i1 = -1, pend_i2 = -1;
+      int pend_s1 = -1, pend_s2 = -1, pend_i1 = -1, pend_i2 = -1, pend_d1 = 0, pend_d2 = 0;
       int4 meta_next = p.tp_meta[warp];
 
       auto step = [&](int s) {
         uint32_t h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
         uint32_t e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
-        if (lane == 0) { h_sh = vh; e_sh = vh + gow; }
-        vh += gew;
+        if (lane == 0) { h_sh = Hc; e_sh = Ec; }
         const int code = smem[tb_off + s];
         mm16_load_S<K>(lut + code * P, lane, S);
         uint32_t e = e_sh;
-        mm16b_row<K>(hleft, e, Hp, F, S, gow, ge2);
+        mm16d_row<K>(hleft, e, Hp, F, S, gop2);
         hleft = h_sh; e_out = e; h_out = Hp[K - 1];
       };
-      auto capture = [&](int half, int idx) {
+      auto capture = [&](int half, int idx, int drift) {
         if (lane == tstar) {
           const uint32_t hs = mm16_pick<K>(Hp, kstar);
-          const int sc = half ? b16::hi(hs) : b16::lo(hs);
+          const int sc = (half ? b16::hi(hs) : b16::lo(hs)) + drift;     // undo the drift: + g*(c + r) of the corner
           if (sc > wbest || (sc == wbest && idx < widx)) { wbest = sc; widx = idx; }
           if (p.all_scores) p.all_scores[(long long)qi * p.n_t + idx] = sc;
         }
@@ -599,23 +598,20 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         const int cs1 = real ? meta.x - 1 + tstar : -1;
         const int cs2 = (real && meta.w >= 0) ? meta.y - 1 + tstar : -1;
         tb_off += prev_rows;
-        vh = v0;
+        const int dr1 = ge * (lq - 1 + meta.x - 1), dr2 = ge * (lq - 1 + meta.y - 1);
         // the first 32 steps: lane s switches to this pair at step s
         for (int s = 0; s < MM16G_MIN_ROWS; ++s) {
           if (lane == s) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-              Hp[k] = hinit0 + (uint32_t)k * gew;
-              F[k] = Hp[k] + gow;                    // F entering row 0 (global_align.c:146)
-            }
+            for (int k = 0; k < K; ++k) { Hp[k] = Hc; F[k] = Ec; }
             hleft = hl_init;
             tb_off = bufoff - lane;
           }
           step(s);
-          if (s == pend_s1) capture(0, pend_i1);
-          if (s == pend_s2) capture(1, pend_i2);
-          if (s == cs1) capture(0, meta.z);
-          if (s == cs2) capture(1, meta.w);
+          if (s == pend_s1) capture(0, pend_i1, pend_d1);
+          if (s == pend_s2) capture(1, pend_i2, pend_d2);
+          if (s == cs1) capture(0, meta.z, dr1);
+          if (s == cs2) capture(1, meta.w, dr2);
         }
         // every lane has left pair i-1: its buffer can take pair i+2
         __syncwarp();
@@ -630,11 +626,11 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
           if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
           if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
           for (; s < stop; ++s) step(s);
-          if (s - 1 == cs1) capture(0, meta.z);
-          if (s - 1 == cs2) capture(1, meta.w);
+          if (s - 1 == cs1) capture(0, meta.z, dr1);
+          if (s - 1 == cs2) capture(1, meta.w, dr2);
         }
-        pend_s1 = cs1 >= rows ? cs1 - rows : -1; pend_i1 = meta.z;
-        pend_s2 = cs2 >= rows ? cs2 - rows : -1; pend_i2 = meta.w;
+        pend_s1 = cs1 >= rows ? cs1 - rows : -1; pend_i1 = meta.z; pend_d1 = dr1;
+        pend_s2 = cs2 >= rows ? cs2 - rows : -1; pend_i2 = meta.w; pend_d2 = dr2;
         prev_rows = rows;
       }
     }

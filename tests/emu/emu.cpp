@@ -258,7 +258,7 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
     const int c = t * K + i * V + j;
     const int qa = qcodes[c] * a1;
     const int a = code / a1, b = code - a * a1;
-    lut[idx] = b16::addend(mext[qa + a], mext[qa + b]);
+    lut[idx] = b16::addend(mext[qa + a] - 2 * ge, mext[qa + b] - 2 * ge);
   }
   int max_lt = 1;
   for (int i = 0; i < n_pairs; ++i) max_lt = std::max(max_lt, std::max(l1s[i], l2s[i]));
@@ -272,17 +272,15 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
       sm[tbuf0 + buf * stride + r] = (unsigned char)(a * a1 + b);
     }
   };
-  const uint32_t gow = b16::addend(go, go), gew = b16::addend(ge, ge), ge2 = p16::pack(ge, ge);
+  const uint32_t gop2 = p16::pack(go - ge, go - ge);
+  const uint32_t Hc = b16::biased(go + ge, go + ge), Ec = b16::biased(2 * go, 2 * go), H00 = b16::biased(2 * ge, 2 * ge);
   const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;
-  const uint32_t v0 = b16::biased(go, go);
-  uint32_t Hp[32][K], F[32][K], S[K], hleft[32], h_out[32], e_out[32], vh = v0, hinit0[32], hl_init[32];
+  uint32_t Hp[32][K], F[32][K], S[K], hleft[32], h_out[32], e_out[32], hl_init[32];
   int tb_off[32];
   for (int t = 0; t < 32; ++t) {
-    const int c0 = t * K;
     for (int k = 0; k < K; ++k) { Hp[t][k] = b16::biased(0, 0); F[t][k] = b16::biased(0, 0); }
     hleft[t] = h_out[t] = e_out[t] = b16::biased(0, 0);
-    hinit0[t] = b16::biased(go + ge * c0, go + ge * c0);
-    hl_init[t] = c0 ? b16::biased(go + ge * (c0 - 1), go + ge * (c0 - 1)) : b16::biased(0, 0);
+    hl_init[t] = t ? Hc : H00;
     tb_off[t] = zero + 32 - t;
   }
   const int n_i = n_pairs;
@@ -292,20 +290,20 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
   auto step = [&](int s) {
     uint32_t h_sh[32], e_sh[32];
     for (int t = 0; t < 32; ++t) { h_sh[t] = t ? h_out[t - 1] : h_out[0]; e_sh[t] = t ? e_out[t - 1] : e_out[0]; }
-    h_sh[0] = vh; e_sh[0] = vh + gow;
-    vh += gew;
+    h_sh[0] = Hc; e_sh[0] = Ec;
     for (int t = 0; t < 32; ++t) {
       const int code = sm.at(tb_off[t] + s);
       if (code >= ncodes) throw 1;
       load_S<K>(&lut[(size_t)code * P], t, S);
       uint32_t e = e_sh[t];
-      mm16b_row<K>(hleft[t], e, Hp[t], F[t], S, gow, ge2);
+      mm16d_row<K>(hleft[t], e, Hp[t], F[t], S, gop2);
       hleft[t] = h_sh[t]; e_out[t] = e; h_out[t] = Hp[t][K - 1];
     }
   };
   auto capture = [&](int half, int idx) {
     const uint32_t hs = Hp[tstar][kstar];
-    (half ? sc2_out : sc1_out)[idx] = half ? b16::hi(hs) : b16::lo(hs);
+    const int drift = ge * (lq - 1 + (half ? l2s[idx] : l1s[idx]) - 1);
+    (half ? sc2_out : sc1_out)[idx] = (half ? b16::hi(hs) : b16::lo(hs)) + drift;
   };
   for (int i = 0; i <= n_i; ++i) {
     const bool real = i < n_i;
@@ -313,10 +311,9 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
     if (real) { l1 = l1s[i]; l2 = l2s[i]; has2 = l2 > 0; rows = mm16g_rows(l1, l2); bufoff = tbuf0 + (i % 3) * stride; }
     const int cs1 = real ? l1 - 1 + tstar : -1, cs2 = (real && has2) ? l2 - 1 + tstar : -1;
     for (int t = 0; t < 32; ++t) tb_off[t] += prev_rows;
-    vh = v0;
     for (int s = 0; s < MM16G_MIN_ROWS; ++s) {
       const int t = s;
-      for (int k = 0; k < K; ++k) { Hp[t][k] = hinit0[t] + (uint32_t)k * gew; F[t][k] = Hp[t][k] + gow; }
+      for (int k = 0; k < K; ++k) { Hp[t][k] = Hc; F[t][k] = Ec; }
       hleft[t] = hl_init[t];
       tb_off[t] = bufoff - t;
       step(s);
