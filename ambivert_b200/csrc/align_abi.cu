@@ -44,6 +44,7 @@ struct Options {
   int path = ABV_PATH_AUTO;
   int wf32_blocks_per_sm = 4;
   int mm16_blocks_per_sm = 0;   // 0 = what the occupancy query returns
+  int split = 0;                // 0 = automatic; otherwise slices of the target pairs per query
   int global_v1 = 0;            // 1 = use the first-generation packed kernel for global mode too
 };
 
@@ -189,8 +190,17 @@ int wf32_grid(long long n_pairs, size_t scratch_per_warp) {
 }
 
 // ---- mm16 launcher ----------------------------------------------------------------------------
-const int MM16_KS[] = {2, 4, 6, 8, 10, 12, 16};
-constexpr int MM16_NK = 7;
+const int MM16_KS[] = {2, 4, 6, 7, 8, 10, 12, 16};   // 7: streaming global kernel only
+constexpr int MM16_NK = 8;
+
+// Work items per launch: a query is cut into `split` slices of the target pairs when there are too few
+// queries to keep the tail of the persistent grid short (each slice keeps >= 4 pairs per warp).
+int pick_split(int n_list, int n_pairs, int resident_ctas) {
+  if (g.opt.split > 0) return std::max(1, std::min(g.opt.split, std::max(1, n_pairs / MM16_WARPS)));
+  int split = 1;
+  while (split < 16 && (long long)n_list * split < 24ll * resident_ctas && n_pairs / (split * 2) >= 4 * MM16_WARPS) split *= 2;
+  return split;
+}
 
 template <int MODE, int K>
 int mm16_launch_one(int grid_cap, cudaStream_t st, const Mm16Params &p, int &launched) {
@@ -201,9 +211,11 @@ int mm16_launch_one(int grid_cap, cudaStream_t st, const Mm16Params &p, int &lau
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MM16_WARPS * 32, L.total));
   if (per_sm < 1) return fail(ABV_ERR_CUDA, "mm16 kernel K=%d does not fit (smem %d)", K, L.total);
   if (g.opt.mm16_blocks_per_sm > 0) per_sm = std::min(per_sm, g.opt.mm16_blocks_per_sm);
-  int grid = std::min(p.n_list, g.sms * per_sm);
+  Mm16Params q = p;
+  q.split = pick_split(p.n_list, p.n_pairs, g.sms * per_sm);
+  int grid = (int)std::min<long long>((long long)p.n_list * q.split, g.sms * per_sm);
   if (grid_cap > 0) grid = std::min(grid, grid_cap);
-  kern<<<grid, MM16_WARPS * 32, L.total, st>>>(p);
+  kern<<<grid, MM16_WARPS * 32, L.total, st>>>(q);
   CU(cudaGetLastError());
   ++launched;
   return ABV_OK;
@@ -218,8 +230,10 @@ int mm16g_launch_one(cudaStream_t st, const Mm16Params &p, int &launched) {
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MM16_WARPS * 32, L.total));
   if (per_sm < 1) return fail(ABV_ERR_CUDA, "mm16g kernel K=%d does not fit (smem %d)", K, L.total);
   if (g.opt.mm16_blocks_per_sm > 0) per_sm = std::min(per_sm, g.opt.mm16_blocks_per_sm);
-  const int grid = std::min(p.n_list, g.sms * per_sm);
-  kern<<<grid, MM16_WARPS * 32, L.total, st>>>(p);
+  Mm16Params q = p;
+  q.split = pick_split(p.n_list, p.n_pairs, g.sms * per_sm);
+  const int grid = (int)std::min<long long>((long long)p.n_list * q.split, g.sms * per_sm);
+  kern<<<grid, MM16_WARPS * 32, L.total, st>>>(q);
   CU(cudaGetLastError());
   ++launched;
   return ABV_OK;
@@ -230,6 +244,7 @@ int mm16g_launch(int K, cudaStream_t st, const Mm16Params &p, int &launched) {
     case 2: return mm16g_launch_one<2>(st, p, launched);
     case 4: return mm16g_launch_one<4>(st, p, launched);
     case 6: return mm16g_launch_one<6>(st, p, launched);
+    case 7: return mm16g_launch_one<7>(st, p, launched);
     case 8: return mm16g_launch_one<8>(st, p, launched);
     case 10: return mm16g_launch_one<10>(st, p, launched);
     case 12: return mm16g_launch_one<12>(st, p, launched);
@@ -272,7 +287,7 @@ struct abv_job {
   bool want_all_scores = false;
   // device data
   DevMem q_codes, q_off, t_codes, t_off, map, matrix, matrix_ext, tp_codes, tp_meta, lists, counters;
-  DevMem best_score, best_idx, all_scores, chunk_scores, border;
+  DevMem best_score, best_idx, all_scores, chunk_scores, border, best_key;
   int tp_stride = 0, n_pairs = 0, a1 = 0, max_lt = 0, max_lq = 0;
   struct Bucket { int K, n, offset; double cells; cudaEvent_t e0, e1; bool streaming; };
   std::vector<Bucket> buckets;     // packed-kernel launches (one per K class), lists at `offset`
@@ -321,6 +336,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   }
   CU(J.best_score.alloc(sizeof(int) * (size_t)std::max(n_q, 1)));
   CU(J.best_idx.alloc(sizeof(int) * (size_t)std::max(n_q, 1)));
+  CU(J.best_key.alloc(sizeof(unsigned long long) * (size_t)std::max(n_q, 1)));
   if (all_scores) {
     if ((long long)n_q * n_t > (1ll << 28)) return fail(ABV_ERR_ARGS, "score matrix of %d x %d is too large", n_q, n_t);
     CU(J.all_scores.alloc(sizeof(int) * (size_t)std::max<long long>((long long)n_q * n_t, 1)));
@@ -346,8 +362,11 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
     const int lq = (int)(q_off[i + 1] - q_off[i]);
     int slot = -1;
     if (packed_ok) {
-      for (int k = 0; k < MM16_NK; ++k)
-        if (32 * MM16_KS[k] >= lq) { slot = k; break; }
+      for (int k = 0; k < MM16_NK; ++k) {
+        const int K = MM16_KS[k];
+        if (K % 2 && !(mode == ABV_GLOBAL && !g.opt.global_v1 && packed_exact_streaming(32 * K, tp_stride, maxabs, sc.ge))) continue;
+        if (32 * K >= lq) { slot = k; break; }
+      }
       if (slot >= 0) {
         const int K = MM16_KS[slot];
         if (!packed_exact(mode, 32 * K, tp_stride, maxabs)) slot = -1;
@@ -458,6 +477,7 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
     return ABV_OK;
   }
   CU(cudaMemsetAsync(J.counters.p, 0, sizeof(unsigned long long) * J.n_counters, st));
+  if (!J.buckets.empty()) CU(cudaMemsetAsync(J.best_key.p, 0, sizeof(unsigned long long) * (size_t)J.n_q, st));
   int launched = 0;
   int ci = 0;
   for (const auto &b : J.buckets) {
@@ -471,9 +491,17 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
     p.best_score = d_best_score; p.best_idx = d_best_idx;
     p.all_scores = J.want_all_scores ? J.all_scores.as<int>() : nullptr; p.n_t = J.n_t;
     p.q_counter = reinterpret_cast<unsigned int *>(J.counters.as<unsigned long long>() + ci++);
+    p.best_key = J.best_key.as<unsigned long long>(); p.split = 1;
     CU(cudaEventRecord(b.e0, st));
     if ((rc = mm16_launch(J.mode, b.K, b.streaming, st, p, launched))) return rc;
     CU(cudaEventRecord(b.e1, st));
+  }
+  if (!J.buckets.empty()) {   // seed rule + unpack, over the queries the packed kernels served
+    const int n_packed = J.wf32_offset;
+    best_key_finalize_kernel<<<(n_packed + 255) / 256, 256, 0, st>>>(J.best_key.as<unsigned long long>(), J.lists.as<int>(), n_packed,
+                                                                     J.seed, d_best_score, d_best_idx);
+    CU(cudaGetLastError());
+    ++launched;
   }
   if (J.n_wf32 > 0) {
     const long long max_chunk_scores = 32ll << 20;
@@ -540,6 +568,7 @@ int abv_set_option(const char *key, int value) {
   if (!key) return fail(ABV_ERR_ARGS, "NULL key");
   if (!strcmp(key, "path")) { if (value < 0 || value > 2) return fail(ABV_ERR_ARGS, "bad path"); g.opt.path = value; return ABV_OK; }
   if (!strcmp(key, "wf32_blocks_per_sm")) { g.opt.wf32_blocks_per_sm = std::max(1, std::min(value, 8)); return ABV_OK; }
+  if (!strcmp(key, "split")) { g.opt.split = std::max(0, std::min(value, 64)); return ABV_OK; }
   if (!strcmp(key, "global_v1")) { g.opt.global_v1 = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "mm16_blocks_per_sm")) { g.opt.mm16_blocks_per_sm = std::max(0, std::min(value, 8)); return ABV_OK; }
   return fail(ABV_ERR_ARGS, "unknown option %s", key);

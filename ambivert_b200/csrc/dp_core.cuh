@@ -338,8 +338,17 @@ ABV_HD int hi(uint32_t v) { return p16::hi(v) - BIAS; }
 //   S[]   : in  addend-packed (S - 2g) of this row's symbols; scratch
 //   hleft : H~[c0-1][r-1]       e : in E~[r] entering the strip, out E~[r] leaving it
 //   gop2  : p16::pack(go - g, go - g)
+// K = query columns per lane; the profile is stored with KP >= K words per lane (StripCfg) so that odd
+// K still loads with 16-byte vectors; S[] has KP entries of which the first K are used.
 template <int K>
-ABV_HD void mm16d_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], uint32_t (&S)[K], uint32_t gop2) {
+struct StripCfg {
+  static constexpr int KP = (K % 2) ? ((K + 3) & ~3) : K;   // padded strip width in the profile
+  static constexpr int V = (KP % 4 == 0) ? 4 : 2;           // words per shared-memory vector load
+  static constexpr int P = 32 * KP;                         // profile row length in words
+};
+
+template <int K, int KP>
+ABV_HD void mm16d_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], uint32_t (&S)[KP], uint32_t gop2) {
 #pragma unroll
   for (int k = K - 1; k >= 1; --k) S[k] += Hp[k - 1];
   S[0] += hleft;

@@ -227,7 +227,27 @@ struct Mm16Params {
   int *best_score, *best_idx;                 // indexed by query
   int *all_scores; int n_t;                   // optional full score matrix [query*n_t + target]
   unsigned int *q_counter;
+  unsigned long long *best_key;               // per query: packed (score, target) of the best hit so far, see best_key_pack
+  int split;                                  // work item = (query, one of `split` slices of the target pairs)
 };
+
+// Per-query best hits are combined across work items with one 64-bit atomicMax: higher score wins, then
+// the lower target index (the first maximum in target order, ambivert.py:478-485).  0 = no hit yet.
+__host__ __device__ inline unsigned long long best_key_pack(int score, int idx) {
+  return ((unsigned long long)((unsigned)score ^ 0x80000000u) << 32) | (unsigned)(0x7fffffff - idx);
+}
+
+__global__ void best_key_finalize_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ q_list, int n, int seed,
+                                         int *__restrict__ best_score, int *__restrict__ best_idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int qi = q_list[i];
+  const unsigned long long k = keys[qi];
+  const int bs = (int)((unsigned)(k >> 32) ^ 0x80000000u), bi = 0x7fffffff - (int)(unsigned)k;
+  const bool hit = k != 0ull && bs > seed;            // strict '>' against the seed (ambivert.py:482)
+  best_score[qi] = hit ? bs : seed;
+  best_idx[qi] = hit ? bi : -1;
+}
 
 constexpr int MM16_WARPS = 8;
 
@@ -236,6 +256,7 @@ struct Mm16Cfg {
   static constexpr int V = (K % 4 == 0) ? 4 : 2;     // words per shared-memory vector load
   static constexpr int P = 32 * K;                   // profile row length in words
   static constexpr int MIN_BLOCKS = K <= 8 ? 4 : (K <= 12 ? 3 : 2);
+  static constexpr int KP = StripCfg<K>::KP;
 };
 
 template <int K>
@@ -318,8 +339,10 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16_
   for (;;) {
     if (threadIdx.x == 0) misc[0] = (int)atomicAdd(p.q_counter, 1u);
     __syncthreads();
-    const int li = misc[0];
-    if (li >= p.n_list) break;
+    const int item = misc[0];
+    if (item >= p.n_list * p.split) break;
+    const int li = item / p.split, part = item - li * p.split;
+    const int pair_lo = (int)((long long)p.n_pairs * part / p.split), pair_hi = (int)((long long)p.n_pairs * (part + 1) / p.split);
     const int qi = p.q_list[li];
     const uint8_t *qs = p.q + p.q_off[qi];
     const int lq = (int)(p.q_off[qi + 1] - p.q_off[qi]);
@@ -340,14 +363,14 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16_
     const int c0 = lane * K;
     int wbest = INT_MIN, widx = INT_MAX;
 
-    int pi = warp;
-    if (pi < p.n_pairs && lane == 0) bulk_load(tbuf0, p.tp_codes + (long long)pi * p.tp_stride, p.tp_stride, &bar[0]);
+    int pi = pair_lo + warp;
+    if (pi < pair_hi && lane == 0) bulk_load(tbuf0, p.tp_codes + (long long)pi * p.tp_stride, p.tp_stride, &bar[0]);
     int it = 0;
-    for (; pi < p.n_pairs; pi += MM16_WARPS, ++it) {
+    for (; pi < pair_hi; pi += MM16_WARPS, ++it) {
       const int cur = it & 1;
       const int pn = pi + MM16_WARPS;
       __syncwarp();
-      if (pn < p.n_pairs && lane == 0)
+      if (pn < pair_hi && lane == 0)
         bulk_load(tbuf0 + (cur ^ 1) * p.tp_stride, p.tp_codes + (long long)pn * p.tp_stride, p.tp_stride, &bar[cur ^ 1]);
       const int4 meta = p.tp_meta[pi];
       if (cur == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
@@ -458,9 +481,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16_
         const int s = wres[2 * w], i = wres[2 * w + 1];
         if (i != INT_MAX && (s > bs || (s == bs && i < bi))) { bs = s; bi = i; }
       }
-      const bool hit = bi != INT_MAX && bs > p.seed;     // strict '>' against the seed (ambivert.py:482)
-      p.best_score[qi] = hit ? bs : p.seed;
-      p.best_idx[qi] = hit ? bi : -1;
+      if (bi != INT_MAX) atomicMax(p.best_key + qi, best_key_pack(bs, bi));   // seed rule applied by best_key_finalize_kernel
     }
     // the next iteration's first __syncthreads orders these reads before wres/lut are rewritten
   }
@@ -483,14 +504,15 @@ struct Mm16gSmem {
 __host__ __device__ inline Mm16gSmem mm16g_smem_layout(int K, int a1, int tp_stride) {
   Mm16gSmem L;
   int off = 0;
-  L.lut = off; off += a1 * a1 * 32 * K * 4;
+  const int KP = (K % 2) ? ((K + 3) & ~3) : K;             // StripCfg<K>::KP
+  L.lut = off; off += a1 * a1 * 32 * KP * 4;
   L.tbuf = off; off += MM16_WARPS * 3 * tp_stride;
   L.mbar = off; off += MM16_WARPS * 3 * 8;
   L.mext = off; off += a1 * a1 * 4;
   L.wres = off; off += MM16_WARPS * 2 * 4;
   L.misc = off; off += 16;
   L.zero = off; off += 64;
-  L.qcodes = off; off += 32 * K;
+  L.qcodes = off; off += 32 * KP;
   L.total = (off + 15) & ~15;
   return L;
 }
@@ -498,8 +520,9 @@ __host__ __device__ inline Mm16gSmem mm16g_smem_layout(int K, int a1, int tp_str
 template <int K>
 __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g_kernel(Mm16Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int P = Mm16Cfg<K>::P;
-  constexpr int V = Mm16Cfg<K>::V;
+  constexpr int KP = StripCfg<K>::KP;
+  constexpr int P = StripCfg<K>::P;
+  constexpr int V = StripCfg<K>::V;
   constexpr int W = MM16_WARPS;
   const Mm16gSmem L = mm16g_smem_layout(K, p.a1, p.tp_stride);
   uint32_t *lut = reinterpret_cast<uint32_t *>(smem + L.lut);
@@ -527,8 +550,10 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
   for (;;) {
     if (threadIdx.x == 0) misc[0] = (int)atomicAdd(p.q_counter, 1u);
     __syncthreads();
-    const int li = misc[0];
-    if (li >= p.n_list) break;
+    const int item = misc[0];
+    if (item >= p.n_list * p.split) break;
+    const int li = item / p.split, part = item - li * p.split;
+    const int pair_lo = (int)((long long)p.n_pairs * part / p.split), pair_hi = (int)((long long)p.n_pairs * (part + 1) / p.split);
     const int qi = p.q_list[li];
     const uint8_t *qs = p.q + p.q_off[qi];
     const int lq = (int)(p.q_off[qi + 1] - p.q_off[qi]);
@@ -537,8 +562,8 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
     for (int idx = threadIdx.x; idx < ncodes * P; idx += blockDim.x) {
       const int code = idx / P, pos = idx - code * P;
       const int j = pos % V, it = pos / V, t = it & 31, i = it >> 5;
-      const int c = t * K + i * V + j;
-      const int qa = qcodes[c] * a1;
+      const int k = i * V + j;                                // k >= K: padding word of an odd strip, never used
+      const int qa = (k < K ? (int)qcodes[t * K + k] : a1 - 1) * a1;
       const int a = code / a1, bsym = code - a * a1;
       lut[idx] = b16::addend(mext[qa + a] - 2 * ge, mext[qa + bsym] - 2 * ge);
     }
@@ -546,31 +571,33 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
 
     const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;
     const uint32_t hl_init = lane ? Hc : H00;
-    const int n_i = warp < p.n_pairs ? (p.n_pairs - warp + W - 1) / W : 0;
+    const int n_mine = pair_hi - pair_lo;                          // this item's slice of the target pairs
+    const int n_i = warp < n_mine ? (n_mine - warp + W - 1) / W : 0;
+    const int pbase = pair_lo + warp;                              // this warp takes pairs pbase + i*W
     int wbest = INT_MIN, widx = INT_MAX;
 
     if (n_i > 0) {
       if (lane == 0) {
-        bulk_load(smem + tbuf0, p.tp_codes + (long long)warp * p.tp_stride, p.tp_stride, &bar[0]);
-        if (n_i > 1) bulk_load(smem + tbuf0 + p.tp_stride, p.tp_codes + (long long)(warp + W) * p.tp_stride, p.tp_stride, &bar[1]);
+        bulk_load(smem + tbuf0, p.tp_codes + (long long)pbase * p.tp_stride, p.tp_stride, &bar[0]);
+        if (n_i > 1) bulk_load(smem + tbuf0 + p.tp_stride, p.tp_codes + (long long)(pbase + W) * p.tp_stride, p.tp_stride, &bar[1]);
       }
-      uint32_t Hp[K], F[K], S[K];
+      uint32_t Hp[K], F[K], S[KP];
 #pragma unroll
       for (int k = 0; k < K; ++k) { Hp[k] = b16::biased(0, 0); F[k] = b16::biased(0, 0); }
       uint32_t hleft = b16::biased(0, 0), h_out = b16::biased(0, 0), e_out = b16::biased(0, 0);
       int tb_off = L.zero + 32 - lane;           // before its first pair a lane sweeps zero (valid) symbols
       int prev_rows = 0;
       int pend_s1 = -1, pend_s2 = -1, pend_i1 = -1, pend_i2 = -1, pend_d1 = 0, pend_d2 = 0;
-      int4 meta_next = p.tp_meta[warp];
+      int4 meta_next = p.tp_meta[pbase];
 
       auto step = [&](int s) {
         uint32_t h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
         uint32_t e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
         if (lane == 0) { h_sh = Hc; e_sh = Ec; }
         const int code = smem[tb_off + s];
-        mm16_load_S<K>(lut + code * P, lane, S);
+        mm16_load_S<KP>(lut + code * P, lane, S);
         uint32_t e = e_sh;
-        mm16d_row<K>(hleft, e, Hp, F, S, gop2);
+        mm16d_row<K, KP>(hleft, e, Hp, F, S, gop2);
         hleft = h_sh; e_out = e; h_out = Hp[K - 1];
       };
       auto capture = [&](int half, int idx, int drift) {
@@ -588,7 +615,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         int rows = MM16G_MIN_ROWS, bufoff = L.zero + 32;
         if (real) {
           meta = meta_next;
-          if (i + 1 < n_i) meta_next = p.tp_meta[warp + (i + 1) * W];
+          if (i + 1 < n_i) meta_next = p.tp_meta[pbase + (i + 1) * W];
           rows = mm16g_rows(meta.x, meta.y);
           const int b = i % 3;
           bufoff = tbuf0 + b * p.tp_stride;
@@ -617,7 +644,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         __syncwarp();
         if (lane == 0 && i + 2 < n_i) {
           const int b2 = (i + 2) % 3;
-          bulk_load(smem + tbuf0 + b2 * p.tp_stride, p.tp_codes + (long long)(warp + (i + 2) * W) * p.tp_stride, p.tp_stride, &bar[b2]);
+          bulk_load(smem + tbuf0 + b2 * p.tp_stride, p.tp_codes + (long long)(pbase + (i + 2) * W) * p.tp_stride, p.tp_stride, &bar[b2]);
         }
         // steady state
         int s = MM16G_MIN_ROWS;
@@ -643,9 +670,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         const int s = wres[2 * w], i = wres[2 * w + 1];
         if (i != INT_MAX && (s > bs || (s == bs && i < bi))) { bs = s; bi = i; }
       }
-      const bool hit = bi != INT_MAX && bs > p.seed;
-      p.best_score[qi] = hit ? bs : p.seed;
-      p.best_idx[qi] = hit ? bi : -1;
+      if (bi != INT_MAX) atomicMax(p.best_key + qi, best_key_pack(bs, bi));
     }
   }
 }

@@ -153,7 +153,7 @@ def reference_arm(args, rank):
             "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": arm["threads"], "kind": arm["kind"], "sample": sample},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "projected_full_job_s": float(sum(map(len, queries))) * float(sum(map(len, targets))) / (gcups * 1e9)}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cuda_arm(args, rank, world, local_rank):
@@ -285,12 +285,26 @@ def cuda_arm(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": cells / sec / 1e9, "unit": "GCUPS", "cores": arm["threads"], "kind": arm["kind"],
                                     "sample": "first %d of %d queries x all %d targets (%.2e cells, %.1f s)" % (arm["n"], len(queries), len(targets), cells, sec),
                                     "matches_gpu": bool((bs == gpu_score[:arm["n"]]).all() and (bi == gpu_idx[:arm["n"]]).all())}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else a library prints (e.g. NCCL's version
+    banner) was redirected to stderr in main()"""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                       # stray prints of native libraries go to stderr
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -245,7 +245,7 @@ template <int K>
 static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsigned char *const *t1s, const int *l1s,
                         const unsigned char *const *t2s, const int *l2s, int alpha, const int *M, int go, int ge,
                         int *sc1_out, int *sc2_out) {
-  constexpr int V = (K % 4 == 0) ? 4 : 2, P = 32 * K;
+  constexpr int KP = StripCfg<K>::KP, V = StripCfg<K>::V, P = StripCfg<K>::P;
   const int a1 = alpha + 1, ncodes = a1 * a1;
   std::vector<int> mext((size_t)a1 * a1, 0);
   for (int x = 0; x < alpha; ++x) for (int y = 0; y < alpha; ++y) mext[x * a1 + y] = M[x * alpha + y];
@@ -255,8 +255,8 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
   for (int idx = 0; idx < ncodes * P; ++idx) {
     const int code = idx / P, pos = idx - code * P;
     const int j = pos % V, it = pos / V, t = it & 31, i = it >> 5;
-    const int c = t * K + i * V + j;
-    const int qa = qcodes[c] * a1;
+    const int k = i * V + j;
+    const int qa = (k < K ? (int)qcodes[t * K + k] : a1 - 1) * a1;
     const int a = code / a1, b = code - a * a1;
     lut[idx] = b16::addend(mext[qa + a] - 2 * ge, mext[qa + b] - 2 * ge);
   }
@@ -275,7 +275,7 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
   const uint32_t gop2 = p16::pack(go - ge, go - ge);
   const uint32_t Hc = b16::biased(go + ge, go + ge), Ec = b16::biased(2 * go, 2 * go), H00 = b16::biased(2 * ge, 2 * ge);
   const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;
-  uint32_t Hp[32][K], F[32][K], S[K], hleft[32], h_out[32], e_out[32], hl_init[32];
+  uint32_t Hp[32][K], F[32][K], S[KP], hleft[32], h_out[32], e_out[32], hl_init[32];
   int tb_off[32];
   for (int t = 0; t < 32; ++t) {
     for (int k = 0; k < K; ++k) { Hp[t][k] = b16::biased(0, 0); F[t][k] = b16::biased(0, 0); }
@@ -294,9 +294,9 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
     for (int t = 0; t < 32; ++t) {
       const int code = sm.at(tb_off[t] + s);
       if (code >= ncodes) throw 1;
-      load_S<K>(&lut[(size_t)code * P], t, S);
+      load_S<KP>(&lut[(size_t)code * P], t, S);
       uint32_t e = e_sh[t];
-      mm16d_row<K>(hleft[t], e, Hp[t], F[t], S, gop2);
+      mm16d_row<K, KP>(hleft[t], e, Hp[t], F[t], S, gop2);
       hleft[t] = h_sh[t]; e_out[t] = e; h_out[t] = Hp[t][K - 1];
     }
   };
@@ -347,6 +347,7 @@ extern "C" int emu_mm16g(int K, const unsigned char *q, int lq, int n_pairs, con
       case 2: emu_mm16g_t<2>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
       case 4: emu_mm16g_t<4>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
       case 6: emu_mm16g_t<6>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+      case 7: emu_mm16g_t<7>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
       case 8: emu_mm16g_t<8>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
       case 10: emu_mm16g_t<10>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
       case 12: emu_mm16g_t<12>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;

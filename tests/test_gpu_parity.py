@@ -185,7 +185,7 @@ def test_score_matrix_packed_and_wf32_vs_oracle(B, oracle_port, mode):
     against the oracle; query lengths straddle every K bucket boundary"""
     rng = random.Random(77 + mode)
     queries, targets = _amplicon_set(rng, 37, 60, 180, 262)
-    for L in (1, 2, 31, 63, 64, 65, 127, 128, 129, 191, 192, 193, 256, 257, 300, 320, 321, 383, 384, 385, 500, 512):
+    for L in (1, 2, 31, 63, 64, 65, 127, 128, 129, 191, 192, 193, 223, 224, 225, 256, 257, 300, 320, 321, 383, 384, 385, 500, 512):
         queries.append(rand_dna(rng, L))
     targets += [rand_dna(rng, 2), rand_dna(rng, 3), rand_dna(rng, 85), "A" * 85]
     q = [O.encode(s) for s in queries]
@@ -336,3 +336,32 @@ def test_full_size_properties_packed_path(B):
     s1, i1 = B.best_hits(queries[:700], targets)
     s2, i2 = B.best_hits(queries[700:], targets)
     assert (np.concatenate([s1, s2]) == bs).all() and (np.concatenate([i1, i2]) == bi).all()
+
+
+def test_target_slicing_is_invisible(B, oracle_port):
+    """work items = (query, slice of the target pairs): any slicing must give the same best hits
+    (combined with a 64-bit atomicMax: higher score, then lower target index)"""
+    rng = random.Random(31)
+    targets = [rand_dna(rng, rng.randint(180, 260)) for _ in range(150)]
+    targets[120] = targets[7]                  # duplicate far apart: lands in another slice, index 7 must still win
+    targets[140] = targets[7]
+    queries = [mutate(rng, targets[rng.randrange(len(targets))], rng.randint(0, 3)) for _ in range(40)]
+    queries[0] = targets[7]
+    ref = None
+    for mode, seed in ((O.GLOBAL, -1000000), (O.GLOCAL, 0), (O.LOCAL, 0)):
+        ref = None
+        for split in (1, 2, 3, 5, 8, 0):
+            B.set_option("split", split)
+            try:
+                got = B.best_hits([s.encode() for s in queries], [s.encode() for s in targets], mode, seed)
+            finally:
+                B.set_option("split", 0)
+            if ref is None:
+                ref = got
+                q = [O.encode(s) for s in queries[:6]]
+                t = [O.encode(s) for s in targets]
+                ws, wi = oracle_port.best_hits(mode, q, t, 5, O.DNA_SCORE, -7, -1, seed)
+                assert (got[0][:6] == ws).all() and (got[1][:6] == wi).all()
+            assert (got[0] == ref[0]).all() and (got[1] == ref[1]).all(), (mode, split)
+        if mode == O.GLOBAL:
+            assert ref[1][0] == 7

@@ -154,7 +154,7 @@ def test_streaming_global_logic_vs_oracle(emu, oracle_port):
     rng = random.Random(2024)
     chk = oracle_port
     for it in range(120):
-        K = rng.choice(KS)
+        K = rng.choice(KS + [7, 7])
         lq = rng.randint(max(1, 32 * K - 70), 32 * K) if rng.random() < 0.7 else rng.randint(1, 32 * K)
         q = bytes(rng.choice([0, 1, 2, 3, 0, 1, 2, 3, 4]) for _ in range(lq))
         n_pairs = rng.choice([1, 2, 3, 4, 7])
