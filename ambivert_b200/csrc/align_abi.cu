@@ -221,10 +221,10 @@ int mm16_launch_one(int grid_cap, cudaStream_t st, const Mm16Params &p, int &lau
   return ABV_OK;
 }
 
-template <int K>
+template <int MODE, int K>
 int mm16g_launch_one(cudaStream_t st, const Mm16Params &p, int &launched) {
   const Mm16gSmem L = mm16g_smem_layout(K, p.a1, p.tp_stride);
-  auto kern = mm16g_kernel<K>;
+  auto kern = mm16g_kernel<MODE, K>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MM16_WARPS * 32, L.total));
@@ -239,18 +239,23 @@ int mm16g_launch_one(cudaStream_t st, const Mm16Params &p, int &launched) {
   return ABV_OK;
 }
 
-int mm16g_launch(int K, cudaStream_t st, const Mm16Params &p, int &launched) {
+template <int MODE>
+int mm16g_launch_mode(int K, cudaStream_t st, const Mm16Params &p, int &launched) {
   switch (K) {
-    case 2: return mm16g_launch_one<2>(st, p, launched);
-    case 4: return mm16g_launch_one<4>(st, p, launched);
-    case 6: return mm16g_launch_one<6>(st, p, launched);
-    case 7: return mm16g_launch_one<7>(st, p, launched);
-    case 8: return mm16g_launch_one<8>(st, p, launched);
-    case 10: return mm16g_launch_one<10>(st, p, launched);
-    case 12: return mm16g_launch_one<12>(st, p, launched);
-    case 16: return mm16g_launch_one<16>(st, p, launched);
+    case 2: return mm16g_launch_one<MODE, 2>(st, p, launched);
+    case 4: return mm16g_launch_one<MODE, 4>(st, p, launched);
+    case 6: return mm16g_launch_one<MODE, 6>(st, p, launched);
+    case 7: return mm16g_launch_one<MODE, 7>(st, p, launched);
+    case 8: return mm16g_launch_one<MODE, 8>(st, p, launched);
+    case 10: return mm16g_launch_one<MODE, 10>(st, p, launched);
+    case 12: return mm16g_launch_one<MODE, 12>(st, p, launched);
+    case 16: return mm16g_launch_one<MODE, 16>(st, p, launched);
   }
   return fail(ABV_ERR_ARGS, "no packed kernel for K=%d", K);
+}
+
+int mm16g_launch(int mode, int K, cudaStream_t st, const Mm16Params &p, int &launched) {
+  return mode == ABV_GLOCAL ? mm16g_launch_mode<GLOCAL>(K, st, p, launched) : mm16g_launch_mode<GLOBAL>(K, st, p, launched);
 }
 
 template <int MODE>
@@ -268,7 +273,7 @@ int mm16_launch_mode(int K, cudaStream_t st, const Mm16Params &p, int &launched)
 }
 
 int mm16_launch(int mode, int K, bool streaming, cudaStream_t st, const Mm16Params &p, int &launched) {
-  if (mode == ABV_GLOBAL && streaming) return mm16g_launch(K, st, p, launched);
+  if ((mode == ABV_GLOBAL || mode == ABV_GLOCAL) && streaming) return mm16g_launch(mode, K, st, p, launched);
   if (mode == ABV_GLOBAL) return mm16_launch_mode<GLOBAL>(K, st, p, launched);
   if (mode == ABV_LOCAL) return mm16_launch_mode<LOCAL>(K, st, p, launched);
   if (mode == ABV_GLOCAL) return mm16_launch_mode<GLOCAL>(K, st, p, launched);
@@ -317,9 +322,11 @@ int mm_validate(int mode, const char *q, const long long *q_off, int n_q, const 
   return ABV_OK;
 }
 
-// drift-normalised values carry an extra |ge| per column and row (dp_core.cuh, mm16d_row)
-bool packed_exact_streaming(int P, int max_lt, int maxabs, int ge) {
-  return (long long)(P + max_lt + 12) * (maxabs + std::abs(ge)) <= b16::LIMIT;
+// drift-normalised values carry an extra |ge| per column and row (dp_core.cuh, mm16d_row); glocal
+// keeps half the range free for its minus-infinity sentinel
+bool packed_exact_streaming(int mode, int P, int max_lt, int maxabs, int ge) {
+  if (mode != ABV_GLOBAL && mode != ABV_GLOCAL) return false;
+  return (long long)(P + max_lt + 12) * (maxabs + std::abs(ge)) <= (mode == ABV_GLOCAL ? p16::P16_LIMIT : b16::LIMIT);
 }
 
 int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int n_q,
@@ -364,7 +371,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
     if (packed_ok) {
       for (int k = 0; k < MM16_NK; ++k) {
         const int K = MM16_KS[k];
-        if (K % 2 && !(mode == ABV_GLOBAL && !g.opt.global_v1 && packed_exact_streaming(32 * K, tp_stride, maxabs, sc.ge))) continue;
+        if (K % 2 && !(!g.opt.global_v1 && packed_exact_streaming(mode, 32 * K, tp_stride, maxabs, sc.ge))) continue;
         if (32 * K >= lq) { slot = k; break; }
       }
       if (slot >= 0) {
@@ -384,7 +391,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
       double qlen = 0;
       for (int i : lists[k]) qlen += (double)(q_off[i + 1] - q_off[i]);
       abv_job::Bucket b{MM16_KS[k], (int)lists[k].size(), (int)flat.size(), qlen * (double)(t_off[n_t] - t_off[0]), nullptr, nullptr,
-                        mode == ABV_GLOBAL && !g.opt.global_v1 && packed_exact_streaming(32 * MM16_KS[k], tp_stride, maxabs, sc.ge)};
+                        !g.opt.global_v1 && packed_exact_streaming(mode, 32 * MM16_KS[k], tp_stride, maxabs, sc.ge)};
       CU(cudaEventCreate(&b.e0));
       CU(cudaEventCreate(&b.e1));
       J.buckets.push_back(b);
@@ -782,7 +789,7 @@ int abv_int_peak(int which, int iters, double *lane_ops_per_s, double *sm_clock_
   std::lock_guard<std::recursive_mutex> lk(g.mu);
   int rc;
   if ((rc = ctx_init())) return rc;
-  if (which < 0 || which > 7 || iters <= 0) return fail(ABV_ERR_ARGS, "bad microbenchmark arguments");
+  if (which < 0 || which > 8 || iters <= 0) return fail(ABV_ERR_ARGS, "bad microbenchmark arguments");
   const int threads = 256, grid = g.sms * 8;
   DevMem out;
   CU(out.alloc(sizeof(uint32_t) * (size_t)grid * threads));
@@ -795,7 +802,8 @@ int abv_int_peak(int which, int iters, double *lane_ops_per_s, double *sm_clock_
       case 4: int_peak_kernel<4><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
       case 5: int_peak_kernel<5><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
       case 6: int_peak_kernel<6><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
-      default: int_peak_kernel<7><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
+      case 7: int_peak_kernel<7><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
+      default: int_peak_kernel<8><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
     }
   };
   run(std::max(1, iters / 10));   // warm-up

@@ -17,6 +17,9 @@
 namespace abv {
 
 #define ABV_FULL 0xffffffffu
+#ifndef ABV_MINB8
+#define ABV_MINB8 4
+#endif
 
 // ---------------------------------------------------------------------------------------------
 __global__ void encode_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, long long n,
@@ -255,7 +258,7 @@ template <int K>
 struct Mm16Cfg {
   static constexpr int V = (K % 4 == 0) ? 4 : 2;     // words per shared-memory vector load
   static constexpr int P = 32 * K;                   // profile row length in words
-  static constexpr int MIN_BLOCKS = K <= 8 ? 4 : (K <= 12 ? 3 : 2);
+  static constexpr int MIN_BLOCKS = K <= 8 ? ABV_MINB8 : (K <= 12 ? 3 : 2);
   static constexpr int KP = StripCfg<K>::KP;
 };
 
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16_
 //     (one lane per step), corner captures at warp-uniform steps outside the inner loop;
 //   * three row buffers per warp; the copy for pair i+2 is issued once every lane has left pair i-1.
 struct Mm16gSmem {
-  int lut, tbuf, mbar, mext, wres, misc, zero, qcodes, total;
+  int lut, tbuf, mbar, mext, wres, misc, zero, slots, qcodes, total;
 };
 __host__ __device__ inline Mm16gSmem mm16g_smem_layout(int K, int a1, int tp_stride) {
   Mm16gSmem L;
@@ -512,13 +515,16 @@ __host__ __device__ inline Mm16gSmem mm16g_smem_layout(int K, int a1, int tp_str
   L.wres = off; off += MM16_WARPS * 2 * 4;
   L.misc = off; off += 16;
   L.zero = off; off += 64;
+  L.slots = off; off += MM16_WARPS * 4 * 4;
   L.qcodes = off; off += 32 * KP;
   L.total = (off + 15) & ~15;
   return L;
 }
 
-template <int K>
+template <int MODE, int K>
 __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g_kernel(Mm16Params p) {
+  static_assert(MODE == GLOBAL || MODE == GLOCAL, "the streaming kernel implements global and glocal");
+  constexpr bool GL = (MODE == GLOCAL);
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int KP = StripCfg<K>::KP;
   constexpr int P = StripCfg<K>::P;
@@ -533,15 +539,21 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tbuf0 = L.tbuf + warp * 3 * p.tp_stride;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.mbar) + warp * 3;
+  int *slots = reinterpret_cast<int *>(smem + L.slots) + warp * 4;       // glocal: [pair parity][half] running last-row maxima
   const int a1 = p.a1, ncodes = a1 * a1;
   const int go = p.go, ge = p.ge;
   const uint32_t gop2 = p16::pack(go - ge, go - ge);
-  const uint32_t Hc = b16::biased(go + ge, go + ge);      // H~ of the virtual row/column (see mm16d_row)
-  const uint32_t Ec = b16::biased(2 * go, 2 * go);        // E~ entering column 0, F~ entering row 0
-  const uint32_t H00 = b16::biased(2 * ge, 2 * ge);       // H~[-1][-1]
+  const uint32_t gopw = b16::addend(go - ge, go - ge), gew = b16::addend(ge, ge);
+  const uint32_t NEGb = b16::biased(p16::NEG16, p16::NEG16);
+  // values handed to column 0 by the virtual column -1 (drift-normalised, see mm16d_row):
+  //   global: H~ = go + g, E~ = 2go (global_align.c:136-140); glocal: minus infinity (glocal_align.c:119-123)
+  const uint32_t Hc = GL ? NEGb : b16::biased(go + ge, go + ge);
+  const uint32_t Ec = GL ? NEGb : b16::biased(2 * go, 2 * go);
+  const uint32_t H00 = b16::biased(2 * ge, 2 * ge);       // global: H~[-1][-1]
 
   for (int i = threadIdx.x; i < ncodes; i += blockDim.x) mext[i] = p.matrix_ext[i];
   if (threadIdx.x < 16) reinterpret_cast<uint32_t *>(smem + L.zero)[threadIdx.x] = 0u;
+  if (lane < 4) slots[lane] = INT_MIN;
   if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1); }
   mbar_fence_init();
   uint32_t phbits = 0;
@@ -570,7 +582,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
     __syncthreads();
 
     const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;
-    const uint32_t hl_init = lane ? Hc : H00;
+    const int c0 = lane * K;
     const int n_mine = pair_hi - pair_lo;                          // this item's slice of the target pairs
     const int n_i = warp < n_mine ? (n_mine - warp + W - 1) / W : 0;
     const int pbase = pair_lo + warp;                              // this warp takes pairs pbase + i*W
@@ -589,19 +601,60 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
       int prev_rows = 0;
       int pend_s1 = -1, pend_s2 = -1, pend_i1 = -1, pend_i2 = -1, pend_d1 = 0, pend_d2 = 0;
       int4 meta_next = p.tp_meta[pbase];
+      // glocal: last-row events of the previous pair that are still to come (they are spread over the
+      // lanes like the pair switches: lane t reaches row r at step r + t of the pair's own time line)
+      const int NOEV = 1 << 20;
+      int pend_e1 = NOEV, pend_e2 = NOEV, pend_r1 = 0, pend_r2 = 0;
 
-      auto step = [&](int s) {
-        uint32_t h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
-        uint32_t e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+      auto exchange = [&](uint32_t &h_sh, uint32_t &e_sh) {
+        h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
+        e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
         if (lane == 0) { h_sh = Hc; e_sh = Ec; }
+      };
+      auto row = [&](int s, uint32_t h_sh, uint32_t e_sh) {   // one ordinary row of this lane
         const int code = smem[tb_off + s];
         mm16_load_S<KP>(lut + code * P, lane, S);
         uint32_t e = e_sh;
         mm16d_row<K, KP>(hleft, e, Hp, F, S, gop2);
         hleft = h_sh; e_out = e; h_out = Hp[K - 1];
       };
-      auto capture = [&](int half, int idx, int drift) {
-        if (lane == tstar) {
+      auto body = [&](int s) {
+        uint32_t h_sh, e_sh;
+        exchange(h_sh, e_sh);
+        row(s, h_sh, e_sh);
+      };
+      // glocal, the lane is on the last target row r of a half: the forced diagonal (glocal_align.c:172-183)
+      // is what S[] holds after the row's first pass; every real query column competes for the end
+      auto last_row = [&](bool h1, bool h2, int r, int parity) {
+        if (lane > tstar) return;                                           // only padding columns
+        uint32_t m = NEGb;
+        const uint32_t d0 = b16::addend(ge * (c0 + r), ge * (c0 + r));          // undo the drift: + g*(c + r)
+        if (lane < tstar) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) m = p16::max2(m, S[k] + d0 + (uint32_t)k * gew);
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+            if (k <= kstar) m = p16::max2(m, S[k] + d0 + (uint32_t)k * gew);
+        }
+        if (h1) atomicMax(slots + 2 * parity, b16::lo(m));
+        if (h2) atomicMax(slots + 2 * parity + 1, b16::hi(m));
+      };
+      // lane t is on the last row of half h of a pair at step ev_h + t of that pair's time line
+      auto last_rows_at = [&](int s, int e1, int e2, int r1, int r2, int parity) {
+        const bool h1 = (lane == s - e1), h2 = (lane == s - e2);
+        if (h1 || h2) last_row(h1, h2, h1 ? r1 : r2, parity);
+      };
+      auto capture = [&](int half, int idx, int drift, int parity) {
+        if (GL) {
+          __syncwarp();
+          const int v = slots[2 * parity + half];
+          const int sc = max(0, v);                                      // max starts at 0 (glocal_align.c:115)
+          if (sc > wbest || (sc == wbest && idx < widx)) { wbest = sc; widx = idx; }
+          if (p.all_scores && lane == 0) p.all_scores[(long long)qi * p.n_t + idx] = sc;
+          __syncwarp();
+          if (lane == 0) slots[2 * parity + half] = INT_MIN;
+        } else if (lane == tstar) {
           const uint32_t hs = mm16_pick<K>(Hp, kstar);
           const int sc = (half ? b16::hi(hs) : b16::lo(hs)) + drift;     // undo the drift: + g*(c + r) of the corner
           if (sc > wbest || (sc == wbest && idx < widx)) { wbest = sc; widx = idx; }
@@ -622,23 +675,51 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
           mbar_wait(&bar[b], (phbits >> b) & 1u);
           phbits ^= 1u << b;
         }
+        // warp-uniform steps at which lane tstar has just finished the last row of half 1 / half 2
         const int cs1 = real ? meta.x - 1 + tstar : -1;
         const int cs2 = (real && meta.w >= 0) ? meta.y - 1 + tstar : -1;
+        // glocal: lane t is on the last row of half h at step ev_h + t
+        const int ev1 = (GL && real) ? meta.x - 1 : NOEV;
+        const int ev2 = (GL && real && meta.w >= 0) ? meta.y - 1 : NOEV;
         tb_off += prev_rows;
         const int dr1 = ge * (lq - 1 + meta.x - 1), dr2 = ge * (lq - 1 + meta.y - 1);
+        const int par = i & 1;
         // the first 32 steps: lane s switches to this pair at step s
         for (int s = 0; s < MM16G_MIN_ROWS; ++s) {
-          if (lane == s) {
+          if (GL) {
+            if (lane == s) tb_off = bufoff - lane;
+            uint32_t h_sh, e_sh;
+            exchange(h_sh, e_sh);
+            if (lane == s) {
+              // row 0 of the new pair has no dependencies: H[c][0] = S(q[c], t[0]), F = H + go
+              // (glocal_align.c:128-136); in drift form H~ = (S - 2g) + g*(2 - c)
+              const int code = smem[tb_off + s];
+              mm16_load_S<KP>(lut + code * P, lane, S);
+              const uint32_t ri0 = b16::addend(ge * (2 - c0), ge * (2 - c0)) + b16::biased(0, 0);
 #pragma unroll
-            for (int k = 0; k < K; ++k) { Hp[k] = Hc; F[k] = Ec; }
-            hleft = hl_init;
-            tb_off = bufoff - lane;
+              for (int k = 0; k < K; ++k) {
+                Hp[k] = S[k] + ri0 - (uint32_t)k * gew;
+                F[k] = Hp[k] + gopw;
+              }
+              hleft = h_sh; e_out = NEGb; h_out = Hp[K - 1];
+            } else {
+              row(s, h_sh, e_sh);
+              last_rows_at(s, pend_e1, pend_e2, pend_r1, pend_r2, par ^ 1);
+              last_rows_at(s, ev1, ev2, meta.x - 1, meta.y - 1, par);
+            }
+          } else {
+            if (lane == s) {
+#pragma unroll
+              for (int k = 0; k < K; ++k) { Hp[k] = Hc; F[k] = Ec; }
+              hleft = lane ? Hc : H00;
+              tb_off = bufoff - lane;
+            }
+            body(s);
           }
-          step(s);
-          if (s == pend_s1) capture(0, pend_i1, pend_d1);
-          if (s == pend_s2) capture(1, pend_i2, pend_d2);
-          if (s == cs1) capture(0, meta.z, dr1);
-          if (s == cs2) capture(1, meta.w, dr2);
+          if (s == pend_s1) capture(0, pend_i1, pend_d1, par ^ 1);
+          if (s == pend_s2) capture(1, pend_i2, pend_d2, par ^ 1);
+          if (s == cs1) capture(0, meta.z, dr1, par);
+          if (s == cs2) capture(1, meta.w, dr2, par);
         }
         // every lane has left pair i-1: its buffer can take pair i+2
         __syncwarp();
@@ -648,21 +729,34 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         }
         // steady state
         int s = MM16G_MIN_ROWS;
-        while (s < rows) {
-          int stop = rows;
-          if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
-          if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
-          for (; s < stop; ++s) step(s);
-          if (s - 1 == cs1) capture(0, meta.z, dr1);
-          if (s - 1 == cs2) capture(1, meta.w, dr2);
+        if (GL) {
+          const int s_chk = min(rows, max(MM16G_MIN_ROWS, min(ev1, ev2)));
+          for (; s < s_chk; ++s) body(s);                      // no lane is on a last row yet
+          for (; s < rows; ++s) {
+            body(s);
+            last_rows_at(s, ev1, ev2, meta.x - 1, meta.y - 1, par);
+            if (s == cs1) capture(0, meta.z, dr1, par);
+            if (s == cs2) capture(1, meta.w, dr2, par);
+          }
+        } else {
+          while (s < rows) {
+            int stop = rows;
+            if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
+            if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
+            for (; s < stop; ++s) body(s);
+            if (s - 1 == cs1) capture(0, meta.z, dr1, par);
+            if (s - 1 == cs2) capture(1, meta.w, dr2, par);
+          }
         }
         pend_s1 = cs1 >= rows ? cs1 - rows : -1; pend_i1 = meta.z; pend_d1 = dr1;
         pend_s2 = cs2 >= rows ? cs2 - rows : -1; pend_i2 = meta.w; pend_d2 = dr2;
+        pend_e1 = ev1 == NOEV ? NOEV : ev1 - rows; pend_r1 = meta.x - 1;
+        pend_e2 = ev2 == NOEV ? NOEV : ev2 - rows; pend_r2 = meta.y - 1;
         prev_rows = rows;
       }
     }
 
-    if (lane == tstar) { wres[2 * warp] = wbest; wres[2 * warp + 1] = widx; }
+    if (lane == (GL ? 0 : tstar)) { wres[2 * warp] = wbest; wres[2 * warp + 1] = widx; }
     __syncthreads();
     if (threadIdx.x == 0) {
       int bs = INT_MIN, bi = INT_MAX;
@@ -712,7 +806,13 @@ __global__ void int_peak_kernel(uint32_t *out, int iters, uint32_t seed) {
         a[i] = (uint32_t)h;
       } else if (WHICH == 6) { a[i] = (uint32_t)__vimax3_s32((int)a[i], (int)b[i], (int)c[i]); b[i] = (uint32_t)__vimax3_s32((int)b[i], (int)c[i], (int)a[i]);
                                c[i] = (uint32_t)__vimax3_s32((int)c[i], (int)a[i], (int)(b[i] ^ 1)); a[i] = (uint32_t)__vimax3_s32((int)a[i], (int)b[i], 65537); }
-      else {                   // packed cell with plain 32-bit adds (biased-operand variant): 5 ops
+      else if (WHICH == 8) {   // the drift-normalised packed cell of mm16g_kernel: add + max3 + 2 add-max (4 ops)
+        uint32_t dd = a[i] + c[i];
+        uint32_t h = __vimax3_s16x2(dd, b[i], c[i]);
+        b[i] = __viaddmax_s16x2(h, 0xfffafffau, b[i]);
+        c[i] = __viaddmax_s16x2(h, 0xfffafffau, c[i]);
+        a[i] = h;
+      } else {                 // packed cell with plain 32-bit adds (biased-operand variant): 5 ops
         uint32_t dd = a[i] + c[i];
         uint32_t h = __vimax3_s16x2(dd, b[i], c[i]);
         uint32_t hg = h + 0xfff8fff9u;
@@ -727,7 +827,7 @@ __global__ void int_peak_kernel(uint32_t *out, int iters, uint32_t seed) {
   for (int i = 0; i < CH; ++i) r ^= a[i] ^ b[i] ^ c[i];
   if (r == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = r;   // keeps the chains live
 }
-constexpr int INT_PEAK_OPS[8] = {4, 4, 4, 4, 5, 5, 4, 5};   // lane-ops per chain per iteration
+constexpr int INT_PEAK_OPS[9] = {4, 4, 4, 4, 5, 5, 4, 5, 4};   // lane-ops per chain per iteration
 constexpr int INT_PEAK_CHAINS = 8;
 
 }  // namespace abv

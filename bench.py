@@ -174,11 +174,12 @@ def cuda_arm(args, rank, world, local_rank):
     total_cells = float(sum(map(len, queries))) * float(sum(map(len, targets)))
 
     # measured denominator of the roofline: the instruction mix of one packed DP cell pair, register-only.
-    # global: the streaming kernel's mix (2 x 32-bit add + VIMNMX3.S16x2 + 2 x VIADDMNMX.S16x2);
-    # glocal/local: the first-generation kernel's mix (VIADD.16x2 instead of the 32-bit adds)
-    peak_which = 7 if args.mode == "global" else 4
-    peak_ops, _ = B.int_peak(peak_which, 20000)
-    peak_gcups = peak_ops / PACKED_CELL_OPS * 2 / 1e9
+    # global/glocal: the streaming kernel's mix (1 x 32-bit add + VIMNMX3.S16x2 + 2 x VIADDMNMX.S16x2 = 4 lane-ops per
+    # cell pair); local: the first-generation kernel's mix (2 x VIADD.16x2 + max3 + 2 add-max = 5 lane-ops)
+    peak_which = 8 if args.mode in ("global", "glocal") else 4
+    peak_ops = max(B.int_peak(peak_which, 20000)[0] for _ in range(6))      # best of 6: the first runs see ramping clocks
+    cell_ops = 4 if peak_which == 8 else PACKED_CELL_OPS
+    peak_gcups = peak_ops / cell_ops * 2 / 1e9
 
     def barrier():
         if world > 1:
@@ -263,9 +264,9 @@ def cuda_arm(args, rank, world, local_rank):
             K, p = dom
             avg_ms = p["ms"] / p["n"]
             achieved = p["cells"] / (avg_ms * 1e-3) / 1e9
-            roofline = {"bound": "int_alu", "kernel": ("mm16g_kernel<K=%d>" % K) if args.mode == "global" else "mm16_kernel<%s,K=%d>" % (args.mode, K), "achieved": achieved,
+            roofline = {"bound": "int_alu", "kernel": ("mm16g_kernel<%s,K=%d>" % (args.mode, K)) if args.mode in ("global", "glocal") else "mm16_kernel<%s,K=%d>" % (args.mode, K), "achieved": achieved,
                         "peak": peak_gcups, "unit": "GCUPS", "frac": achieved / peak_gcups,
-                        "peak_source": "measured in this run by abv_int_peak(%d): register-only chains of the kernel's cell mix (2 adds + VIMNMX3.S16x2 + 2 VIADDMNMX.S16x2 per cell pair = 5 lane-ops per 2 cells), %.3e lane-ops/s" % (peak_which, peak_ops),
+                        "peak_source": "measured in this run by abv_int_peak(%d): register-only chains of the kernel's cell mix (%d lane-ops per cell pair: %s + VIMNMX3.S16x2 + 2 VIADDMNMX.S16x2), %.3e lane-ops/s" % (peak_which, cell_ops, "1 add" if cell_ops == 4 else "2 adds", peak_ops),
                         "avg_launch_ms": avg_ms, "cells_per_launch": p["cells"], "share_of_step": p["ms"] / max(1e-9, sum(x["ms"] for x in prof.values())),
                         "traffic": None,
                         "hbm": {"algorithmic_bytes_per_launch": h2d + d2h, "note": "sequence + result streams; compute-bound (>4e5 cells per byte)"}}

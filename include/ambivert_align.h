@@ -206,6 +206,7 @@ int abv_get_timing(double *out, int n);
  *   which 0: IADD3 (32-bit add)            1: VIMNMX3.S16x2        2: VIADDMNMX.S16x2
  *         3: VIADD.16x2                    4: the packed DP cell mix (2 add + 1 max3 + 2 addmax)
  *         5: the 32-bit DP cell mix        6: VIMNMX3 (32-bit)     7: 32-bit add + 16x2 max mix
+ *         8: the streaming kernel's cell: 1 add + VIMNMX3.S16x2 + 2 VIADDMNMX.S16x2 (4 lane-ops per cell pair)
  */
 int abv_int_peak(int which, int iters, double *lane_ops_per_s, double *sm_clock_mhz);
 

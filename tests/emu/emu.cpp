@@ -238,10 +238,11 @@ int emu_mm16(int mode, int K, const unsigned char *q, int lq, const unsigned cha
 }
 }
 
-// ---- the streaming global kernel (mm16g_kernel): ONE warp sweeping a list of target pairs -------
+// ---- the streaming kernel (mm16g_kernel<GLOBAL|GLOCAL>): ONE warp sweeping a list of target pairs ----
 // Mirrors the control flow of the kernel: three row buffers, 32 switch steps per pair, pending corner
-// captures, the zero-symbol prefix before the first pair and the dummy pair that drains the pipeline.
-template <int K>
+// captures, the zero-symbol prefix before the first pair and the dummy pair that drains the pipeline;
+// for glocal the dependency-free row 0 at the switch step and the last-row maxima collected per lane.
+template <bool GL, int K>
 static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsigned char *const *t1s, const int *l1s,
                         const unsigned char *const *t2s, const int *l2s, int alpha, const int *M, int go, int ge,
                         int *sc1_out, int *sc2_out) {
@@ -263,7 +264,6 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
   int max_lt = 1;
   for (int i = 0; i < n_pairs; ++i) max_lt = std::max(max_lt, std::max(l1s[i], l2s[i]));
   const int stride = std::max(32, (max_lt + 15) & ~15);
-  // "shared memory": [zero 64][buf0][buf1][buf2]; anything else poisons the LUT index
   std::vector<unsigned char> sm(64 + 3 * stride, 0);
   const int zero = 0, tbuf0 = 64;
   auto fill = [&](int buf, int pi) {
@@ -272,87 +272,146 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
       sm[tbuf0 + buf * stride + r] = (unsigned char)(a * a1 + b);
     }
   };
-  const uint32_t gop2 = p16::pack(go - ge, go - ge);
-  const uint32_t Hc = b16::biased(go + ge, go + ge), Ec = b16::biased(2 * go, 2 * go), H00 = b16::biased(2 * ge, 2 * ge);
+  const uint32_t gop2 = p16::pack(go - ge, go - ge), gopw = b16::addend(go - ge, go - ge), gew = b16::addend(ge, ge);
+  const uint32_t NEGb = b16::biased(p16::NEG16, p16::NEG16);
+  const uint32_t Hc = GL ? NEGb : b16::biased(go + ge, go + ge), Ec = GL ? NEGb : b16::biased(2 * go, 2 * go);
+  const uint32_t H00 = b16::biased(2 * ge, 2 * ge);
   const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;
-  uint32_t Hp[32][K], F[32][K], S[KP], hleft[32], h_out[32], e_out[32], hl_init[32];
+  uint32_t Hp[32][K], F[32][K], S[32][KP], hleft[32], h_out[32], e_out[32];
   int tb_off[32];
+  int slots[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
   for (int t = 0; t < 32; ++t) {
     for (int k = 0; k < K; ++k) { Hp[t][k] = b16::biased(0, 0); F[t][k] = b16::biased(0, 0); }
     hleft[t] = h_out[t] = e_out[t] = b16::biased(0, 0);
-    hl_init[t] = t ? Hc : H00;
     tb_off[t] = zero + 32 - t;
   }
   const int n_i = n_pairs;
   if (n_i > 0) fill(0, 0);
   if (n_i > 1) fill(1, 1);
   int prev_rows = 0, pend_s1 = -1, pend_s2 = -1, pend_i1 = -1, pend_i2 = -1;
-  auto step = [&](int s) {
+  const int NOEV = 1 << 20;
+  int pend_e1 = NOEV, pend_e2 = NOEV, pend_r1 = 0, pend_r2 = 0;
+  auto last_row = [&](int t, int half, int r, int parity) {
+    const int c0 = t * K;
+    uint32_t m = NEGb;
+    const uint32_t d0 = b16::addend(ge * (c0 + r), ge * (c0 + r));
+    for (int k = 0; k < K; ++k)
+      if (c0 + k < lq) m = p16::max2(m, S[t][k] + d0 + (uint32_t)k * gew);
+    slots[2 * parity + half] = std::max(slots[2 * parity + half], half ? b16::hi(m) : b16::lo(m));
+  };
+  // one step of the warp; `sw` = lane that switches pair in this step (-1: none), with its new buffer;
+  // ev*/pe*: glocal last-row events of the current / previous pair (lane t fires at step ev + t)
+  auto step = [&](int s, int sw, int bufoff, int ev1, int r1, int ev2, int r2, bool with_pending, int par) {
+    if (sw >= 0) {
+      const int t = sw;
+      tb_off[t] = bufoff - t;
+      if (!GL) {
+        for (int k = 0; k < K; ++k) { Hp[t][k] = Hc; F[t][k] = Ec; }
+        hleft[t] = t ? Hc : H00;
+      }
+    }
     uint32_t h_sh[32], e_sh[32];
     for (int t = 0; t < 32; ++t) { h_sh[t] = t ? h_out[t - 1] : h_out[0]; e_sh[t] = t ? e_out[t - 1] : e_out[0]; }
     h_sh[0] = Hc; e_sh[0] = Ec;
     for (int t = 0; t < 32; ++t) {
       const int code = sm.at(tb_off[t] + s);
       if (code >= ncodes) throw 1;
-      load_S<KP>(&lut[(size_t)code * P], t, S);
+      load_S<KP>(&lut[(size_t)code * P], t, S[t]);
+      if (GL && t == sw) {
+        const int c0 = t * K;
+        const uint32_t ri0 = b16::addend(ge * (2 - c0), ge * (2 - c0)) + b16::biased(0, 0);
+        for (int k = 0; k < K; ++k) { Hp[t][k] = S[t][k] + ri0 - (uint32_t)k * gew; F[t][k] = Hp[t][k] + gopw; }
+        hleft[t] = h_sh[t]; e_out[t] = NEGb; h_out[t] = Hp[t][K - 1];
+        continue;
+      }
       uint32_t e = e_sh[t];
-      mm16d_row<K, KP>(hleft[t], e, Hp[t], F[t], S, gop2);
+      mm16d_row<K, KP>(hleft[t], e, Hp[t], F[t], S[t], gop2);
       hleft[t] = h_sh[t]; e_out[t] = e; h_out[t] = Hp[t][K - 1];
+      if (GL) {
+        if (with_pending && t == s - pend_e1) last_row(t, 0, pend_r1, par ^ 1);
+        if (with_pending && t == s - pend_e2) last_row(t, 1, pend_r2, par ^ 1);
+        if (t == s - ev1) last_row(t, 0, r1, par);
+        if (t == s - ev2) last_row(t, 1, r2, par);
+      }
     }
   };
-  auto capture = [&](int half, int idx) {
-    const uint32_t hs = Hp[tstar][kstar];
-    const int drift = ge * (lq - 1 + (half ? l2s[idx] : l1s[idx]) - 1);
-    (half ? sc2_out : sc1_out)[idx] = (half ? b16::hi(hs) : b16::lo(hs)) + drift;
+  auto capture = [&](int half, int idx, int par) {
+    if (GL) {
+      const int v = slots[2 * par + half];
+      (half ? sc2_out : sc1_out)[idx] = std::max(0, v);
+      slots[2 * par + half] = INT_MIN;
+    } else {
+      const uint32_t hs = Hp[tstar][kstar];
+      const int drift = ge * (lq - 1 + (half ? l2s[idx] : l1s[idx]) - 1);
+      (half ? sc2_out : sc1_out)[idx] = (half ? b16::hi(hs) : b16::lo(hs)) + drift;
+    }
   };
   for (int i = 0; i <= n_i; ++i) {
     const bool real = i < n_i;
     int l1 = 0, l2 = 0, has2 = 0, rows = MM16G_MIN_ROWS, bufoff = zero + 32;
     if (real) { l1 = l1s[i]; l2 = l2s[i]; has2 = l2 > 0; rows = mm16g_rows(l1, l2); bufoff = tbuf0 + (i % 3) * stride; }
     const int cs1 = real ? l1 - 1 + tstar : -1, cs2 = (real && has2) ? l2 - 1 + tstar : -1;
+    const int ev1 = (GL && real) ? l1 - 1 : NOEV, ev2 = (GL && real && has2) ? l2 - 1 : NOEV;
     for (int t = 0; t < 32; ++t) tb_off[t] += prev_rows;
+    const int par = i & 1;
     for (int s = 0; s < MM16G_MIN_ROWS; ++s) {
-      const int t = s;
-      for (int k = 0; k < K; ++k) { Hp[t][k] = Hc; F[t][k] = Ec; }
-      hleft[t] = hl_init[t];
-      tb_off[t] = bufoff - t;
-      step(s);
-      if (s == pend_s1) capture(0, pend_i1);
-      if (s == pend_s2) capture(1, pend_i2);
-      if (s == cs1) capture(0, i);
-      if (s == cs2) capture(1, i);
+      step(s, s, bufoff, ev1, l1 - 1, ev2, l2 - 1, true, par);
+      if (s == pend_s1) capture(0, pend_i1, par ^ 1);
+      if (s == pend_s2) capture(1, pend_i2, par ^ 1);
+      if (s == cs1) capture(0, i, par);
+      if (s == cs2) capture(1, i, par);
     }
     if (i + 2 < n_i) fill((i + 2) % 3, i + 2);
     int s = MM16G_MIN_ROWS;
-    while (s < rows) {
-      int stop = rows;
-      if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
-      if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
-      for (; s < stop; ++s) step(s);
-      if (s - 1 == cs1) capture(0, i);
-      if (s - 1 == cs2) capture(1, i);
+    if (GL) {
+      const int s_chk = std::min(rows, std::max(MM16G_MIN_ROWS, std::min(ev1, ev2)));
+      for (; s < s_chk; ++s) step(s, -1, 0, NOEV, 0, NOEV, 0, false, par);
+      for (; s < rows; ++s) {
+        step(s, -1, 0, ev1, l1 - 1, ev2, l2 - 1, false, par);
+        if (s == cs1) capture(0, i, par);
+        if (s == cs2) capture(1, i, par);
+      }
+    } else {
+      while (s < rows) {
+        int stop = rows;
+        if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
+        if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
+        for (; s < stop; ++s) step(s, -1, 0, NOEV, 0, NOEV, 0, false, par);
+        if (s - 1 == cs1) capture(0, i, par);
+        if (s - 1 == cs2) capture(1, i, par);
+      }
     }
     pend_s1 = cs1 >= rows ? cs1 - rows : -1; pend_i1 = i;
     pend_s2 = cs2 >= rows ? cs2 - rows : -1; pend_i2 = i;
+    pend_e1 = ev1 == NOEV ? NOEV : ev1 - rows; pend_r1 = l1 - 1;
+    pend_e2 = ev2 == NOEV ? NOEV : ev2 - rows; pend_r2 = l2 - 1;
     prev_rows = rows;
   }
 }
 
-extern "C" int emu_mm16g(int K, const unsigned char *q, int lq, int n_pairs, const unsigned char *const *t1s, const int *l1s,
+template <bool GL>
+static int emu_mm16g_k(int K, const unsigned char *q, int lq, int n_pairs, const unsigned char *const *t1s, const int *l1s,
+                       const unsigned char *const *t2s, const int *l2s, int alpha, const int *M, int go, int ge, int *sc1, int *sc2) {
+  switch (K) {
+    case 2: emu_mm16g_t<GL, 2>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 4: emu_mm16g_t<GL, 4>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 6: emu_mm16g_t<GL, 6>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 7: emu_mm16g_t<GL, 7>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 8: emu_mm16g_t<GL, 8>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 10: emu_mm16g_t<GL, 10>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 12: emu_mm16g_t<GL, 12>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 16: emu_mm16g_t<GL, 16>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+  }
+  return -1;
+}
+
+extern "C" int emu_mm16g(int mode, int K, const unsigned char *q, int lq, int n_pairs, const unsigned char *const *t1s, const int *l1s,
                          const unsigned char *const *t2s, const int *l2s, int alpha, const int *M, int go, int ge,
                          int *sc1, int *sc2) {
   if (32 * K < lq) return -1;
   try {
-    switch (K) {
-      case 2: emu_mm16g_t<2>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-      case 4: emu_mm16g_t<4>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-      case 6: emu_mm16g_t<6>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-      case 7: emu_mm16g_t<7>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-      case 8: emu_mm16g_t<8>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-      case 10: emu_mm16g_t<10>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-      case 12: emu_mm16g_t<12>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-      case 16: emu_mm16g_t<16>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-    }
+    if (mode == GLOBAL) return emu_mm16g_k<false>(K, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2);
+    if (mode == GLOCAL) return emu_mm16g_k<true>(K, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2);
   } catch (...) { return -2; }   // an out-of-range symbol read: a pointer bookkeeping error
   return -1;
 }

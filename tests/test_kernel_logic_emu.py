@@ -148,17 +148,22 @@ def test_packed_logic_vs_oracle(emu, oracle_port):
             assert s2 == chk.align_raw(m, q, t2, alpha, M, go, ge)[0], (it, m, K, lq, len(t1), len(t2))
 
 
-def test_streaming_global_logic_vs_oracle(emu, oracle_port):
-    """mm16g_kernel's pipeline: pairs streaming back to back through the lanes, biased operands,
-    pending corner captures, tiny targets (< 32 rows), single (unpaired) last target"""
-    rng = random.Random(2024)
+@pytest.mark.parametrize("mode", [O.GLOBAL, O.GLOCAL])
+def test_streaming_logic_vs_oracle(emu, oracle_port, mode):
+    """mm16g_kernel's pipeline: pairs streaming back to back through the lanes, drift-normalised biased
+    operands, pending corner captures, tiny targets (< 32 rows), single (unpaired) last target; for
+    glocal the dependency-free first row and the last-row maxima collected lane by lane"""
+    rng = random.Random(2024 + mode)
     chk = oracle_port
-    for it in range(120):
+    lmin = 2 if mode == O.GLOCAL else 1
+    for it in range(150):
         K = rng.choice(KS + [7, 7])
         lq = rng.randint(max(1, 32 * K - 70), 32 * K) if rng.random() < 0.7 else rng.randint(1, 32 * K)
         q = bytes(rng.choice([0, 1, 2, 3, 0, 1, 2, 3, 4]) for _ in range(lq))
         n_pairs = rng.choice([1, 2, 3, 4, 7])
-        lens = sorted([rng.choice([1, 2, 5, 31, 32, 33, rng.randint(1, 300), rng.randint(150, 300)]) for _ in range(2 * n_pairs)], reverse=True)
+        lens = sorted([rng.choice([lmin, 2, 5, 31, 32, 33, rng.randint(lmin, 300), rng.randint(150, 300)]) for _ in range(2 * n_pairs)], reverse=True)
+        if rng.random() < 0.3:
+            lens[1] = lens[0]                                # equal lengths: both halves end on the same row
         if rng.random() < 0.5:
             lens[-1] = 0                                     # odd number of targets: the last pair is single
         targets = []
@@ -184,11 +189,11 @@ def test_streaming_global_logic_vs_oracle(emu, oracle_port):
         l2 = np.array([len(x) for x in t2], np.int32)
         s1 = np.full(n_pairs, -99999, np.int32)
         s2 = np.full(n_pairs, -99999, np.int32)
-        rc = emu.emu_mm16g(C.c_int(K), q, C.c_int(lq), C.c_int(n_pairs), arr(t1), l1.ctypes.data_as(C.c_void_p), arr(t2),
+        rc = emu.emu_mm16g(C.c_int(mode), C.c_int(K), q, C.c_int(lq), C.c_int(n_pairs), arr(t1), l1.ctypes.data_as(C.c_void_p), arr(t2),
                            l2.ctypes.data_as(C.c_void_p), C.c_int(5), M.ctypes.data_as(C.c_void_p), C.c_int(go), C.c_int(ge),
                            s1.ctypes.data_as(C.c_void_p), s2.ctypes.data_as(C.c_void_p))
         assert rc == 0, (it, rc)
         for i in range(n_pairs):
-            assert s1[i] == chk.align_raw(O.GLOBAL, q, t1[i], 5, M, go, ge)[0], (it, K, lq, i, list(l1), list(l2))
+            assert s1[i] == chk.align_raw(mode, q, t1[i], 5, M, go, ge)[0], (it, K, lq, i, list(l1), list(l2), go, ge)
             if len(t2[i]):
-                assert s2[i] == chk.align_raw(O.GLOBAL, q, t2[i], 5, M, go, ge)[0], (it, K, lq, i, list(l1), list(l2))
+                assert s2[i] == chk.align_raw(mode, q, t2[i], 5, M, go, ge)[0], (it, K, lq, i, list(l1), list(l2), go, ge)
