@@ -95,3 +95,24 @@ def read_pairs(n_pairs=1000000, read_len=150, seed=0xA3B1, p_sub=0.005, p_n=0.00
         fwd.append(f.tobytes())
         rev.append(reverse_complement(r.tobytes()))
     return fwd, rev
+
+
+def read_pairs_packed(n_pairs=1000000, read_len=150, seed=0xA3B1, p_sub=0.005, p_n=0.001, p_unrelated=0.02):
+    """the read-pair workload of read_pairs() generated with array operations and returned already
+    packed for the C ABI: ((fwd_buffer, offsets), (rev_buffer, offsets)), every read `read_len` long.
+    (Same distribution, different random stream: use read_pairs() where golden results are pinned.)"""
+    rng = np.random.default_rng(seed)
+    max_len = 2 * read_len - 20
+    lens = rng.integers(read_len + 20, max_len + 1, n_pairs)
+    amp = _ACGT[rng.integers(0, 4, (n_pairs, max_len), dtype=np.uint8)]
+    fwd = amp[:, :read_len].copy()
+    cols = (lens - read_len)[:, None] + np.arange(read_len)[None, :]
+    rev = np.take_along_axis(amp, cols, axis=1)                      # last read_len bases of each amplicon (plus strand)
+    unrelated = rng.random(n_pairs) < p_unrelated
+    rev[unrelated] = _ACGT[rng.integers(0, 4, (int(unrelated.sum()), read_len), dtype=np.uint8)]
+    for a in (fwd, rev):
+        sub = rng.random(a.shape) < p_sub
+        a[sub] = _ACGT[rng.integers(0, 4, int(sub.sum()), dtype=np.uint8)]
+        a[rng.random(a.shape) < p_n] = ord("N")
+    off = np.arange(n_pairs + 1, dtype=np.int64) * read_len
+    return (np.ascontiguousarray(fwd).reshape(-1), off), (np.ascontiguousarray(rev).reshape(-1), off.copy())

@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--targets", type=int, default=2000)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work of one cpu_baseline sample / reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--merge-pairs", type=int, default=1000000, help="read pairs of the secondary overlap-merge measurement (0 = skip)")
     return ap.parse_args()
 
 
@@ -154,6 +155,28 @@ def reference_arm(args, rank):
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "projected_full_job_s": float(sum(map(len, queries))) * float(sum(map(len, targets))) / (gcups * 1e9)}
     emit(line)
+
+
+def merge_measurement(n_pairs):
+    """secondary: BASELINE.json configs[1], the overlap merge of unique F/R read pairs -- one batched local
+    alignment WITH traceback per pair (ambivert.py:320-328), host buffers in, scores + fragment lists out"""
+    from ambivert_b200 import batch as B, synth
+    a, b = synth.read_pairs_packed(n_pairs)
+    B.align_pairs((a[0][:150 * 1000], a[1][:1001]), (b[0][:150 * 1000], b[1][:1001]), B.LOCAL)      # warm-up
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        sc, st, cn, fr = B.align_pairs(a, b, B.LOCAL)
+        wall = time.perf_counter() - t0
+        tm = B.timing()
+        if best is None or wall < best[0]:
+            best = (wall, tm, int(fr.shape[0]), int((cn > 0).sum()))
+    wall, tm, nfr, naligned = best
+    return {"workload": "overlap merge: %d unique 150 bp F/R read pairs, local alignment + traceback (BASELINE.json configs[1])" % n_pairs,
+            "cells": tm["cells"], "kernel_ms": tm["kernel_ms"], "gcups_kernel": tm["cells"] / tm["kernel_ms"] / 1e6,
+            "e2e_s": wall, "gcups_e2e": tm["cells"] / wall / 1e9, "pairs_per_s_e2e": n_pairs / wall,
+            "h2d_bytes": tm["h2d_bytes"], "d2h_bytes": tm["d2h_bytes"], "fragments": nfr, "pairs_with_alignment": naligned,
+            "kernel": "wf32_kernel<local,trace>", "timing": "best of 3 calls of abv_align_pairs (CUDA events inside the library for the kernel)"}
 
 
 def cuda_arm(args, rank, world, local_rank):
@@ -280,6 +303,8 @@ def cuda_arm(args, rank, world, local_rank):
                 "e2e": {"value": total_cells * args.steps / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "s_per_step": e2e_s / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+        if world == 1 and args.merge_pairs > 0:
+            line["merge"] = merge_measurement(args.merge_pairs)
         if world == 1 and not args.no_cpu_baseline:
             arm = cpu_arm(queries, targets, mode, args.cpu_seconds)
             sec, cells, bs, bi = arm["run"](queries[:arm["n"]])

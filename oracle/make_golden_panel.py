@@ -33,7 +33,10 @@ def panel_inputs():
 
 
 def pair_inputs():
-    return synth.read_pairs(PAIRS["n_pairs"], seed=PAIRS["seed"])
+    """(forward read, reverse read brought to the forward strand) -- what merge_overlaps hands to the
+    local aligner after its reverse_complement (ambivert.py:321-323)"""
+    fwd, rev = synth.read_pairs(PAIRS["n_pairs"], seed=PAIRS["seed"])
+    return fwd, [synth.reverse_complement(r) for r in rev]
 
 
 def digest(seqs):
