@@ -257,12 +257,6 @@ constexpr int P16_LIMIT = 8000;
 // with K/V vector loads of V words; chunk i of lane t sits at word (i*32 + t)*V, so the 8 (V=4)
 // or 16 (V=2) lanes of one shared-memory phase touch 32 consecutive banks whatever symbol each
 // lane is looking up (the row stride 32*K words is a multiple of 32 banks).
-template <int K, int V>
-ABV_HD int lut_pos(int c) {   // c = t*K + k
-  int t = c / K, k = c % K;
-  return ((k / V) * 32 + t) * V + (k % V);
-}
-
 // One row of one lane of the packed kernel, plain Gotoh form (5 packed ops per cell pair):
 //   d   : in  H[c0-1][r-1]                          (diag of the lane's first column)
 //   e   : in  E[r] entering c0; out E[r] leaving the strip

@@ -365,3 +365,24 @@ def test_target_slicing_is_invisible(B, oracle_port):
             assert (got[0] == ref[0]).all() and (got[1] == ref[1]).all(), (mode, split)
         if mode == O.GLOBAL:
             assert ref[1][0] == 7
+
+
+def test_legacy_abi_is_thread_safe(A, oracle_port):
+    """the reference calls the library from multiprocessing.dummy worker threads with the GIL released
+    (ambivert.py:474-476): concurrent legacy calls must each get their own correct answer"""
+    from multiprocessing.dummy import Pool
+    rng = random.Random(8)
+    refs = [rand_dna(rng, rng.randint(80, 240)) for _ in range(12)]
+    jobs = []
+    for i in range(96):
+        t = refs[rng.randrange(len(refs))]
+        jobs.append((mutate(rng, t, rng.randint(0, 4)), t, rng.choice([O.GLOBAL, O.LOCAL])))
+
+    def run(job):
+        q, t, mode = job
+        return legacy(A, mode, q.encode(), t.encode())
+    pool = Pool(8)
+    got = pool.map(run, jobs)
+    pool.close()
+    for (q, t, mode), g in zip(jobs, got):
+        assert g == oracle_port.align(mode, q.encode(), t.encode())
