@@ -17,6 +17,10 @@
 namespace abv {
 
 #define ABV_FULL 0xffffffffu
+#ifndef ABV_UNROLL
+#define ABV_UNROLL 8
+#endif
+constexpr int kHotUnroll = ABV_UNROLL;   // steps of the steady-state loop unrolled together
 #ifndef ABV_MINB8
 #define ABV_MINB8 3   // measured on B200: 3 CTAs (24 warps, <= 85 registers) beat 4 (32 warps, 64 registers) by 4 %; 2 and 5 are slower
 #endif
@@ -743,6 +747,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
             int stop = rows;
             if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
             if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
+#pragma unroll kHotUnroll
             for (; s < stop; ++s) body(s);
             if (s - 1 == cs1) capture(0, meta.z, dr1, par);
             if (s - 1 == cs2) capture(1, meta.w, dr2, par);
