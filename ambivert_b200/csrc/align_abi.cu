@@ -81,6 +81,50 @@ int ctx_init() {
   return ABV_OK;
 }
 
+// Device allocations go through a small process-wide cache: cudaMalloc/cudaFree cost up to ~100 ms
+// per job on a busy box (cudaFree synchronises the device), which showed up as end-to-end time.  Freed
+// blocks are kept (up to a byte budget) and handed out again to requests of a similar size.  All callers
+// hold g.mu, and every user of a block has synchronised its stream before the block is released.
+struct DevCache {
+  struct Block { void *p; size_t bytes; };
+  std::vector<Block> free_blocks;
+  size_t cached_bytes = 0;
+  size_t budget = (size_t)8 << 30;
+  cudaError_t get(size_t n, void **out, size_t *got) {
+    int best = -1;
+    for (int i = 0; i < (int)free_blocks.size(); ++i)
+      if (free_blocks[i].bytes >= n && free_blocks[i].bytes <= 2 * n + 4096 && (best < 0 || free_blocks[i].bytes < free_blocks[best].bytes)) best = i;
+    if (best >= 0) {
+      *out = free_blocks[best].p; *got = free_blocks[best].bytes;
+      cached_bytes -= free_blocks[best].bytes;
+      free_blocks.erase(free_blocks.begin() + best);
+      return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(out, n);
+    if (e != cudaSuccess && !free_blocks.empty()) {   // out of memory: drop the cache and retry once
+      cudaGetLastError();
+      trim(0);
+      e = cudaMalloc(out, n);
+    }
+    *got = n;
+    return e;
+  }
+  void put(void *p, size_t bytes) {
+    if (bytes > budget / 2) { cudaFree(p); return; }
+    free_blocks.push_back({p, bytes});
+    cached_bytes += bytes;
+    if (cached_bytes > budget) trim(budget / 2);
+  }
+  void trim(size_t keep) {
+    while (!free_blocks.empty() && cached_bytes > keep) {
+      cudaFree(free_blocks.front().p);
+      cached_bytes -= free_blocks.front().bytes;
+      free_blocks.erase(free_blocks.begin());
+    }
+  }
+};
+DevCache g_cache;
+
 // RAII device allocation
 struct DevMem {
   void *p = nullptr;
@@ -89,13 +133,12 @@ struct DevMem {
   DevMem(const DevMem &) = delete;
   DevMem &operator=(const DevMem &) = delete;
   ~DevMem() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  void release() { if (p) g_cache.put(p, bytes); p = nullptr; bytes = 0; }
   cudaError_t alloc(size_t n) {
     release();
     if (n == 0) n = 16;
-    cudaError_t e = cudaMalloc(&p, n);
-    if (e == cudaSuccess) bytes = n;
-    return e;
+    n = (n + 255) & ~(size_t)255;
+    return g_cache.get(n, &p, &bytes);
   }
   template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
@@ -575,6 +618,7 @@ int abv_set_option(const char *key, int value) {
   if (!key) return fail(ABV_ERR_ARGS, "NULL key");
   if (!strcmp(key, "path")) { if (value < 0 || value > 2) return fail(ABV_ERR_ARGS, "bad path"); g.opt.path = value; return ABV_OK; }
   if (!strcmp(key, "wf32_blocks_per_sm")) { g.opt.wf32_blocks_per_sm = std::max(1, std::min(value, 8)); return ABV_OK; }
+  if (!strcmp(key, "cache_mb")) { g_cache.budget = (size_t)std::max(0, value) << 20; g_cache.trim(g_cache.budget); return ABV_OK; }
   if (!strcmp(key, "split")) { g.opt.split = std::max(0, std::min(value, 64)); return ABV_OK; }
   if (!strcmp(key, "global_v1")) { g.opt.global_v1 = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "mm16_blocks_per_sm")) { g.opt.mm16_blocks_per_sm = std::max(0, std::min(value, 8)); return ABV_OK; }
