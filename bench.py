@@ -157,6 +157,33 @@ def reference_arm(args, rank):
     emit(line)
 
 
+def ncu_traffic(mode, K):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this workload, from the
+    committed ncu capture (profiles/traffic.json); None if that kernel/workload was not captured"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get("mm16g_kernel<%s,K=%d>" % (mode, K))
+    except (OSError, ValueError):
+        return None
+
+
+def hbm_info(cells, n_q, n_t, total_cells, io_bytes_step, avg_ms):
+    """the sequence and result streams of the dominant launch against the measured HBM peak: for information,
+    the path is compute-bound (hundreds of thousands of cells per byte)"""
+    alg = io_bytes_step * cells / total_cells
+    peak = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = json.load(f).get("hbm_gbs")
+    except (OSError, ValueError):
+        pass
+    gbs = alg / (avg_ms * 1e-3) / 1e9
+    return {"algorithmic_bytes_per_launch": alg, "achieved_gbs": gbs, "peak_gbs": peak if peak else 6650.0,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peak else "fallback of B200_PROFILING.md",
+            "frac": gbs / (peak if peak else 6650.0), "cells_per_byte": cells / alg,
+            "note": "sequence + result streams; the kernel is bound by the integer/DPX pipe, not by HBM"}
+
+
 def merge_measurement(n_pairs):
     """secondary: BASELINE.json configs[1], the overlap merge of unique F/R read pairs -- one batched local
     alignment WITH traceback per pair (ambivert.py:320-328), host buffers in, scores + fragment lists out"""
@@ -291,8 +318,8 @@ def cuda_arm(args, rank, world, local_rank):
                         "peak": peak_gcups, "unit": "GCUPS", "frac": achieved / peak_gcups,
                         "peak_source": "measured in this run by abv_int_peak(%d): register-only chains of the kernel's cell mix (%d lane-ops per cell pair: %s + VIMNMX3.S16x2 + 2 VIADDMNMX.S16x2), %.3e lane-ops/s" % (peak_which, cell_ops, "1 add" if cell_ops == 4 else "2 adds", peak_ops),
                         "avg_launch_ms": avg_ms, "cells_per_launch": p["cells"], "share_of_step": p["ms"] / max(1e-9, sum(x["ms"] for x in prof.values())),
-                        "traffic": None,
-                        "hbm": {"algorithmic_bytes_per_launch": h2d + d2h, "note": "sequence + result streams; compute-bound (>4e5 cells per byte)"}}
+                        "traffic": ncu_traffic(args.mode, K),
+                        "hbm": hbm_info(p["cells"], p["queries"], len(targets), total_cells, h2d + d2h, avg_ms)}
         line = {"metric": "hashtable-build alignment throughput", "value": value, "unit": "GCUPS", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "s16x2 (int32-exact)", "data": "synthetic",
