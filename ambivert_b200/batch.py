@@ -43,6 +43,10 @@ _lib.abv_job_free.argtypes = [_vp]
 _lib.abv_job_free.restype = None
 _lib.abv_align_pairs.argtypes = [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int,
                                  _vp, _vp, _vp, _vp, C.c_longlong, _vp]
+_lib.abv_gapped_pairs.argtypes = [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int,
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, _vp]
+_lib.abv_merge_pairs.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int,
+                                 _vp, _vp, _vp, _vp, C.c_longlong, _vp]
 _lib.abv_get_timing.argtypes = [_vp, C.c_int]
 _lib.abv_int_peak.argtypes = [C.c_int, C.c_int, _vp, _vp]
 
@@ -219,6 +223,46 @@ def align_pairs(seqs_a, seqs_b, mode, alpha_len=DNA_MAP[0], map256=DNA_MAP[1], m
         _check(rc)
         return scores, start, count, frags[:total.value]
     _check(rc)
+
+
+def gapped_pairs(seqs_a, seqs_b, mode, alpha_len=DNA_MAP[0], map256=DNA_MAP[1], matrix=DNA_SCORE,
+                 gap_open=GAP_OPEN, gap_extend=GAP_EXTEND):
+    """One-to-one alignments returned as gapped rows built on the device (ambivert.py:95-111, :136-152).
+    -> (scores, status, start_a, start_b, out_off int64[n+1], rows_a uint8[total], rows_b uint8[total])"""
+    a, ao = pack(seqs_a)
+    b, bo = pack(seqs_b)
+    n = len(ao) - 1
+    assert len(bo) - 1 == n
+    mp, m = _scoring(alpha_len, map256, matrix)
+    scores, status = np.empty(n, np.int32), np.empty(n, np.int32)
+    sa, sb = np.empty(n, np.int32), np.empty(n, np.int32)
+    off = np.zeros(n + 1, np.int64)
+    cap = int(a.size + b.size) + 16          # a gapped row is never longer than both sequences together
+    ra, rb = np.empty(cap, np.uint8), np.empty(cap, np.uint8)
+    total = C.c_longlong(0)
+    _check(_lib.abv_gapped_pairs(mode, _ptr(a), _ptr(ao), _ptr(b), _ptr(bo), n, alpha_len, _ptr(mp), _ptr(m), gap_open, gap_extend,
+                                 _ptr(scores), _ptr(status), _ptr(sa), _ptr(sb), _ptr(off), _ptr(ra), _ptr(rb), cap, C.byref(total)))
+    return scores, status, sa, sb, off, ra[:total.value], rb[:total.value]
+
+
+def merge_pairs(fwds, revs, minimum_overlap=10, alpha_len=DNA_MAP[0], map256=DNA_MAP[1], matrix=DNA_SCORE,
+                gap_open=GAP_OPEN, gap_extend=GAP_EXTEND):
+    """Local alignment + merged read of every (forward read, reverse-complemented reverse read) pair, built on
+    the device (ambivert.py:320-327).  -> (scores, status, merged_off int64[n+1], merged uint8[total]);
+    status: 1 merged, 0 unmergable (overlap below minimum_overlap), -1 empty alignment, -2 bad base pair"""
+    a, ao = pack(fwds)
+    b, bo = pack(revs)
+    n = len(ao) - 1
+    assert len(bo) - 1 == n
+    mp, m = _scoring(alpha_len, map256, matrix)
+    scores, status = np.empty(n, np.int32), np.empty(n, np.int32)
+    off = np.zeros(n + 1, np.int64)
+    cap = int(a.size + b.size) + 16          # a merged read is never longer than both reads together
+    merged = np.empty(cap, np.uint8)
+    total = C.c_longlong(0)
+    _check(_lib.abv_merge_pairs(_ptr(a), _ptr(ao), _ptr(b), _ptr(bo), n, alpha_len, _ptr(mp), _ptr(m), gap_open, gap_extend,
+                                int(minimum_overlap), _ptr(scores), _ptr(status), _ptr(off), _ptr(merged), cap, C.byref(total)))
+    return scores, status, off, merged[:total.value]
 
 
 def fragments(k, start, count, frags):

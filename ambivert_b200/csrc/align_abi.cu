@@ -13,6 +13,8 @@
 #include <vector>
 
 #include "../../include/ambivert_align.h"
+#include <cub/device/device_scan.cuh>
+
 #include "kernels.cuh"
 
 namespace {
@@ -181,7 +183,7 @@ int check_mode_lengths(int mode, int min_la, int min_lb) {
 
 // upload a concatenated sequence set and encode it on the device
 int upload_encoded(const char *buf, const long long *off, int n, const Scoring &sc, cudaStream_t st,
-                   DevMem &d_codes, DevMem &d_off, DevMem &d_map, double &h2d_bytes) {
+                   DevMem &d_codes, DevMem &d_off, DevMem &d_map, double &h2d_bytes, DevMem *keep_raw = nullptr) {
   const long long total = n ? off[n] - off[0] : 0;
   std::vector<long long> rel(n + 1);
   for (int i = 0; i <= n; ++i) rel[i] = n ? off[i] - off[0] : 0;
@@ -205,6 +207,7 @@ int upload_encoded(const char *buf, const long long *off, int n, const Scoring &
     encode_kernel<<<blocks, 256, 0, st>>>(raw.as<uint8_t>(), d_codes.as<uint8_t>(), total, d_map.as<uint8_t>());
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
+    if (keep_raw) { keep_raw->release(); keep_raw->p = raw.p; keep_raw->bytes = raw.bytes; raw.p = nullptr; raw.bytes = 0; }
   }
   h2d_bytes += (double)total + sizeof(long long) * (n + 1) + 256;
   return ABV_OK;
@@ -730,6 +733,79 @@ int abv_score_matrix(int mode, const char *q, const long long *q_off, int n_q,
 }
 
 // -------------------------------------------------------------------------------------------------
+// One-to-one alignments with traceback, results left on the device.
+struct PairsRun {
+  DevMem a_codes, a_off, b_codes, b_off, a_raw, b_raw, map, matrix;
+  DevMem dir, tmp, border, scores, start, count, frags, counters;
+  long long pool = 0;
+  unsigned long long total = 0;
+  int max_la = 0, max_lb = 0;
+  double h2d = 0, cells = 0;
+};
+
+static int pairs_validate(int mode, const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
+                          const Scoring &sc, int &max_la, int &max_lb) {
+  int rc, min_la, min_lb;
+  if ((rc = check_scoring(sc))) return rc;
+  if ((rc = check_seqs(a, a_off, n, "sequence a", max_la, min_la))) return rc;
+  if ((rc = check_seqs(b, b_off, n, "sequence b", max_lb, min_lb))) return rc;
+  if (mode < 0 || mode > 3) return fail(ABV_ERR_ARGS, "unknown mode %d", mode);
+  if (n > 0 && (rc = check_mode_lengths(mode, min_la, min_lb))) return rc;
+  return ABV_OK;
+}
+
+// upload + encode + fill + traceback for n > 0 validated pairs; g.ev[0..2] bracket upload and kernel
+static int pairs_run(PairsRun &R, int mode, const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
+                     const Scoring &sc, long long pool_cap, bool keep_raw) {
+  int rc;
+  cudaStream_t st = g.stream;
+  CU(cudaEventRecord(g.ev[0], st));
+  if (!R.a_codes.p) {   // first attempt: the inputs are not on the device yet
+    if ((rc = upload_encoded(a, a_off, n, sc, st, R.a_codes, R.a_off, R.map, R.h2d, keep_raw ? &R.a_raw : nullptr))) return rc;
+    if ((rc = upload_encoded(b, b_off, n, sc, st, R.b_codes, R.b_off, R.map, R.h2d, keep_raw ? &R.b_raw : nullptr))) return rc;
+    CU(R.matrix.alloc(sizeof(int) * sc.alpha * sc.alpha));
+    CU(cudaMemcpyAsync(R.matrix.p, sc.matrix, sizeof(int) * sc.alpha * sc.alpha, cudaMemcpyHostToDevice, st));
+    R.cells = 0;
+    for (int i = 0; i < n; ++i) R.cells += (double)(a_off[i + 1] - a_off[i]) * (double)(b_off[i + 1] - b_off[i]);
+  }
+  const long long dwords = dir_words(R.max_la, R.max_lb);
+  const int tmp_cap = R.max_la + R.max_lb + 2;
+  const size_t per_warp = (size_t)dwords * 4 + (size_t)tmp_cap * sizeof(FragOut) + (size_t)R.max_lb * 8;
+  const int grid = wf32_grid(n, per_warp);
+  const long long warps = (long long)grid * WF32_WARPS;
+  R.pool = std::min<long long>(pool_cap, (long long)n * (R.max_la + R.max_lb + 1));
+  CU(R.dir.alloc((size_t)dwords * 4 * warps));
+  CU(R.tmp.alloc((size_t)tmp_cap * sizeof(FragOut) * warps));
+  CU(R.border.alloc((size_t)R.max_lb * 8 * warps));
+  CU(R.scores.alloc(sizeof(int) * (size_t)n));
+  CU(R.start.alloc(sizeof(long long) * (size_t)n));
+  CU(R.count.alloc(sizeof(int) * (size_t)n));
+  CU(R.frags.alloc(sizeof(FragOut) * (size_t)std::max<long long>(R.pool, 1)));
+  CU(R.counters.alloc(16));
+  CU(cudaMemsetAsync(R.counters.p, 0, 16, st));
+  CU(cudaEventRecord(g.ev[1], st));
+
+  Wf32Params p{};
+  p.a = R.a_codes.as<uint8_t>(); p.a_off = R.a_off.as<long long>();
+  p.b = R.b_codes.as<uint8_t>(); p.b_off = R.b_off.as<long long>();
+  p.n_pairs = n; p.n_t = 0; p.q_base = 0; p.q_list = nullptr;
+  p.matrix = R.matrix.as<int>(); p.alpha = sc.alpha; p.go = sc.go; p.ge = sc.ge;
+  p.scores = R.scores.as<int>(); p.score_rows_by_query = 0;
+  p.dir = R.dir.as<uint32_t>(); p.dir_words_per_warp = dwords;
+  p.frag_tmp = R.tmp.as<FragOut>(); p.frag_tmp_cap = tmp_cap;
+  p.frags = R.frags.as<FragOut>(); p.frag_cap = R.pool;
+  p.frag_total = R.counters.as<unsigned long long>() + 1;
+  p.frag_start = R.start.as<long long>(); p.frag_count = R.count.as<int>();
+  p.border = R.border.as<int>(); p.border_len = R.max_lb;
+  p.pair_counter = R.counters.as<unsigned long long>();
+  wf32_dispatch<true>(mode, grid, st, p);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(g.ev[2], st));
+  CU(cudaMemcpyAsync(&R.total, p.frag_total, sizeof R.total, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return ABV_OK;
+}
+
 int abv_align_pairs(int mode, const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
                     int alpha_len, const unsigned char *map256, const int *score_matrix,
                     int gap_open, int gap_extend,
@@ -738,12 +814,8 @@ int abv_align_pairs(int mode, const char *a, const long long *a_off, const char 
   std::lock_guard<std::recursive_mutex> lk(g.mu);
   int rc;
   Scoring sc{alpha_len, gap_open, gap_extend, map256, score_matrix};
-  if ((rc = check_scoring(sc))) return rc;
-  int max_la, min_la, max_lb, min_lb;
-  if ((rc = check_seqs(a, a_off, n, "sequence a", max_la, min_la))) return rc;
-  if ((rc = check_seqs(b, b_off, n, "sequence b", max_lb, min_lb))) return rc;
-  if (mode < 0 || mode > 3) return fail(ABV_ERR_ARGS, "unknown mode %d", mode);
-  if (n > 0 && (rc = check_mode_lengths(mode, min_la, min_lb))) return rc;
+  PairsRun R;
+  if ((rc = pairs_validate(mode, a, a_off, b, b_off, n, sc, R.max_la, R.max_lb))) return rc;
   if (frag_cap < 0 || (frag_cap > 0 && !frags)) return fail(ABV_ERR_ARGS, "bad fragment pool");
   if (frag_total) *frag_total = 0;
   if (n == 0) return ABV_OK;
@@ -751,75 +823,126 @@ int abv_align_pairs(int mode, const char *a, const long long *a_off, const char 
   if ((rc = ctx_init())) return rc;
   for (double &v : t_timing) v = 0;
   cudaStream_t st = g.stream;
-  CU(cudaEventRecord(g.ev[0], st));
-  double h2d = 0;
-  DevMem da, da_off, db, db_off, dmap, dmatrix;
-  if ((rc = upload_encoded(a, a_off, n, sc, st, da, da_off, dmap, h2d))) return rc;
-  if ((rc = upload_encoded(b, b_off, n, sc, st, db, db_off, dmap, h2d))) return rc;
-  CU(dmatrix.alloc(sizeof(int) * alpha_len * alpha_len));
-  CU(cudaMemcpyAsync(dmatrix.p, score_matrix, sizeof(int) * alpha_len * alpha_len, cudaMemcpyHostToDevice, st));
-
-  const long long dwords = dir_words(max_la, max_lb);
-  const int tmp_cap = max_la + max_lb + 2;
-  const size_t per_warp = (size_t)dwords * 4 + (size_t)tmp_cap * sizeof(FragOut) + (size_t)max_lb * 8;
-  const int grid = wf32_grid(n, per_warp);
-  const long long warps = (long long)grid * WF32_WARPS;
-  const long long pool = std::min<long long>(frag_cap, (long long)n * (max_la + max_lb + 1));
-  DevMem ddir, dtmp, dborder, dscores, dstart, dcount, dfrags, dcounters;
-  CU(ddir.alloc((size_t)dwords * 4 * warps));
-  CU(dtmp.alloc((size_t)tmp_cap * sizeof(FragOut) * warps));
-  CU(dborder.alloc((size_t)max_lb * 8 * warps));
-  CU(dscores.alloc(sizeof(int) * (size_t)n));
-  CU(dstart.alloc(sizeof(long long) * (size_t)n));
-  CU(dcount.alloc(sizeof(int) * (size_t)n));
-  CU(dfrags.alloc(sizeof(FragOut) * (size_t)std::max<long long>(pool, 1)));
-  CU(dcounters.alloc(16));
-  CU(cudaMemsetAsync(dcounters.p, 0, 16, st));
-  CU(cudaEventRecord(g.ev[1], st));
-
-  Wf32Params p{};
-  p.a = da.as<uint8_t>(); p.a_off = da_off.as<long long>();
-  p.b = db.as<uint8_t>(); p.b_off = db_off.as<long long>();
-  p.n_pairs = n; p.n_t = 0; p.q_base = 0; p.q_list = nullptr;
-  p.matrix = dmatrix.as<int>(); p.alpha = alpha_len; p.go = gap_open; p.ge = gap_extend;
-  p.scores = dscores.as<int>(); p.score_rows_by_query = 0;
-  p.dir = ddir.as<uint32_t>(); p.dir_words_per_warp = dwords;
-  p.frag_tmp = dtmp.as<FragOut>(); p.frag_tmp_cap = tmp_cap;
-  p.frags = dfrags.as<FragOut>(); p.frag_cap = pool;
-  p.frag_total = dcounters.as<unsigned long long>() + 1;
-  p.frag_start = dstart.as<long long>(); p.frag_count = dcount.as<int>();
-  p.border = dborder.as<int>(); p.border_len = max_lb;
-  p.pair_counter = dcounters.as<unsigned long long>();
-  wf32_dispatch<true>(mode, grid, st, p);
-  CU(cudaGetLastError());
-  CU(cudaEventRecord(g.ev[2], st));
-
-  unsigned long long total = 0;
-  CU(cudaMemcpyAsync(scores, dscores.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(frag_start, dstart.p, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(frag_count, dcount.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(&total, p.frag_total, sizeof total, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  if ((rc = pairs_run(R, mode, a, a_off, b, b_off, n, sc, frag_cap, false))) return rc;
+  CU(cudaMemcpyAsync(scores, R.scores.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(frag_start, R.start.p, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(frag_count, R.count.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
   double d2h = 16.0 * n + 8;
-  const long long ncopy = std::min<long long>((long long)total, pool);
+  const long long ncopy = std::min<long long>((long long)R.total, R.pool);
   if (ncopy > 0) {
-    CU(cudaMemcpyAsync(frags, dfrags.p, sizeof(FragOut) * (size_t)ncopy, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(frags, R.frags.p, sizeof(FragOut) * (size_t)ncopy, cudaMemcpyDeviceToHost, st));
     d2h += 16.0 * ncopy;
   }
   CU(cudaEventRecord(g.ev[3], st));
   CU(cudaStreamSynchronize(st));
-  if (frag_total) *frag_total = (long long)total;
+  if (frag_total) *frag_total = (long long)R.total;
   float t0 = 0, t1 = 0, t2 = 0;
   cudaEventElapsedTime(&t0, g.ev[0], g.ev[1]);
   cudaEventElapsedTime(&t1, g.ev[1], g.ev[2]);
   cudaEventElapsedTime(&t2, g.ev[2], g.ev[3]);
-  double cells = 0;
-  for (int i = 0; i < n; ++i) cells += (double)(a_off[i + 1] - a_off[i]) * (double)(b_off[i + 1] - b_off[i]);
-  t_timing[0] = t0; t_timing[1] = t1; t_timing[2] = t2; t_timing[3] = cells; t_timing[4] = 3;
-  t_timing[5] = h2d; t_timing[6] = d2h; t_timing[7] = t1;
-  if ((long long)total > frag_cap)
-    return fail(ABV_ERR_FRAG_CAP, "fragment pool of %lld entries is too small, %llu needed", frag_cap, total);
+  t_timing[0] = t0; t_timing[1] = t1; t_timing[2] = t2; t_timing[3] = R.cells; t_timing[4] = 3;
+  t_timing[5] = R.h2d; t_timing[6] = d2h; t_timing[7] = t1;
+  if ((long long)R.total > frag_cap)
+    return fail(ABV_ERR_FRAG_CAP, "fragment pool of %lld entries is too small, %llu needed", frag_cap, R.total);
   return ABV_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// The two host-side string builders that follow the aligner in the pipeline, on the device:
+//   gapped rows  (ambivert.py:95-111 / :136-152)  and  merged read (ambivert.py:324-327)
+static int assemble_impl(int what, int mode, const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
+                         int alpha_len, const unsigned char *map256, const int *score_matrix, int gap_open, int gap_extend,
+                         int minimum_overlap, int *scores, int *status, int *start_a, int *start_b,
+                         long long *out_off, char *out1, char *out2, long long out_cap, long long *out_total) {
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  int rc;
+  Scoring sc{alpha_len, gap_open, gap_extend, map256, score_matrix};
+  PairsRun R;
+  if ((rc = pairs_validate(mode, a, a_off, b, b_off, n, sc, R.max_la, R.max_lb))) return rc;
+  if (out_total) *out_total = 0;
+  if (n == 0) { if (out_off) out_off[0] = 0; return ABV_OK; }
+  if (!scores || !status || !out_off || out_cap < 0) return fail(ABV_ERR_ARGS, "NULL output");
+  if ((rc = ctx_init())) return rc;
+  for (double &v : t_timing) v = 0;
+  cudaStream_t st = g.stream;
+  long long cap = std::max<long long>(1024, 8ll * n);
+  for (int attempt = 0; attempt < 2; ++attempt) {          // the fragment pool lives on the device only
+    if ((rc = pairs_run(R, mode, a, a_off, b, b_off, n, sc, cap, true))) return rc;
+    if ((long long)R.total <= R.pool) break;
+    cap = (long long)R.total;
+  }
+  DevMem lens, offs, dstatus, dsa, dsb, dout1, dout2, scan_tmp;
+  CU(lens.alloc(sizeof(long long) * ((size_t)n + 1)));
+  CU(offs.alloc(sizeof(long long) * ((size_t)n + 1)));
+  CU(dstatus.alloc(sizeof(int) * (size_t)n));
+  CU(dsa.alloc(sizeof(int) * (size_t)n));
+  CU(dsb.alloc(sizeof(int) * (size_t)n));
+  AssembleParams q{};
+  q.what = what; q.n = n; q.min_overlap = minimum_overlap;
+  q.a = R.a_raw.as<uint8_t>(); q.a_off = R.a_off.as<long long>();
+  q.b = R.b_raw.as<uint8_t>(); q.b_off = R.b_off.as<long long>();
+  q.frags = R.frags.as<FragOut>(); q.frag_start = R.start.as<long long>(); q.frag_count = R.count.as<int>();
+  q.lens = lens.as<long long>(); q.offs = offs.as<long long>(); q.status = dstatus.as<int>();
+  q.start_a = dsa.as<int>(); q.start_b = dsb.as<int>();
+  assemble_len_kernel<<<(n + 255) / 256, 256, 0, st>>>(q);
+  CU(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, lens.as<long long>(), offs.as<long long>(), n + 1, st));
+  CU(scan_tmp.alloc(tmp_bytes));
+  CU(cub::DeviceScan::ExclusiveSum(scan_tmp.p, tmp_bytes, lens.as<long long>(), offs.as<long long>(), n + 1, st));
+  long long total = 0;
+  CU(cudaMemcpyAsync(&total, offs.as<long long>() + n, sizeof total, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (out_total) *out_total = total;
+  CU(cudaMemcpyAsync(scores, R.scores.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_off, offs.p, sizeof(long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
+  if (start_a) CU(cudaMemcpyAsync(start_a, dsa.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (start_b) CU(cudaMemcpyAsync(start_b, dsb.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  double d2h = 24.0 * n;
+  if (total > out_cap) {
+    CU(cudaMemcpyAsync(status, dstatus.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return fail(ABV_ERR_FRAG_CAP, "output buffer of %lld bytes is too small, %lld needed", out_cap, total);
+  }
+  if (total > 0) {
+    CU(dout1.alloc((size_t)total));
+    if (what == ASSEMBLE_GAPPED) CU(dout2.alloc((size_t)total));
+    q.out1 = dout1.as<uint8_t>(); q.out2 = dout2.as<uint8_t>();
+    const int wpb = 8;
+    assemble_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, st>>>(q);
+    CU(cudaGetLastError());
+    if (out1) CU(cudaMemcpyAsync(out1, dout1.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+    if (what == ASSEMBLE_GAPPED && out2) CU(cudaMemcpyAsync(out2, dout2.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+    d2h += (what == ASSEMBLE_GAPPED ? 2.0 : 1.0) * total;
+  }
+  CU(cudaMemcpyAsync(status, dstatus.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));   // after assembly: it may flag -2
+  CU(cudaEventRecord(g.ev[3], st));
+  CU(cudaStreamSynchronize(st));
+  float t0 = 0, t1 = 0, t2 = 0;
+  cudaEventElapsedTime(&t0, g.ev[0], g.ev[1]);
+  cudaEventElapsedTime(&t1, g.ev[1], g.ev[2]);
+  cudaEventElapsedTime(&t2, g.ev[2], g.ev[3]);
+  t_timing[0] = t0; t_timing[1] = t1; t_timing[2] = t2; t_timing[3] = R.cells; t_timing[4] = 6;
+  t_timing[5] = R.h2d; t_timing[6] = d2h; t_timing[7] = t1;
+  return ABV_OK;
+}
+
+int abv_merge_pairs(const char *fwd, const long long *fwd_off, const char *rev, const long long *rev_off, int n,
+                    int alpha_len, const unsigned char *map256, const int *score_matrix, int gap_open, int gap_extend,
+                    int minimum_overlap, int *scores, int *status, long long *merged_off, char *merged, long long merged_cap,
+                    long long *merged_total) {
+  if (!map256) return fail(ABV_ERR_ARGS, "abv_merge_pairs needs character input and a map");
+  return assemble_impl(ASSEMBLE_MERGE, ABV_LOCAL, fwd, fwd_off, rev, rev_off, n, alpha_len, map256, score_matrix, gap_open, gap_extend,
+                       minimum_overlap, scores, status, nullptr, nullptr, merged_off, merged, nullptr, merged_cap, merged_total);
+}
+
+int abv_gapped_pairs(int mode, const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
+                     int alpha_len, const unsigned char *map256, const int *score_matrix, int gap_open, int gap_extend,
+                     int *scores, int *status, int *start_a, int *start_b, long long *out_off, char *gapped_a, char *gapped_b,
+                     long long out_cap, long long *out_total) {
+  if (!map256) return fail(ABV_ERR_ARGS, "abv_gapped_pairs needs character input and a map");
+  return assemble_impl(ASSEMBLE_GAPPED, mode, a, a_off, b, b_off, n, alpha_len, map256, score_matrix, gap_open, gap_extend,
+                       0, scores, status, start_a, start_b, out_off, gapped_a, gapped_b, out_cap, out_total);
 }
 
 int abv_get_timing(double *out, int n) {

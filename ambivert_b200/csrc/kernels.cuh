@@ -175,6 +175,107 @@ __global__ void __launch_bounds__(WF32_WARPS * 32) wf32_kernel(Wf32Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// String assembly after the aligner, on the device:
+//   ASSEMBLE_GAPPED  the two gapped rows of an alignment, as ambivert.py:95-111 / :136-152 build them
+//   ASSEMBLE_MERGE   the merged read of a forward/reverse pair, ambivert.py:324-327:
+//                    fwd[:fwd_start] + flatten_paired_alignment(rows) + rev[rev_start + rev bases aligned:]
+//                    (flatten_paired_alignment / encode_ambiguous: sequence_utilities.py:130-169)
+enum { ASSEMBLE_GAPPED = 0, ASSEMBLE_MERGE = 1 };
+// per-pair status: 1 assembled; 0 merge skipped (aligned length < minimum_overlap: "unmergable");
+// -1 empty alignment (the reference dereferences a NULL fragment: ValueError);
+// -2 a mismatching base pair outside ACGTN (encode_ambiguous raises KeyError)
+struct AssembleParams {
+  int what, n, min_overlap;
+  const uint8_t *a; const long long *a_off;      // original characters
+  const uint8_t *b; const long long *b_off;
+  const FragOut *frags; const long long *frag_start; const int *frag_count;
+  long long *lens, *offs;                        // [n+1]
+  int *status, *start_a, *start_b;
+  uint8_t *out1, *out2;
+};
+
+__global__ void assemble_len_kernel(AssembleParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) p.lens[p.n] = 0;
+  if (i >= p.n) return;
+  const int cnt = p.frag_count[i];
+  const FragOut *f = p.frags + p.frag_start[i];
+  long long aligned = 0, b_used = 0;
+  for (int k = 0; k < cnt; ++k) {
+    aligned += f[k].hsp_len;
+    if (f[k].type != FRAG_B_GAP) b_used += f[k].hsp_len;
+  }
+  const int sa = cnt ? f[0].sa_start : 0, sb = cnt ? f[0].sb_start : 0;
+  p.start_a[i] = sa; p.start_b[i] = sb;
+  int status = 1;
+  long long len = aligned;
+  if (p.what == ASSEMBLE_MERGE) {
+    const long long lb = p.b_off[i + 1] - p.b_off[i];
+    if (cnt == 0) { status = -1; len = 0; }
+    else if (aligned < p.min_overlap) { status = 0; len = 0; }           // ambivert.py:324-325
+    else len = sa + aligned + (lb - (sb + b_used));
+  } else if (cnt == 0) status = -1;
+  p.status[i] = status;
+  p.lens[i] = len;
+}
+
+__device__ __forceinline__ int acgt_index(uint8_t c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+__device__ __forceinline__ uint8_t ascii_upper(uint8_t c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
+
+// one column of flatten_paired_alignment where neither row has a gap; 0 = KeyError in the reference
+__device__ __forceinline__ uint8_t flatten_bases(uint8_t a, uint8_t b) {
+  if (a == b) return a;
+  const uint8_t ua = ascii_upper(a), ub = ascii_upper(b);
+  if (ua == ub) return ua;
+  if (ua == 'N' || ub == 'N') return 'N';
+  const int ia = acgt_index(ua), ib = acgt_index(ub);
+  if (ia < 0 || ib < 0) return 0;
+  const char table[17] = "?MRWM?SYRS?KWYK?";       // IUPAC code of two different bases, indexed [ia*4+ib]
+  return (uint8_t)table[ia * 4 + ib];
+}
+
+__global__ void assemble_kernel(AssembleParams p) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= p.n || p.status[i] != 1) return;
+  const uint8_t *a = p.a + p.a_off[i], *b = p.b + p.b_off[i];
+  const int lb = (int)(p.b_off[i + 1] - p.b_off[i]);
+  const int cnt = p.frag_count[i];
+  const FragOut *f = p.frags + p.frag_start[i];
+  uint8_t *o1 = p.out1 + p.offs[i];
+  uint8_t *o2 = p.what == ASSEMBLE_GAPPED ? p.out2 + p.offs[i] : nullptr;
+  long long pos = 0;
+  bool bad = false;
+  if (p.what == ASSEMBLE_MERGE) {
+    const int sa = f[0].sa_start;
+    for (int j = lane; j < sa; j += 32) o1[j] = a[j];
+    pos = sa;
+  }
+  int b_end = cnt ? f[0].sb_start : 0;
+  for (int k = 0; k < cnt; ++k) {
+    const FragOut fr = f[k];
+    for (int j = lane; j < fr.hsp_len; j += 32) {
+      if (p.what == ASSEMBLE_GAPPED) {
+        o1[pos + j] = fr.type == FRAG_A_GAP ? (uint8_t)'-' : a[fr.sa_start + j];
+        o2[pos + j] = fr.type == FRAG_B_GAP ? (uint8_t)'-' : b[fr.sb_start + j];
+      } else if (fr.type == FRAG_MATCH) {
+        const uint8_t c = flatten_bases(a[fr.sa_start + j], b[fr.sb_start + j]);
+        if (c == 0) bad = true;
+        o1[pos + j] = c;
+      } else {
+        o1[pos + j] = fr.type == FRAG_A_GAP ? b[fr.sb_start + j] : a[fr.sa_start + j];   // a gap takes the other row's base
+      }
+    }
+    pos += fr.hsp_len;
+    if (fr.type != FRAG_B_GAP) b_end += fr.hsp_len;
+  }
+  if (p.what == ASSEMBLE_MERGE) {
+    for (int j = b_end + lane; j < lb; j += 32) o1[pos + (j - b_end)] = b[j];
+    if (__any_sync(ABV_FULL, bad) && lane == 0) p.status[i] = -2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // per-query selection over a score matrix: strict '>' in target order from the seed
 // (ambivert.py:478-485): first maximum wins; idx -1 when nothing beats the seed.
 __global__ void argmax_rows_kernel(const int *__restrict__ scores, int n_rows, int n_t, int seed,

@@ -19,6 +19,8 @@ import pickle
 import warnings
 from collections import defaultdict
 
+import numpy as np
+
 from . import batch as B
 
 _COMP = {ord(a): b for a, b in zip("acgtACGT-.nNUMRWSYKVHDBumrwsykvhdb", "tgcaTGCA-.nNAKYWSRMBDHVakywsrmbdhv")}
@@ -89,28 +91,25 @@ def _ascii(seqs):
 
 def batched_pairwise(seqs1, seqs2, local):
     """smith_waterman (local=True, ambivert.py:75-114) / needleman_wunsch (ambivert.py:116-155) for a
-    whole batch: -> list of (align_seq1, align_seq2, start_seq1, start_seq2)."""
+    whole batch: -> list of (align_seq1, align_seq2, start_seq1, start_seq2).  The aligner sees
+    seq2.upper() in the reference; DNA_MAP is case-insensitive, so seq2 goes in as it is and the gapped
+    rows, built on the device, keep its case as the reference's slices do."""
     for s1, s2 in zip(seqs1, seqs2):
         if "-" in s1 or "-" in s2:
             raise RuntimeError("Aligning Sequences with gaps is not supported", s1, s2)
     try:
-        sc, st, cn, fr = B.align_pairs(_ascii(seqs1), _ascii(s.upper() for s in seqs2), B.LOCAL if local else B.GLOBAL)
+        sc, status, st1, st2, off, rows1, rows2 = B.gapped_pairs(_ascii(seqs1), _ascii(seqs2), B.LOCAL if local else B.GLOBAL)
     except B.AlignError as e:
         if e.code in (B.ERR_ARGS, B.ERR_UNDEFINED):
             raise ValueError("NULL pointer access") from e     # what ctypes raises on the reference's NULL result
         raise
-    out = []
-    for k, (s1, s2) in enumerate(zip(seqs1, seqs2)):
-        frags = B.fragments(k, st, cn, fr)
-        if local:
-            if not frags:
-                raise ValueError("NULL pointer access")        # alignment.contents.align_frag.contents on an empty list
-            start1, start2 = frags[0][1], frags[0][2]
-        else:
-            start1 = start2 = 0
-        a1, a2 = gapped_strings(s1, s2, frags)
-        out.append((a1, a2, start1, start2))
-    return out
+    if local and (status < 0).any():
+        raise ValueError("NULL pointer access")                # alignment.contents.align_frag.contents on an empty list
+    t1, t2 = rows1.tobytes().decode("ascii"), rows2.tobytes().decode("ascii")
+    offs = off.tolist()
+    if local:
+        return [(t1[offs[k]:offs[k + 1]], t2[offs[k]:offs[k + 1]], int(st1[k]), int(st2[k])) for k in range(len(seqs1))]
+    return [(t1[offs[k]:offs[k + 1]], t2[offs[k]:offs[k + 1]], 0, 0) for k in range(len(seqs1))]
 
 
 def smith_waterman(seq1, seq2):
@@ -126,17 +125,35 @@ def get_above_threshold(self, threshold=1):
 
 
 def merge_overlaps(self, threshold=0, minimum_overlap=10):
-    """ambivert.py:301-331 with one batched local alignment for all unique pairs above threshold"""
+    """ambivert.py:301-331 with ONE batched call: local alignment with traceback of every unique pair above
+    threshold and assembly of the merged read on the device (abv_merge_pairs)"""
     self.threshold = threshold
     keys = get_above_threshold(self, threshold)
     logging.info("Merging overlaps for {0} unique pairs".format(len(keys)))
-    fwds = [self.data[k][0][0][1] for k in keys]
-    revs = [reverse_complement(self.data[k][0][1][1]) for k in keys]
-    for key, fwd, rev, (fa, ra, fstart, rstart) in zip(keys, fwds, revs, batched_pairwise(fwds, revs, True)):
-        if len(fa) < minimum_overlap:
-            self.unmergable.append(key)
-        else:
-            self.merged[key] = fwd[:fstart] + flatten_paired_alignment(fa, ra) + rev[rstart + len(ra.replace("-", "")):]
+    if keys:
+        fwds = [self.data[k][0][0][1] for k in keys]
+        revs = [reverse_complement(self.data[k][0][1][1]) for k in keys]
+        for s1, s2 in zip(fwds, revs):
+            if "-" in s1 or "-" in s2:
+                raise RuntimeError("Aligning Sequences with gaps is not supported", s1, s2)
+        try:
+            sc, status, off, merged = B.merge_pairs(_ascii(fwds), _ascii(revs), minimum_overlap)
+        except B.AlignError as e:
+            if e.code in (B.ERR_ARGS, B.ERR_UNDEFINED):
+                raise ValueError("NULL pointer access") from e
+            raise
+        if (status == -1).any():
+            raise ValueError("NULL pointer access")            # smith_waterman on an empty alignment (ambivert.py:93)
+        if (status == -2).any():
+            k = int(np.argmax(status == -2))
+            raise KeyError("mismatching bases outside ACGTN cannot be encoded (sequence_utilities.py:152-156)", fwds[k], revs[k])
+        text = merged.tobytes().decode("ascii")
+        offs = off.tolist()
+        for k, key in enumerate(keys):
+            if status[k] == 1:
+                self.merged[key] = text[offs[k]:offs[k + 1]]
+            else:
+                self.unmergable.append(key)
     logging.info("\nSuccessfully merged {0} reads. {1} reads could not be merged".format(len(self.merged), len(self.unmergable)))
 
 

@@ -191,6 +191,35 @@ int abv_align_pairs(int mode,
                     abv_frag *frags, long long frag_cap, long long *frag_total);
 
 /*
+ * The string work that follows the aligner in the pipeline, done on the device as well
+ * (SURVEY.md section 8f, row f1).  Both take CHARACTER input (map256 != NULL); outputs are concatenated:
+ * pair k owns bytes [out_off[k], out_off[k+1]).  status[k]: 1 ok; 0 merge skipped because the aligned
+ * length is below minimum_overlap (ambivert.py:324-325, "unmergable"); -1 the alignment is empty (the
+ * reference raises ValueError on the NULL fragment, ambivert.py:93); -2 a mismatching base pair outside
+ * ACGTN (encode_ambiguous raises KeyError, sequence_utilities.py:152-156).
+ * ABV_ERR_FRAG_CAP with *out_total = needed bytes when out_cap is too small (offsets/status are valid).
+ *
+ * abv_gapped_pairs: the two gapped rows that smith_waterman / needleman_wunsch return
+ *   (ambivert.py:95-111, :136-152): '-' in the row that has the gap, the other row's characters as given
+ *   (case preserved); start_a/start_b = first fragment's starts (what smith_waterman reports).
+ * abv_merge_pairs: local alignment of every forward read with its (already reverse-complemented) reverse
+ *   read and the merged read of merge_overlaps (ambivert.py:327):
+ *   fwd[:fwd_start] + flatten_paired_alignment(rows) + rev[rev_start + aligned rev bases:]
+ *   where flatten_paired_alignment / encode_ambiguous are sequence_utilities.py:130-169.
+ */
+int abv_gapped_pairs(int mode,
+                     const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
+                     int alpha_len, const unsigned char *map256, const int *score_matrix,
+                     int gap_open, int gap_extend,
+                     int *scores, int *status, int *start_a, int *start_b,
+                     long long *out_off, char *gapped_a, char *gapped_b, long long out_cap, long long *out_total);
+int abv_merge_pairs(const char *fwd, const long long *fwd_off, const char *rev, const long long *rev_off, int n,
+                    int alpha_len, const unsigned char *map256, const int *score_matrix,
+                    int gap_open, int gap_extend, int minimum_overlap,
+                    int *scores, int *status, long long *merged_off, char *merged, long long merged_cap,
+                    long long *merged_total);
+
+/*
  * Timings of the last batched call of this thread, CUDA events on the library's stream:
  *   out[0] host->device ms, out[1] kernel ms, out[2] device->host ms, out[3] cells,
  *   out[4] kernel launches, out[5] bytes host->device, out[6] bytes device->host,

@@ -1,0 +1,80 @@
+"""GPU parity of the device-side string assembly (merged reads, gapped rows) against what the reference
+PYTHON + C produce (tests/golden/merge_strings.json.gz, made by oracle/make_golden_merge.py):
+smith_waterman / needleman_wunsch rows (ambivert.py:75-155) and the merged read of merge_overlaps
+(ambivert.py:320-327 with sequence_utilities.flatten_paired_alignment / encode_ambiguous)."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "merge_strings.json.gz")
+
+
+@pytest.fixture(scope="module")
+def G():
+    with gzip.open(GOLD, "rt") as f:
+        return json.load(f)
+
+
+def test_merged_reads_match_reference_python(G):
+    from ambivert_b200 import batch as B
+    pairs = G["pairs"]
+    sc, status, off, merged = B.merge_pairs([p["fwd"] for p in pairs], [p["rev"] for p in pairs], G["minimum_overlap"])
+    text = merged.tobytes().decode("ascii")
+    n_un = 0
+    for k, p in enumerate(pairs):
+        if p["merged"] is None:
+            assert status[k] == 0 and off[k + 1] == off[k], k
+            n_un += 1
+        else:
+            assert status[k] == 1 and text[off[k]:off[k + 1]] == p["merged"], k
+    assert n_un > 10 and n_un < len(pairs) // 2
+
+
+def test_merge_overlaps_host_stage(G):
+    """through the host mirror: keys, merged dict, unmergable list in data order"""
+    from ambivert_b200.host import AmpliconData, reverse_complement
+    amp = AmpliconData()
+    want_merged, want_un = {}, []
+    for i, p in enumerate(G["pairs"]):
+        key = "k%04d" % i
+        amp.data[key] = [(("r", p["fwd"], ""), ("r", reverse_complement(p["rev"]), ""))] * (1 + i % 3)
+        if i % 3 == 0:
+            continue                         # count 1 is not above threshold 1
+        if p["merged"] is None:
+            want_un.append(key)
+        else:
+            want_merged[key] = p["merged"]
+    amp.merge_overlaps(threshold=1, minimum_overlap=G["minimum_overlap"])
+    assert amp.merged == want_merged and list(amp.merged) == list(want_merged)
+    assert amp.unmergable == want_un
+
+
+def test_gapped_rows_match_reference_python(G):
+    from ambivert_b200 import host as H
+    al = G["aligns"]
+    qs, refs = [a["q"] for a in al], [a["ref"] for a in al]
+    for tag, local in (("nw", False), ("sw", True)):
+        got = H.batched_pairwise(qs, refs, local)
+        for k, a in enumerate(al):
+            assert list(got[k]) == a[tag], (tag, k)
+
+
+def test_bad_base_pair_is_reported():
+    """two different non-ACGTN bases facing each other: encode_ambiguous raises KeyError in the reference"""
+    from ambivert_b200 import batch as B
+    from ambivert_b200.host import AmpliconData, reverse_complement
+    fwd = "ACGTACGTACGTACGTACGTAGGCTTACGATCGATCGGATCRATCGATTAGC"
+    rev = "ACGTACGTACGTACGTACGTAGGCTTACGATCGATCGGATCYATCGATTAGC"     # R vs Y at one column
+    sc, status, off, merged = B.merge_pairs([fwd], [rev], 10)
+    assert status[0] == -2
+    amp = AmpliconData()
+    amp.data["k"] = [(("r", fwd, ""), ("r", reverse_complement(rev), ""))]
+    with pytest.raises(KeyError):
+        amp.merge_overlaps(threshold=0, minimum_overlap=10)
+    # identical ambiguity codes and N are fine: same base -> itself, anything vs N -> N
+    sc, status, off, merged = B.merge_pairs([fwd], [fwd.replace("R", "N")], 10)
+    assert status[0] == 1 and merged.tobytes().decode() == fwd.replace("R", "N")
