@@ -18,6 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libalign_ref.so")
+REF_O3_SO = os.path.join(HERE, "_ref", "libalign_ref_O3.so")
 REF_SRC = "/root/reference/lib/align"
 
 OVERLAP, LOCAL, GLOBAL, GLOCAL = 0, 1, 2, 3
@@ -197,10 +198,11 @@ class Ref:
     def available():
         return os.path.exists(REF_SO)
 
-    def __init__(self):
-        if not os.path.exists(REF_SO):
-            raise FileNotFoundError(REF_SO)
-        self.lib = L = C.CDLL(REF_SO)
+    def __init__(self, path=REF_SO):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.path = path
+        self.lib = L = C.CDLL(path)
         for n in self.RAW.values():
             getattr(L, n).argtypes = _RAW_ARGS
             getattr(L, n).restype = C.POINTER(_RefAlignment)

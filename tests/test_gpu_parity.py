@@ -282,6 +282,15 @@ def test_empty_and_degenerate_batches(B):
     assert bs.size == 0 and bi.size == 0
     bs, bi = B.best_hits([b"ACGT", b"GG"], [], seed=-5)
     assert list(bs) == [-5, -5] and list(bi) == [-1, -1]
+    # one query, one target (a single, unpaired target row) on the packed and the 32-bit path
+    for path in (B.PATH_AUTO, B.PATH_WF32):
+        B.set_option("path", path)
+        try:
+            bs, bi = B.best_hits([b"ACGTACGTTTGACCA"], [b"ACGTTCGTTTGACA"])
+            gs, gi = B.best_hits([b"ACGTACGTTTGACCA"], [b"ACGTTCGTTTGACA"], O.GLOCAL, 0)
+        finally:
+            B.set_option("path", B.PATH_AUTO)
+        assert (int(bs[0]), int(bi[0])) == (2, 0) and (int(gs[0]), int(gi[0])) == (4, 0)     # oracle: global 2, glocal 4
     sc, st, cn, fr = B.align_pairs([], [], O.LOCAL)
     assert sc.size == 0 and fr.shape[0] == 0
     sc, st, cn, fr = B.align_pairs([b"A"], [b"A"], O.GLOBAL)
