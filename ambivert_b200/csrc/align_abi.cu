@@ -214,13 +214,35 @@ int upload_encoded(const char *buf, const long long *off, int n, const Scoring &
 }
 
 // ---- wf32 launcher ----------------------------------------------------------------------------
+// shared-memory staging of the target + border rows: 9 bytes per target position per warp
+int wf32_stage_len(int max_lb) {
+  const int len = (max_lb + 15) & ~15;
+  return (size_t)len * 9 * WF32_WARPS <= 64 * 1024 ? len : 0;      // 0: the batch is too long, use the global-memory variant
+}
+
+template <int MODE, bool TRACE>
+int wf32_launch_mode(int grid, cudaStream_t st, Wf32Params p, int max_lb) {
+  p.stage_len = wf32_stage_len(max_lb);
+  if (p.stage_len > 0) {
+    const int smem = p.stage_len * 9 * WF32_WARPS;
+    auto kern = wf32_kernel<MODE, TRACE, true>;
+    if (smem > 48 * 1024 - (int)sizeof(int) * WF32_MAX_SMEM_ALPHA * WF32_MAX_SMEM_ALPHA)
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, WF32_WARPS * 32, smem, st>>>(p);
+  } else {
+    wf32_kernel<MODE, TRACE, false><<<grid, WF32_WARPS * 32, 0, st>>>(p);
+  }
+  CU(cudaGetLastError());
+  return ABV_OK;
+}
+
 template <bool TRACE>
-void wf32_dispatch(int mode, int grid, cudaStream_t st, const Wf32Params &p) {
+int wf32_dispatch(int mode, int grid, cudaStream_t st, const Wf32Params &p, int max_lb) {
   switch (mode) {
-    case ABV_OVERLAP: wf32_kernel<OVERLAP, TRACE><<<grid, WF32_WARPS * 32, 0, st>>>(p); break;
-    case ABV_LOCAL:   wf32_kernel<LOCAL, TRACE><<<grid, WF32_WARPS * 32, 0, st>>>(p); break;
-    case ABV_GLOBAL:  wf32_kernel<GLOBAL, TRACE><<<grid, WF32_WARPS * 32, 0, st>>>(p); break;
-    default:          wf32_kernel<GLOCAL, TRACE><<<grid, WF32_WARPS * 32, 0, st>>>(p); break;
+    case ABV_OVERLAP: return wf32_launch_mode<OVERLAP, TRACE>(grid, st, p, max_lb);
+    case ABV_LOCAL:   return wf32_launch_mode<LOCAL, TRACE>(grid, st, p, max_lb);
+    case ABV_GLOBAL:  return wf32_launch_mode<GLOBAL, TRACE>(grid, st, p, max_lb);
+    default:          return wf32_launch_mode<GLOCAL, TRACE>(grid, st, p, max_lb);
   }
 }
 
@@ -578,8 +600,7 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
       // full-matrix requests write scores[query*n_t + target]; otherwise a dense chunk in row order
       p.scores = J.want_all_scores ? J.all_scores.as<int>() : J.chunk_scores.as<int>();
       p.score_rows_by_query = J.want_all_scores ? 1 : 0;
-      wf32_dispatch<false>(J.mode, std::min<long long>(grid, (p.n_pairs + WF32_WARPS - 1) / WF32_WARPS), st, p);
-      CU(cudaGetLastError());
+      if ((rc = wf32_dispatch<false>(J.mode, (int)std::min<long long>(grid, (p.n_pairs + WF32_WARPS - 1) / WF32_WARPS), st, p, J.max_lt))) return rc;
       ++launched;
       const int wpb = 8;
       argmax_rows_kernel<<<(int)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
@@ -798,8 +819,7 @@ static int pairs_run(PairsRun &R, int mode, const char *a, const long long *a_of
   p.frag_start = R.start.as<long long>(); p.frag_count = R.count.as<int>();
   p.border = R.border.as<int>(); p.border_len = R.max_lb;
   p.pair_counter = R.counters.as<unsigned long long>();
-  wf32_dispatch<true>(mode, grid, st, p);
-  CU(cudaGetLastError());
+  if ((rc = wf32_dispatch<true>(mode, grid, st, p, R.max_lb))) return rc;
   CU(cudaEventRecord(g.ev[2], st));
   CU(cudaMemcpyAsync(&R.total, p.frag_total, sizeof R.total, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));

@@ -55,14 +55,19 @@ struct Wf32Params {
   long long *frag_start; int *frag_count;
   // column-block border hand-over (queries longer than 32): 2*border_len ints per warp
   int *border; int border_len;
+  int stage_len;                                 // STAGED kernels: per-warp shared-memory rows of this many entries (multiple of 16)
   unsigned long long *pair_counter;
 };
 
 constexpr int WF32_WARPS = 8;
 constexpr int WF32_MAX_SMEM_ALPHA = 48;
 
-template <int MODE, bool TRACE>
+// STAGED: the target symbols and the column-block border arrays of each warp live in dynamic shared
+// memory (stage_len bytes + 2*stage_len ints per warp) instead of global memory; the host picks it when
+// the longest target of the batch fits (Wf32Params::stage_len > 0).
+template <int MODE, bool TRACE, bool STAGED>
 __global__ void __launch_bounds__(WF32_WARPS * 32) wf32_kernel(Wf32Params p) {
+  extern __shared__ __align__(16) unsigned char wf32_smem[];
   __shared__ int s_matrix[WF32_MAX_SMEM_ALPHA * WF32_MAX_SMEM_ALPHA];
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
@@ -75,8 +80,17 @@ __global__ void __launch_bounds__(WF32_WARPS * 32) wf32_kernel(Wf32Params p) {
   const int *M = smem_matrix ? s_matrix : p.matrix;
 
   uint32_t *dir = TRACE ? p.dir + gwarp * p.dir_words_per_warp : nullptr;
-  int *borderH = p.border + gwarp * 2 * (long long)p.border_len;
-  int *borderE = borderH + p.border_len;
+  int *borderH, *borderE;
+  uint8_t *ssb = nullptr;
+  if (STAGED) {
+    unsigned char *mine = wf32_smem + (size_t)warp_in_block * (size_t)p.stage_len * 9;
+    borderH = reinterpret_cast<int *>(mine);
+    borderE = borderH + p.stage_len;
+    ssb = mine + (size_t)p.stage_len * 8;
+  } else {
+    borderH = p.border + gwarp * 2 * (long long)p.border_len;
+    borderE = borderH + p.border_len;
+  }
 
   for (;;) {
     unsigned long long pidx = 0;
@@ -96,6 +110,11 @@ __global__ void __launch_bounds__(WF32_WARPS * 32) wf32_kernel(Wf32Params p) {
     const int lb = (int)(p.b_off[ib + 1] - p.b_off[ib]);
     const int nblk = (la + 31) >> 5;
     const int steps8 = dir_steps8(lb);
+    if (STAGED) {
+      __syncwarp();
+      for (int i = lane; i < lb; i += 32) ssb[i] = sb[i];
+      __syncwarp();
+    }
 
     EndCell wbest = wf32_initial_candidate<MODE>();
     int corner = 0;
@@ -119,7 +138,7 @@ __global__ void __launch_bounds__(WF32_WARPS * 32) wf32_kernel(Wf32Params p) {
         }
         unsigned nib = 0;
         if (r >= 0 && r < lb && colvalid) {
-          const int sub = M[qa + (int)sb[r]];
+          const int sub = M[qa + (int)(STAGED ? ssb[r] : sb[r])];
           int h, eo;
           nib = wf32_cell<MODE>(c, r, la, lb, sub, hleft_prev, e_sh, F, go, ge, h, eo, cand);
           hleft_prev = h_sh;
