@@ -215,14 +215,15 @@ int upload_encoded(const char *buf, const long long *off, int n, const Scoring &
 
 // ---- wf32 launcher ----------------------------------------------------------------------------
 // shared-memory staging of the target + border rows: 9 bytes per target position per warp
-int wf32_stage_len(int max_lb) {
+int wf32_stage_len(int max_lb, int alpha) {
+  if (alpha > WF32_MAX_SMEM_ALPHA) return 0;
   const int len = (max_lb + 15) & ~15;
   return (size_t)len * 9 * WF32_WARPS <= 64 * 1024 ? len : 0;      // 0: the batch is too long, use the global-memory variant
 }
 
 template <int MODE, bool TRACE>
 int wf32_launch_mode(int grid, cudaStream_t st, Wf32Params p, int max_lb) {
-  p.stage_len = wf32_stage_len(max_lb);
+  p.stage_len = wf32_stage_len(max_lb, p.alpha);
   if (p.stage_len > 0) {
     const int smem = p.stage_len * 9 * WF32_WARPS;
     auto kern = wf32_kernel<MODE, TRACE, true>;

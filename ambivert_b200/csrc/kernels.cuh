@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(WF32_WARPS * 32) wf32_kernel(Wf32Params p) {
   if (smem_matrix)
     for (int i = threadIdx.x; i < alpha * alpha; i += blockDim.x) s_matrix[i] = p.matrix[i];
   __syncthreads();
-  const int *M = smem_matrix ? s_matrix : p.matrix;
+  const int *M = (STAGED || smem_matrix) ? s_matrix : p.matrix;   // STAGED launches always have alpha <= WF32_MAX_SMEM_ALPHA
 
   uint32_t *dir = TRACE ? p.dir + gwarp * p.dir_words_per_warp : nullptr;
   int *borderH, *borderE;
