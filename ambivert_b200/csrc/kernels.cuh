@@ -2,12 +2,19 @@
 //
 //   encode_kernel        to_raw (lib/align/helpers.h:26-32): bytes -> symbol indices, on the device
 //   wf32_kernel          general kernel: one warp per (sa, sb) pair, 32-bit, anti-diagonal wavefront
-//                        over 32-column blocks with shuffle exchange; all four modes; optional
-//                        4-bit direction matrix + traceback (bit-exact fragment lists)
-//   mm16_kernel          many-to-many score-only kernel: one warp per (query, target PAIR), packed
-//                        16x2 DPX arithmetic, per-query substitution profile in shared memory,
-//                        target symbols staged by bulk async copies (TMA 1-D), fused per-query arg-max
-//   argmax_rows_kernel   per-query first-maximum selection over a score matrix (general path)
+//                        over 32-column blocks with shuffle exchange; all four modes with the reference's
+//                        tie rules; optional 4-bit direction matrix + traceback (bit-exact fragment lists)
+//   assemble_*_kernel    gapped rows / merged reads built from the fragment pool (the string work that
+//                        follows the aligner in merge_overlaps and align_to_reference)
+//   mm16g_kernel         THE BULK KERNEL: many-to-many score-only, global and glocal.  One warp per
+//                        (query, target PAIR) with both alignments packed in 16x2 DPX words; target pairs
+//                        stream through the lane pipeline; drift-normalised recurrences (1 add + 3 DPX
+//                        per cell pair); per-query substitution profile in shared memory; target rows
+//                        staged by bulk async copies (TMA 1-D, mbarrier); fused per-query arg-max
+//   mm16_kernel          first-generation packed kernel (one pair at a time per warp): local mode, and
+//                        the fallback for value ranges beyond the biased 16-bit range
+//   argmax_rows_kernel, best_key_finalize_kernel   first-maximum selection + seed rule (ambivert.py:478-485)
+//   int_peak_kernel      register-only chains of the DP cell's instruction mix: the measured roofline denominator
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
