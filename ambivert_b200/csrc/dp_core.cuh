@@ -178,10 +178,10 @@ struct FragOut {
 };
 
 // Traceback (global_align.c:25-92, local_align.c:23-72, glocal_align.c:25-70, align.c:25-65).
-// Writes fragments in REVERSE sequence order into out[0..cap) and returns how many there are
-// (which may exceed cap; the excess is counted but not stored).
-template <int MODE, class Reader>
-ABV_HD int walk_back(const Reader &rd, int col, int row, FragOut *out, int cap) {
+// Fragments are found in REVERSE sequence order; emit(j, frag) receives the j-th one found.  Returns how
+// many there are.
+template <int MODE, class Reader, class Emit>
+ABV_HD int walk_back_emit(const Reader &rd, int col, int row, Emit emit) {
   int n = 0;
   while (col >= 0 && row >= 0) {
     unsigned nib = rd.get(col, row);
@@ -205,17 +205,30 @@ ABV_HD int walk_back(const Reader &rd, int col, int row, FragOut *out, int cap) 
       f.type = FRAG_MATCH; f.hsp_len = run;
     }
     f.sa_start = col + 1; f.sb_start = row + 1;
-    if (n < cap) out[n] = f;
+    emit(n, f);
     ++n;
   }
   if (MODE == GLOBAL && (col >= 0 || row >= 0)) {   // leading end gap (global_align.c:69-86)
     FragOut f; f.sa_start = 0; f.sb_start = 0;
     if (col >= 0) { f.type = FRAG_B_GAP; f.hsp_len = col + 1; }
     else          { f.type = FRAG_A_GAP; f.hsp_len = row + 1; }
-    if (n < cap) out[n] = f;
+    emit(n, f);
     ++n;
   }
   return n;
+}
+
+struct FragStore {      // out[j] = j-th fragment found, while j < cap
+  FragOut *out; int cap;
+  ABV_HD void operator()(int j, const FragOut &f) const { if (j < cap) out[j] = f; }
+};
+
+// Writes fragments in REVERSE sequence order into out[0..cap) and returns how many there are (which may
+// exceed cap; the excess is counted but not stored).
+template <int MODE, class Reader>
+ABV_HD int walk_back(const Reader &rd, int col, int row, FragOut *out, int cap) {
+  FragStore st; st.out = out; st.cap = cap;
+  return walk_back_emit<MODE>(rd, col, row, st);
 }
 
 // ---------------------------------------------------------------------------------------------
