@@ -395,3 +395,49 @@ def test_legacy_abi_is_thread_safe(A, oracle_port):
     pool.close()
     for (q, t, mode), g in zip(jobs, got):
         assert g == oracle_port.align(mode, q.encode(), t.encode())
+
+
+def test_packed_vs_wf32_random_sweep(B):
+    """many small random jobs: the packed kernels (streaming global/glocal, first-generation local) must
+    give the same full score matrix and best hits as the 32-bit kernel (itself checked against the oracle
+    above), whatever the lengths, the alphabet, the penalties and the slicing of the targets"""
+    rng = random.Random(20261020)
+    for it in range(120):
+        alpha = rng.choice([2, 4, 5, 5, 5, 7])
+        alphabet = "ACGTNRY"[:alpha]
+        _, mp = O.make_map(alphabet, alphabet[-1], True)
+        if alpha == 5 and rng.random() < 0.5:
+            M, go, ge = O.DNA_SCORE, -7, -1
+        else:
+            M = np.array([rng.randint(-6, 6) for _ in range(alpha * alpha)], np.int32)
+            go, ge = -rng.randint(0, 12), -rng.randint(0, 4)
+        n_q, n_t = rng.randint(1, 24), rng.randint(1, 60)
+        lmax = rng.choice([8, 40, 130, 300, 520])
+        targets = [rand_dna(rng, rng.randint(2, lmax), alphabet) for _ in range(n_t)]
+        if rng.random() < 0.3:
+            targets = [targets[0][:rng.randint(2, len(targets[0]))] if rng.random() < 0.5 else t for t in targets]
+        queries = []
+        for _ in range(n_q):
+            if rng.random() < 0.5:
+                queries.append(mutate(rng, targets[rng.randrange(n_t)], rng.randint(0, 4), alphabet))
+            else:
+                queries.append(rand_dna(rng, rng.randint(1, min(512, lmax + 60)), alphabet))
+        mode = rng.choice([O.GLOBAL, O.GLOBAL, O.GLOCAL, O.LOCAL])
+        seed = rng.choice([-1000000, 0, 5])
+        q = [s.encode() for s in queries]
+        t = [s.encode() for s in targets]
+        B.set_option("path", B.PATH_WF32)
+        try:
+            want = B.score_matrix(q, t, mode, alpha, mp, M, go, ge)
+            want_hits = B.best_hits(q, t, mode, seed, alpha, mp, M, go, ge)
+        finally:
+            B.set_option("path", B.PATH_AUTO)
+        B.set_option("split", rng.choice([0, 0, 1, 2, 3, 7]))
+        try:
+            got = B.score_matrix(q, t, mode, alpha, mp, M, go, ge)
+            got_hits = B.best_hits(q, t, mode, seed, alpha, mp, M, go, ge)
+        finally:
+            B.set_option("split", 0)
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, (it, mode, alpha, go, ge, bad[:3], len(queries[bad[0][0]]), len(targets[bad[0][1]]))
+        assert (got_hits[0] == want_hits[0]).all() and (got_hits[1] == want_hits[1]).all(), (it, mode, seed)
