@@ -815,9 +815,16 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         tb_off += prev_rows;
         const int dr1 = ge * (lq - 1 + meta.x - 1), dr2 = ge * (lq - 1 + meta.y - 1);
         const int par = i & 1;
-        // the first 32 steps: lane s switches to this pair at step s
-        for (int s = 0; s < MM16G_MIN_ROWS; ++s) {
-          if (GL) {
+        auto issue_next_copy = [&]() {       // every lane has left pair i-1: its buffer can take pair i+2
+          __syncwarp();
+          if (lane == 0 && i + 2 < n_i) {
+            const int b2 = (i + 2) % 3;
+            bulk_load(smem + tbuf0 + b2 * p.tp_stride, p.tp_codes + (long long)(pbase + (i + 2) * W) * p.tp_stride, p.tp_stride, &bar[b2]);
+          }
+        };
+        if (GL) {
+          // the first 32 steps: lane s switches to this pair at step s
+          for (int s = 0; s < MM16G_MIN_ROWS; ++s) {
             if (lane == s) tb_off = bufoff - lane;
             uint32_t h_sh, e_sh;
             exchange(h_sh, e_sh);
@@ -838,30 +845,15 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
               last_rows_at(s, pend_e1, pend_e2, pend_r1, pend_r2, par ^ 1);
               last_rows_at(s, ev1, ev2, meta.x - 1, meta.y - 1, par);
             }
-          } else {
-            if (lane == s) {
-#pragma unroll
-              for (int k = 0; k < K; ++k) { Hp[k] = Hc; F[k] = Ec; }
-              hleft = lane ? Hc : H00;
-              tb_off = bufoff - lane;
-            }
-            body(s);
+            if (s == pend_s1) capture(0, pend_i1, pend_d1, par ^ 1);
+            if (s == pend_s2) capture(1, pend_i2, pend_d2, par ^ 1);
+            if (s == cs1) capture(0, meta.z, dr1, par);
+            if (s == cs2) capture(1, meta.w, dr2, par);
           }
-          if (s == pend_s1) capture(0, pend_i1, pend_d1, par ^ 1);
-          if (s == pend_s2) capture(1, pend_i2, pend_d2, par ^ 1);
-          if (s == cs1) capture(0, meta.z, dr1, par);
-          if (s == cs2) capture(1, meta.w, dr2, par);
-        }
-        // every lane has left pair i-1: its buffer can take pair i+2
-        __syncwarp();
-        if (lane == 0 && i + 2 < n_i) {
-          const int b2 = (i + 2) % 3;
-          bulk_load(smem + tbuf0 + b2 * p.tp_stride, p.tp_codes + (long long)(pbase + (i + 2) * W) * p.tp_stride, p.tp_stride, &bar[b2]);
-        }
-        // steady state
-        int s = MM16G_MIN_ROWS;
-        if (GL) {
+          issue_next_copy();
+          int s = MM16G_MIN_ROWS;
           const int s_chk = min(rows, max(MM16G_MIN_ROWS, min(ev1, ev2)));
+#pragma unroll kHotUnroll
           for (; s < s_chk; ++s) body(s);                      // no lane is on a last row yet
           for (; s < rows; ++s) {
             body(s);
@@ -870,14 +862,42 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
             if (s == cs2) capture(1, meta.w, dr2, par);
           }
         } else {
+          // The pair's steps run in segments that end where a corner cell has to be captured (a warp-uniform
+          // step), so that the loops themselves carry no capture tests and unroll; in the first 32 steps lane
+          // s switches to this pair at step s (state reset to the global boundary, global_align.c:136-148).
+          int s = 0;
           while (s < rows) {
-            int stop = rows;
+            const bool switching = s < MM16G_MIN_ROWS;
+            int stop = switching ? MM16G_MIN_ROWS : rows;
+            if (switching) {
+              if (pend_s1 >= s && pend_s1 < stop) stop = pend_s1 + 1;
+              if (pend_s2 >= s && pend_s2 < stop) stop = pend_s2 + 1;
+            }
             if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
             if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
+            if (switching) {
 #pragma unroll kHotUnroll
-            for (; s < stop; ++s) body(s);
-            if (s - 1 == cs1) capture(0, meta.z, dr1, par);
-            if (s - 1 == cs2) capture(1, meta.w, dr2, par);
+              for (; s < stop; ++s) {
+                if (lane == s) {
+#pragma unroll
+                  for (int k = 0; k < K; ++k) { Hp[k] = Hc; F[k] = Ec; }
+                  hleft = lane ? Hc : H00;
+                  tb_off = bufoff - lane;
+                }
+                body(s);
+              }
+            } else {
+#pragma unroll kHotUnroll
+              for (; s < stop; ++s) body(s);
+            }
+            const int done = s - 1;
+            if (done < MM16G_MIN_ROWS) {
+              if (done == pend_s1) capture(0, pend_i1, pend_d1, par ^ 1);
+              if (done == pend_s2) capture(1, pend_i2, pend_d2, par ^ 1);
+            }
+            if (done == cs1) capture(0, meta.z, dr1, par);
+            if (done == cs2) capture(1, meta.w, dr2, par);
+            if (s == MM16G_MIN_ROWS) issue_next_copy();
           }
         }
         pend_s1 = cs1 >= rows ? cs1 - rows : -1; pend_i1 = meta.z; pend_d1 = dr1;
