@@ -116,3 +116,25 @@ def read_pairs_packed(n_pairs=1000000, read_len=150, seed=0xA3B1, p_sub=0.005, p
         a[rng.random(a.shape) < p_n] = ord("N")
     off = np.arange(n_pairs + 1, dtype=np.int64) * read_len
     return (np.ascontiguousarray(fwd).reshape(-1), off), (np.ascontiguousarray(rev).reshape(-1), off.copy())
+
+
+def panel_pipeline_inputs(n_targets=300, n_unique=20000, read_len=150, seed=0xB2CA):
+    """BASELINE.json configs[2] shape: a TruSeq-style panel and the unique read pairs of its amplicons.
+    -> (references: list of ((name, chrom, start, end, strand), sequence str),
+        pairs: list of (forward read, reverse read as sequenced, copies))
+    Targets are 170..250 bp with soft-masked 27 bp probes, alternating strand; amplicons are mutated copies
+    (SNVs, occasional indel, rare IUPAC base); F = first read_len bases, R = reverse complement of the last."""
+    rng = np.random.default_rng(seed + 7)
+    targets = panel_targets(n_targets, 170, 250, seed=seed)
+    refs = []
+    for i, t in enumerate(targets):
+        refs.append((("target%03d" % i, "chr%d" % (1 + i % 2), str(1000 * i), str(1000 * i + len(t)), "+" if i % 2 == 0 else "-"), t.decode()))
+    # reads carry ACGT only: two different IUPAC codes facing each other make the reference's own
+    # encode_ambiguous raise KeyError (sequence_utilities.py:152-156)
+    queries, src = panel_queries(targets, n_unique, seed=seed + 1, p_unrelated=0.0, p_iupac=0.0)
+    pairs = []
+    for q in queries:
+        if len(q) < read_len:
+            continue
+        pairs.append((q[:read_len].decode(), reverse_complement(q[-read_len:]).decode(), int(rng.integers(1, 4))))
+    return refs, pairs
