@@ -1046,11 +1046,137 @@ Alignment *alignment_new(AlignFrag *align_frag, int score) {
   return al;
 }
 
+}  // extern "C" (the helpers below are C++)
+
+// ---- the lean single-pair path of the legacy symbols -------------------------------------------------
+// The reference calls these from multiprocessing.dummy worker threads, one pair per call
+// (ambivert.py:474-476).  A call costs one host->device copy, one launch of wf32_one_kernel and one
+// device->host copy on a stream of its own, so calls from different host threads overlap on the GPU.  The
+// per-call resources (stream, pinned staging, device scratch) are pooled: worker threads come and go (the
+// reference builds a new Pool per amplicon), the contexts stay.
+struct OneCtx {
+  cudaStream_t st = nullptr;
+  unsigned char *h = nullptr; size_t h_cap = 0;     // pinned: [input blob][result blob]
+  unsigned char *d = nullptr; size_t d_cap = 0;     // device: input blob + scratch + result blob
+};
+std::mutex g_one_mu;
+std::vector<OneCtx *> g_one_free;
+
+static OneCtx *one_acquire() {
+  {
+    std::lock_guard<std::mutex> lk(g_one_mu);
+    if (!g_one_free.empty()) { OneCtx *c = g_one_free.back(); g_one_free.pop_back(); return c; }
+  }
+  OneCtx *c = new OneCtx();
+  if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete c; return nullptr; }
+  return c;
+}
+static void one_release(OneCtx *c) {
+  std::lock_guard<std::mutex> lk(g_one_mu);
+  g_one_free.push_back(c);
+}
+static bool one_reserve(OneCtx *c, size_t h_bytes, size_t d_bytes) {
+  if (h_bytes > c->h_cap) {
+    if (c->h) cudaFreeHost(c->h);
+    c->h = nullptr; c->h_cap = 0;
+    const size_t want = std::max<size_t>(h_bytes * 2, 64 << 10);
+    if (cudaMallocHost((void **)&c->h, want) != cudaSuccess) { cudaGetLastError(); return false; }
+    c->h_cap = want;
+  }
+  if (d_bytes > c->d_cap) {
+    if (c->d) cudaFree(c->d);
+    c->d = nullptr; c->d_cap = 0;
+    const size_t want = std::max<size_t>(d_bytes * 2, 256 << 10);
+    if (cudaMalloc((void **)&c->d, want) != cudaSuccess) { cudaGetLastError(); return false; }
+    c->d_cap = want;
+  }
+  return true;
+}
+
+template <int MODE>
+static void one_launch(cudaStream_t st, const Wf32OneParams &p) { wf32_one_kernel<MODE><<<1, 32, 0, st>>>(p); }
+
+// returns 1 = done (result in *out), 0 = not eligible for the lean path, -1 = CUDA failure
+static int legacy_align_lean(int mode, const char *sa, int la, const char *sb, int lb, int alpha, const unsigned char *map,
+                             const int *matrix, int go, int ge, Alignment **out) {
+  if (alpha > WF32_MAX_SMEM_ALPHA || la > (1 << 15) || lb > (1 << 15)) return 0;
+  const size_t dir_bytes = (size_t)dir_words(la, lb) * 4;
+  if (dir_bytes > ((size_t)256 << 20)) return 0;
+  {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (ctx_init() != ABV_OK) return -1;
+  }
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const int frag_cap = la + lb + 2;
+  const size_t in_bytes = 256 + (size_t)alpha * alpha * 4 + la + lb;
+  const size_t out_bytes = 16 + (size_t)frag_cap * sizeof(FragOut);
+  const size_t o_in = 0, o_codes = up(in_bytes), o_dir = o_codes + up((size_t)la + lb), o_border = o_dir + up(dir_bytes),
+               o_tmp = o_border + up((size_t)lb * 8), o_out = o_tmp + up((size_t)frag_cap * sizeof(FragOut)), d_total = o_out + up(out_bytes);
+  OneCtx *c = one_acquire();
+  if (!c) return -1;
+  int rc = -1;
+  do {
+    if (cudaSetDevice(g.device) != cudaSuccess) break;
+    if (!one_reserve(c, up(in_bytes) + up(out_bytes), d_total)) break;
+    unsigned char *hin = c->h;
+    int *hout = reinterpret_cast<int *>(c->h + up(in_bytes));
+    if (map) memcpy(hin, map, 256); else memset(hin, 0, 256);
+    memcpy(hin + 256, matrix, (size_t)alpha * alpha * 4);
+    memcpy(hin + 256 + (size_t)alpha * alpha * 4, sa, la);
+    memcpy(hin + 256 + (size_t)alpha * alpha * 4 + la, sb, lb);
+    if (cudaMemcpyAsync(c->d + o_in, hin, in_bytes, cudaMemcpyHostToDevice, c->st) != cudaSuccess) break;
+    Wf32OneParams p{};
+    p.in = c->d + o_in; p.la = la; p.lb = lb; p.alpha = alpha; p.go = go; p.ge = ge; p.use_map = map ? 1 : 0;
+    p.codes = c->d + o_codes; p.dir = reinterpret_cast<uint32_t *>(c->d + o_dir);
+    p.border = reinterpret_cast<int *>(c->d + o_border);
+    p.tmp = reinterpret_cast<FragOut *>(c->d + o_tmp); p.tmp_cap = frag_cap;
+    p.out = reinterpret_cast<int *>(c->d + o_out); p.out_frag_cap = frag_cap;
+    switch (mode) {
+      case ABV_OVERLAP: one_launch<OVERLAP>(c->st, p); break;
+      case ABV_LOCAL: one_launch<LOCAL>(c->st, p); break;
+      case ABV_GLOBAL: one_launch<GLOBAL>(c->st, p); break;
+      default: one_launch<GLOCAL>(c->st, p); break;
+    }
+    if (cudaGetLastError() != cudaSuccess) break;
+    const int first = std::min(frag_cap, 62);           // 16 + 62*16 = 1008 bytes: most alignments fit the first copy
+    if (cudaMemcpyAsync(hout, c->d + o_out, 16 + (size_t)first * sizeof(FragOut), cudaMemcpyDeviceToHost, c->st) != cudaSuccess) break;
+    if (cudaStreamSynchronize(c->st) != cudaSuccess) break;
+    const int score = hout[0], n = hout[1];
+    if (n > first) {
+      if (cudaMemcpyAsync(hout + 4 + first * 4, c->d + o_out + 16 + (size_t)first * sizeof(FragOut), (size_t)(n - first) * sizeof(FragOut),
+                          cudaMemcpyDeviceToHost, c->st) != cudaSuccess) break;
+      if (cudaStreamSynchronize(c->st) != cudaSuccess) break;
+    }
+    const FragOut *fr = reinterpret_cast<const FragOut *>(hout + 4);
+    AlignFrag *head = nullptr;
+    bool oom = false;
+    for (int i = n - 1; i >= 0; --i) {
+      AlignFrag *f = (AlignFrag *)malloc(sizeof(AlignFrag));
+      if (!f) { oom = true; break; }
+      f->next = head; f->type = (FragType)fr[i].type; f->sa_start = fr[i].sa_start; f->sb_start = fr[i].sb_start; f->hsp_len = fr[i].hsp_len;
+      head = f;
+    }
+    if (oom) { align_frag_free(head); *out = nullptr; rc = 1; break; }
+    *out = alignment_new(head, score);
+    if (!*out) align_frag_free(head);
+    rc = 1;
+  } while (0);
+  if (rc < 0) cudaGetLastError();
+  one_release(c);
+  return rc;
+}
+
 static Alignment *legacy_align(int mode, const char *sa, int la, const char *sb, int lb, int alpha_len,
                                const unsigned char *map, int *matrix, int go, int ge, bool need_map) {
   // global_align.c:118-122, :241-243
   if (la <= 0 || lb <= 0 || !sa || !sb || !matrix || go > 0 || ge > 0) return nullptr;
   if (need_map && !map) return nullptr;
+  if (alpha_len <= 0 || alpha_len > 256) return nullptr;
+  if ((mode == ABV_GLOCAL && lb < 2) || (mode == ABV_OVERLAP && la < 2)) return nullptr;   // undefined in the reference
+  Alignment *lean = nullptr;
+  const int how = legacy_align_lean(mode, sa, la, sb, lb, alpha_len, need_map ? map : nullptr, matrix, go, ge, &lean);
+  if (how == 1) return lean;
+  if (how < 0) return nullptr;
   const long long a_off[2] = {0, la}, b_off[2] = {0, lb};
   const long long cap = (long long)la + lb + 2;
   std::vector<abv_frag> frags((size_t)cap);
@@ -1071,6 +1197,8 @@ static Alignment *legacy_align(int mode, const char *sa, int la, const char *sb,
   if (!al) align_frag_free(head);
   return al;
 }
+
+extern "C" {
 
 #define ABV_LEGACY(NAME, MODE)                                                                                     \
   Alignment *NAME##_raw(const unsigned char *sa, int sa_len, const unsigned char *sb, int sb_len, int alpha_len,   \

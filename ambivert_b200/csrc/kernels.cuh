@@ -69,6 +69,72 @@ struct Wf32Params {
 constexpr int WF32_WARPS = 8;
 constexpr int WF32_MAX_SMEM_ALPHA = 48;
 
+// The fill of one pair by one warp: 32-column blocks, lane = column, rows skewed by lane; the block's
+// right border (H, E per row) goes through borderH/borderE to the next block.  Warp-uniform results.
+template <int MODE, bool TRACE, bool STAGED>
+__device__ __forceinline__ void wf32_fill(const uint8_t *sa, int la, const uint8_t *sb, int lb, const int *M, int alpha,
+                                          int go, int ge, uint32_t *dir, int *borderH, int *borderE, uint8_t *ssb, int lane,
+                                          int &score, int &ec, int &er) {
+  const int nblk = (la + 31) >> 5;
+  const int steps8 = dir_steps8(lb);
+  if (STAGED) {
+    __syncwarp();
+    for (int i = lane; i < lb; i += 32) ssb[i] = sb[i];
+    __syncwarp();
+  }
+  EndCell wbest = wf32_initial_candidate<MODE>();
+  int corner = 0;
+  for (int b = 0; b < nblk; ++b) {
+    const int c = (b << 5) + lane;
+    const bool colvalid = c < la;
+    const int qa = colvalid ? (int)sa[c] * alpha : 0;
+    int F = 0, hleft_prev = 0, h_out = 0, e_out = 0;
+    EndCell cand = wf32_initial_candidate<MODE>();
+    uint32_t acc = 0;
+    const int lanes_used = min(32, la - (b << 5));
+    const int nsteps = lb + lanes_used - 1;
+    for (int s = 0; s < nsteps; ++s) {
+      int h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
+      int e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+      const int r = s - lane;
+      if (lane == 0 && s < lb) {
+        if (b == 0) wf32_virtual_column<MODE>(s, go, ge, h_sh, e_sh);
+        else { h_sh = borderH[s]; e_sh = borderE[s]; }
+      }
+      unsigned nib = 0;
+      if (r >= 0 && r < lb && colvalid) {
+        const int sub = M[qa + (int)(STAGED ? ssb[r] : sb[r])];
+        int h, eo;
+        nib = wf32_cell<MODE>(c, r, la, lb, sub, hleft_prev, e_sh, F, go, ge, h, eo, cand);
+        hleft_prev = h_sh;
+        h_out = h;
+        e_out = eo;
+        if (MODE == GLOBAL && c == la - 1 && r == lb - 1) corner = h;
+        if (lane == 31 && b + 1 < nblk) { borderH[r] = h; borderE[r] = eo; }
+      }
+      if (TRACE) {
+        acc |= nib << ((s & 7) * 4);
+        if ((s & 7) == 7 || s == nsteps - 1) {
+          dir[((long long)b * steps8 + (s >> 3)) * 32 + lane] = acc;
+          acc = 0;
+        }
+      }
+    }
+    // best end cell of this block, then fold into the running best (later blocks win ties)
+    for (int off = 16; off > 0; off >>= 1) {
+      EndCell o;
+      o.score = __shfl_xor_sync(ABV_FULL, cand.score, off);
+      o.col = __shfl_xor_sync(ABV_FULL, cand.col, off);
+      o.row = __shfl_xor_sync(ABV_FULL, cand.row, off);
+      if (end_better(o, cand)) cand = o;
+    }
+    if (cand.col >= 0 && cand.score >= wbest.score) wbest = cand;
+    __syncwarp();
+  }
+  if (MODE == GLOBAL) corner = __shfl_sync(ABV_FULL, corner, (la - 1) & 31);
+  wf32_finish<MODE>(wbest, corner, la, lb, score, ec, er);
+}
+
 // STAGED: the target symbols and the column-block border arrays of each warp live in dynamic shared
 // memory (stage_len bytes + 2*stage_len ints per warp) instead of global memory; the host picks it when
 // the longest target of the batch fits (Wf32Params::stage_len > 0).
@@ -115,67 +181,9 @@ __global__ void __launch_bounds__(WF32_WARPS * 32) wf32_kernel(Wf32Params p) {
     const uint8_t *sb = p.b + p.b_off[ib];
     const int la = (int)(p.a_off[ia + 1] - p.a_off[ia]);
     const int lb = (int)(p.b_off[ib + 1] - p.b_off[ib]);
-    const int nblk = (la + 31) >> 5;
     const int steps8 = dir_steps8(lb);
-    if (STAGED) {
-      __syncwarp();
-      for (int i = lane; i < lb; i += 32) ssb[i] = sb[i];
-      __syncwarp();
-    }
-
-    EndCell wbest = wf32_initial_candidate<MODE>();
-    int corner = 0;
-
-    for (int b = 0; b < nblk; ++b) {
-      const int c = (b << 5) + lane;
-      const bool colvalid = c < la;
-      const int qa = colvalid ? (int)sa[c] * alpha : 0;
-      int F = 0, hleft_prev = 0, h_out = 0, e_out = 0;
-      EndCell cand = wf32_initial_candidate<MODE>();
-      uint32_t acc = 0;
-      const int lanes_used = min(32, la - (b << 5));
-      const int nsteps = lb + lanes_used - 1;
-      for (int s = 0; s < nsteps; ++s) {
-        int h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
-        int e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
-        const int r = s - lane;
-        if (lane == 0 && s < lb) {
-          if (b == 0) wf32_virtual_column<MODE>(s, go, ge, h_sh, e_sh);
-          else { h_sh = borderH[s]; e_sh = borderE[s]; }
-        }
-        unsigned nib = 0;
-        if (r >= 0 && r < lb && colvalid) {
-          const int sub = M[qa + (int)(STAGED ? ssb[r] : sb[r])];
-          int h, eo;
-          nib = wf32_cell<MODE>(c, r, la, lb, sub, hleft_prev, e_sh, F, go, ge, h, eo, cand);
-          hleft_prev = h_sh;
-          h_out = h;
-          e_out = eo;
-          if (MODE == GLOBAL && c == la - 1 && r == lb - 1) corner = h;
-          if (lane == 31 && b + 1 < nblk) { borderH[r] = h; borderE[r] = eo; }
-        }
-        if (TRACE) {
-          acc |= nib << ((s & 7) * 4);
-          if ((s & 7) == 7 || s == nsteps - 1) {
-            dir[((long long)b * steps8 + (s >> 3)) * 32 + lane] = acc;
-            acc = 0;
-          }
-        }
-      }
-      // best end cell of this block, then fold into the running best (later blocks win ties)
-      for (int off = 16; off > 0; off >>= 1) {
-        EndCell o;
-        o.score = __shfl_xor_sync(ABV_FULL, cand.score, off);
-        o.col = __shfl_xor_sync(ABV_FULL, cand.col, off);
-        o.row = __shfl_xor_sync(ABV_FULL, cand.row, off);
-        if (end_better(o, cand)) cand = o;
-      }
-      if (cand.col >= 0 && cand.score >= wbest.score) wbest = cand;
-      __syncwarp();
-    }
-    if (MODE == GLOBAL) corner = __shfl_sync(ABV_FULL, corner, (la - 1) & 31);
     int score, ec, er;
-    wf32_finish<MODE>(wbest, corner, la, lb, score, ec, er);
+    wf32_fill<MODE, TRACE, STAGED>(sa, la, sb, lb, M, alpha, go, ge, dir, borderH, borderE, ssb, lane, score, ec, er);
     if (lane == 0) p.scores[out_idx] = score;
 
     if (TRACE) {
@@ -198,6 +206,52 @@ __global__ void __launch_bounds__(WF32_WARPS * 32) wf32_kernel(Wf32Params p) {
       __syncwarp();
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One pair, one launch: what a call through the reference's own ABI (global_align, local_align, ...) costs.
+// The call's whole input arrives in ONE host->device copy (`in`: 256-byte map, alpha*alpha ints, sa bytes, sb
+// bytes) and its whole result leaves in ONE device->host copy (`out`: score, fragment count, fragments in
+// sequence order).  One warp encodes, fills, walks back.  Host threads call concurrently on their own streams.
+struct Wf32OneParams {
+  const unsigned char *in;       // [map 256][matrix alpha*alpha ints][sa la bytes][sb lb bytes]
+  int la, lb, alpha, go, ge, use_map;
+  uint8_t *codes;                // la + lb bytes of scratch
+  uint32_t *dir;                 // dir_words(la, lb)
+  int *border;                   // 2 * lb ints
+  FragOut *tmp; int tmp_cap;     // la + lb + 2
+  int *out;                      // [score, n_frags, pad, pad][frags ...]
+  int out_frag_cap;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(32) wf32_one_kernel(Wf32OneParams p) {
+  __shared__ int s_matrix[WF32_MAX_SMEM_ALPHA * WF32_MAX_SMEM_ALPHA];
+  __shared__ uint8_t s_map[256];
+  const int lane = threadIdx.x;
+  const int alpha = p.alpha;
+  const int *matrix = reinterpret_cast<const int *>(p.in + 256);
+  const unsigned char *ra = p.in + 256 + (size_t)alpha * alpha * 4, *rb = ra + p.la;
+  for (int i = lane; i < 256; i += 32) s_map[i] = p.in[i];
+  for (int i = lane; i < alpha * alpha; i += 32) s_matrix[i] = matrix[i];
+  __syncwarp();
+  uint8_t *sa = p.codes, *sb = p.codes + p.la;
+  for (int i = lane; i < p.la; i += 32) sa[i] = (uint8_t)min((int)(p.use_map ? s_map[ra[i]] : ra[i]), alpha - 1);
+  for (int i = lane; i < p.lb; i += 32) sb[i] = (uint8_t)min((int)(p.use_map ? s_map[rb[i]] : rb[i]), alpha - 1);
+  __syncwarp();
+  int score, ec, er;
+  wf32_fill<MODE, true, false>(sa, p.la, sb, p.lb, s_matrix, alpha, p.go, p.ge, p.dir, p.border, p.border + p.lb, nullptr, lane, score, ec, er);
+  __syncwarp();
+  int n = 0;
+  if (lane == 0) {
+    DirReader rd; rd.w = p.dir; rd.steps8 = dir_steps8(p.lb);
+    n = walk_back<MODE>(rd, ec, er, p.tmp, p.tmp_cap);
+    p.out[0] = score; p.out[1] = n;
+  }
+  n = __shfl_sync(ABV_FULL, n, 0);
+  __syncwarp();
+  FragOut *of = reinterpret_cast<FragOut *>(p.out + 4);
+  for (int i = lane; i < n && i < p.out_frag_cap; i += 32) of[i] = p.tmp[n - 1 - i];
 }
 
 // ---------------------------------------------------------------------------------------------
