@@ -1094,7 +1094,17 @@ static bool one_reserve(OneCtx *c, size_t h_bytes, size_t d_bytes) {
 }
 
 template <int MODE>
-static void one_launch(cudaStream_t st, const Wf32OneParams &p) { wf32_one_kernel<MODE><<<1, 32, 0, st>>>(p); }
+static void one_launch(cudaStream_t st, const Wf32OneParams &p) {
+  const size_t smem = (size_t)((p.la + 31) / 32) * 2 * p.lb * 4 + p.la + p.lb;
+  if (smem <= 150 * 1024) {
+    auto kern = wf32_one_kernel<MODE, true>;
+    static thread_local bool raised = false;
+    if (smem > 40 * 1024 && !raised) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024); raised = true; }
+    kern<<<1, WF32_ONE_WARPS * 32, smem, st>>>(p);
+  } else {
+    wf32_one_kernel<MODE, false><<<1, WF32_ONE_WARPS * 32, 0, st>>>(p);
+  }
+}
 
 // returns 1 = done (result in *out), 0 = not eligible for the lean path, -1 = CUDA failure
 static int legacy_align_lean(int mode, const char *sa, int la, const char *sb, int lb, int alpha, const unsigned char *map,
@@ -1111,7 +1121,7 @@ static int legacy_align_lean(int mode, const char *sa, int la, const char *sb, i
   const size_t in_bytes = 256 + (size_t)alpha * alpha * 4 + la + lb;
   const size_t out_bytes = 16 + (size_t)frag_cap * sizeof(FragOut);
   const size_t o_in = 0, o_codes = up(in_bytes), o_dir = o_codes + up((size_t)la + lb), o_border = o_dir + up(dir_bytes),
-               o_tmp = o_border + up((size_t)lb * 8), o_out = o_tmp + up((size_t)frag_cap * sizeof(FragOut)), d_total = o_out + up(out_bytes);
+               o_tmp = o_border + up((size_t)lb * 8 * ((la + 31) / 32)), o_out = o_tmp + up((size_t)frag_cap * sizeof(FragOut)), d_total = o_out + up(out_bytes);
   OneCtx *c = one_acquire();
   if (!c) return -1;
   int rc = -1;

@@ -218,33 +218,126 @@ struct Wf32OneParams {
   int la, lb, alpha, go, ge, use_map;
   uint8_t *codes;                // la + lb bytes of scratch
   uint32_t *dir;                 // dir_words(la, lb)
-  int *border;                   // 2 * lb ints
+  int *border;                   // 2 * lb ints per 32-column block
   FragOut *tmp; int tmp_cap;     // la + lb + 2
   int *out;                      // [score, n_frags, pad, pad][frags ...]
   int out_frag_cap;
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(32) wf32_one_kernel(Wf32OneParams p) {
+constexpr int WF32_ONE_WARPS = 8;
+constexpr int WF32_ONE_CHUNK = 16;      // border rows handed from one column block to the next at a time
+
+// The column blocks of the one pair are pipelined over the warps of the CTA: warp w fills blocks w, w+8, ...
+// and block b may run as soon as block b-1 has published the next chunk of its right border (a progress
+// counter in shared memory; forward dependencies only, all warps resident, so the spin cannot deadlock).
+// SMEM: the encoded sequences and the block borders live in dynamic shared memory
+// ([border: nblk*2*lb ints][sa: la bytes][sb: lb bytes]); otherwise in the global scratch of the call.
+template <int MODE, bool SMEM>
+__global__ void __launch_bounds__(WF32_ONE_WARPS * 32) wf32_one_kernel(Wf32OneParams p) {
+  extern __shared__ __align__(16) unsigned char one_smem[];
   __shared__ int s_matrix[WF32_MAX_SMEM_ALPHA * WF32_MAX_SMEM_ALPHA];
   __shared__ uint8_t s_map[256];
-  const int lane = threadIdx.x;
-  const int alpha = p.alpha;
+  __shared__ volatile int s_progress[WF32_ONE_WARPS];     // rows of the right border published by the block a warp is on
+  __shared__ volatile int s_block_of[WF32_ONE_WARPS];     // which block that is
+  __shared__ int s_best[WF32_ONE_WARPS * 3];
+  __shared__ int s_corner;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int alpha = p.alpha, la = p.la, lb = p.lb, go = p.go, ge = p.ge;
   const int *matrix = reinterpret_cast<const int *>(p.in + 256);
-  const unsigned char *ra = p.in + 256 + (size_t)alpha * alpha * 4, *rb = ra + p.la;
-  for (int i = lane; i < 256; i += 32) s_map[i] = p.in[i];
-  for (int i = lane; i < alpha * alpha; i += 32) s_matrix[i] = matrix[i];
-  __syncwarp();
-  uint8_t *sa = p.codes, *sb = p.codes + p.la;
-  for (int i = lane; i < p.la; i += 32) sa[i] = (uint8_t)min((int)(p.use_map ? s_map[ra[i]] : ra[i]), alpha - 1);
-  for (int i = lane; i < p.lb; i += 32) sb[i] = (uint8_t)min((int)(p.use_map ? s_map[rb[i]] : rb[i]), alpha - 1);
-  __syncwarp();
+  const unsigned char *ra = p.in + 256 + (size_t)alpha * alpha * 4, *rb = ra + la;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_map[i] = p.in[i];
+  for (int i = threadIdx.x; i < alpha * alpha; i += blockDim.x) s_matrix[i] = matrix[i];
+  if (threadIdx.x < WF32_ONE_WARPS) { s_progress[threadIdx.x] = 0; s_block_of[threadIdx.x] = -1; }
+  __syncthreads();
+  const int nblk = (la + 31) >> 5;
+  int *border = SMEM ? reinterpret_cast<int *>(one_smem) : p.border;
+  uint8_t *sa = SMEM ? one_smem + (size_t)nblk * 2 * lb * 4 : p.codes;
+  uint8_t *sb = sa + la;
+  for (int i = threadIdx.x; i < la; i += blockDim.x) sa[i] = (uint8_t)min((int)(p.use_map ? s_map[ra[i]] : ra[i]), alpha - 1);
+  for (int i = threadIdx.x; i < lb; i += blockDim.x) sb[i] = (uint8_t)min((int)(p.use_map ? s_map[rb[i]] : rb[i]), alpha - 1);
+  __syncthreads();
+
+  const int steps8 = dir_steps8(lb);
+  EndCell wbest = wf32_initial_candidate<MODE>();
+  int corner = 0;
+  for (int b = warp; b < nblk; b += WF32_ONE_WARPS) {
+    // borders: block b reads rows of border b-1 and writes border b (2*lb ints each)
+    int *outH = border + (size_t)b * 2 * lb, *outE = outH + lb;
+    const int *inH = border + (size_t)(b - 1) * 2 * lb, *inE = inH + lb;
+    const int prod = (b - 1) & (WF32_ONE_WARPS - 1);       // the warp that fills block b-1
+    if (lane == 0) { s_progress[warp] = 0; __threadfence_block(); s_block_of[warp] = b; }
+    const int c = (b << 5) + lane;
+    const bool colvalid = c < la;
+    const int qa = colvalid ? (int)sa[c] * alpha : 0;
+    int F = 0, hleft_prev = 0, h_out = 0, e_out = 0;
+    EndCell cand = wf32_initial_candidate<MODE>();
+    uint32_t acc = 0;
+    const int lanes_used = min(32, la - (b << 5));
+    const int nsteps = lb + lanes_used - 1;
+    for (int s = 0; s < nsteps; ++s) {
+      if (b > 0 && s < lb && (s % WF32_ONE_CHUNK) == 0) {   // wait for the next chunk of the left block's border
+        const int need = min(lb, s + WF32_ONE_CHUNK);
+        if (lane == 0) while (s_block_of[prod] < b - 1 || (s_block_of[prod] == b - 1 && s_progress[prod] < need)) { }
+        __syncwarp();
+        __threadfence_block();
+      }
+      int h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
+      int e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+      const int r = s - lane;
+      if (lane == 0 && s < lb) {
+        if (b == 0) wf32_virtual_column<MODE>(s, go, ge, h_sh, e_sh);
+        else if (SMEM) { h_sh = inH[s]; e_sh = inE[s]; }
+        else { h_sh = __ldcg(inH + s); e_sh = __ldcg(inE + s); }
+      }
+      unsigned nib = 0;
+      if (r >= 0 && r < lb && colvalid) {
+        const int sub = s_matrix[qa + (int)sb[r]];
+        int h, eo;
+        nib = wf32_cell<MODE>(c, r, la, lb, sub, hleft_prev, e_sh, F, go, ge, h, eo, cand);
+        hleft_prev = h_sh;
+        h_out = h;
+        e_out = eo;
+        if (MODE == GLOBAL && c == la - 1 && r == lb - 1) corner = h;
+        if (lane == 31 && b + 1 < nblk) {
+          if (SMEM) { outH[r] = h; outE[r] = eo; } else { __stcg(outH + r, h); __stcg(outE + r, eo); }
+          if (((r + 1) % WF32_ONE_CHUNK) == 0 || r + 1 == lb) { __threadfence_block(); s_progress[warp] = r + 1; }
+        }
+      }
+      acc |= nib << ((s & 7) * 4);
+      if ((s & 7) == 7 || s == nsteps - 1) {
+        p.dir[((long long)b * steps8 + (s >> 3)) * 32 + lane] = acc;
+        acc = 0;
+      }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      EndCell o;
+      o.score = __shfl_xor_sync(ABV_FULL, cand.score, off);
+      o.col = __shfl_xor_sync(ABV_FULL, cand.col, off);
+      o.row = __shfl_xor_sync(ABV_FULL, cand.row, off);
+      if (end_better(o, cand)) cand = o;
+    }
+    if (cand.col >= 0 && cand.score >= wbest.score) wbest = cand;
+    if (MODE == GLOBAL && b == nblk - 1) {
+      corner = __shfl_sync(ABV_FULL, corner, (la - 1) & 31);
+      if (lane == 0) s_corner = corner;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) { s_best[3 * warp] = wbest.score; s_best[3 * warp + 1] = wbest.col; s_best[3 * warp + 2] = wbest.row; }
+  __threadfence();
+  __syncthreads();
+  if (warp != 0) return;
+  // warps own interleaved blocks: the overall end cell is the best by (score, then larger column)
+  EndCell best = wf32_initial_candidate<MODE>();
+  for (int w = 0; w < WF32_ONE_WARPS; ++w) {
+    EndCell o; o.score = s_best[3 * w]; o.col = s_best[3 * w + 1]; o.row = s_best[3 * w + 2];
+    if (o.col >= 0 && (best.col < 0 || end_better(o, best))) best = o;
+  }
   int score, ec, er;
-  wf32_fill<MODE, true, false>(sa, p.la, sb, p.lb, s_matrix, alpha, p.go, p.ge, p.dir, p.border, p.border + p.lb, nullptr, lane, score, ec, er);
-  __syncwarp();
+  wf32_finish<MODE>(best, MODE == GLOBAL ? s_corner : 0, la, lb, score, ec, er);
   int n = 0;
   if (lane == 0) {
-    DirReader rd; rd.w = p.dir; rd.steps8 = dir_steps8(p.lb);
+    DirReader rd; rd.w = p.dir; rd.steps8 = steps8;
     n = walk_back<MODE>(rd, ec, er, p.tmp, p.tmp_cap);
     p.out[0] = score; p.out[1] = n;
   }

@@ -441,3 +441,20 @@ def test_packed_vs_wf32_random_sweep(B):
         bad = np.argwhere(got != want)
         assert bad.size == 0, (it, mode, alpha, go, ge, bad[:3], len(queries[bad[0][0]]), len(targets[bad[0][1]]))
         assert (got_hits[0] == want_hits[0]).all() and (got_hits[1] == want_hits[1]).all(), (it, mode, seed)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_legacy_single_calls_fuzz(A, oracle_port, mode):
+    """the lean one-launch path behind the reference's own symbols: the column blocks of the one pair are
+    pipelined over the warps of a CTA, so lengths around the 32-column block and 8-block round boundaries matter"""
+    rng = random.Random(500 + mode)
+    for it in range(60):
+        la = rng.choice([1, 2, 31, 32, 33, 64, 255, 256, 257, 289, rng.randint(3, 700), rng.randint(3, 300)])
+        lb = rng.choice([1, 2, 15, 16, 17, 32, 33, rng.randint(3, 700), rng.randint(3, 300)])
+        a = rand_dna(rng, la, "ACGTN")
+        b = mutate(rng, a, rng.randint(0, 6)) if rng.random() < 0.5 else rand_dna(rng, lb, "ACGT")
+        if (mode == O.GLOCAL and len(b) < 2) or (mode == O.OVERLAP and len(a) < 2):
+            continue
+        go, ge = rng.choice([(-7, -1), (-7, -1), (0, -2), (-3, 0)])
+        want = oracle_port.align(mode, a.encode(), b.encode(), go=go, ge=ge)
+        assert legacy(A, mode, a.encode(), b.encode(), go=go, ge=ge) == want, (it, la, len(b), go, ge)
