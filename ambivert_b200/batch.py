@@ -47,6 +47,7 @@ _lib.abv_gapped_pairs.argtypes = [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int,
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, _vp]
 _lib.abv_merge_pairs.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int,
                                  _vp, _vp, _vp, _vp, C.c_longlong, _vp]
+_lib.abv_cluster_pairs.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]
 _lib.abv_get_timing.argtypes = [_vp, C.c_int]
 _lib.abv_int_peak.argtypes = [C.c_int, C.c_int, _vp, _vp]
 
@@ -263,6 +264,28 @@ def merge_pairs(fwds, revs, minimum_overlap=10, alpha_len=DNA_MAP[0], map256=DNA
     _check(_lib.abv_merge_pairs(_ptr(a), _ptr(ao), _ptr(b), _ptr(bo), n, alpha_len, _ptr(mp), _ptr(m), gap_open, gap_extend,
                                 int(minimum_overlap), _ptr(scores), _ptr(status), _ptr(off), _ptr(merged), cap, C.byref(total)))
     return scores, status, off, merged[:total.value]
+
+
+def cluster_pairs(fwds, revs, trim5=None, trim3=None):
+    """Cluster read pairs by md5(f[trim5:trim3] + r[trim5:trim3]) on the device (AmpliconData.add_reads,
+    ambivert.py:244-262).  trim3 is the slice stop as the reference stores it (None or a negative number).
+    -> (cluster_of int32[n], keys: list of hexdigests in order of first occurrence, count int32[k], first int32[k])"""
+    a, ao = pack(fwds)
+    b, bo = pack(revs)
+    n = len(ao) - 1
+    assert len(bo) - 1 == n
+    cluster_of = np.empty(n, np.int32)
+    digest = np.empty((max(n, 1), 16), np.uint8)
+    count = np.empty(max(n, 1), np.int32)
+    first = np.empty(max(n, 1), np.int32)
+    k = C.c_int(0)
+    _check(_lib.abv_cluster_pairs(_ptr(a), _ptr(ao), _ptr(b), _ptr(bo), n, 0 if trim5 is None else 1, 0 if trim5 is None else int(trim5),
+                                  0 if trim3 is None else 1, 0 if trim3 is None else int(trim3),
+                                  _ptr(cluster_of), C.byref(k), _ptr(digest), _ptr(count), _ptr(first)))
+    k = k.value
+    hexes = digest[:k].tobytes().hex()
+    keys = [hexes[32 * i:32 * i + 32] for i in range(k)]
+    return cluster_of, keys, count[:k], first[:k]
 
 
 def fragments(k, start, count, frags):

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -13,6 +14,7 @@
 #include <vector>
 
 #include "../../include/ambivert_align.h"
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "kernels.cuh"
@@ -964,6 +966,107 @@ int abv_gapped_pairs(int mode, const char *a, const long long *a_off, const char
   if (!map256) return fail(ABV_ERR_ARGS, "abv_gapped_pairs needs character input and a map");
   return assemble_impl(ASSEMBLE_GAPPED, mode, a, a_off, b, b_off, n, alpha_len, map256, score_matrix, gap_open, gap_extend,
                        0, scores, status, start_a, start_b, out_off, gapped_a, gapped_b, out_cap, out_total);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Clustering front end: md5 keys of read pairs + grouping, on the device.
+__global__ void gather_u64_kernel(const unsigned long long *in, const unsigned int *idx, int n, unsigned long long *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[idx[i]];
+}
+
+int abv_cluster_pairs(const char *fwd, const long long *fwd_off, const char *rev, const long long *rev_off, int n,
+                      int has_trim5, int trim5, int has_trim3, int trim3,
+                      int *cluster_of, int *n_clusters, unsigned char *digest, int *count, int *first) {
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  if (n < 0) return fail(ABV_ERR_ARGS, "negative count");
+  if (n_clusters) *n_clusters = 0;
+  if (n == 0) return ABV_OK;
+  if (!fwd_off || !rev_off || !cluster_of || !n_clusters || !digest || !count || !first) return fail(ABV_ERR_ARGS, "NULL argument");
+  const long long fbytes = fwd_off[n] - fwd_off[0], rbytes = rev_off[n] - rev_off[0];
+  if ((fbytes > 0 && !fwd) || (rbytes > 0 && !rev)) return fail(ABV_ERR_ARGS, "NULL read buffer");
+  for (int i = 0; i < n; ++i)
+    if (fwd_off[i + 1] < fwd_off[i] || rev_off[i + 1] < rev_off[i]) return fail(ABV_ERR_ARGS, "offsets must not decrease");
+  int rc;
+  if ((rc = ctx_init())) return rc;
+  for (double &v : t_timing) v = 0;
+  cudaStream_t st = g.stream;
+  static bool k_ready = false;
+  if (!k_ready) {      // K[i] = floor(2^32 * |sin(i + 1)|)  (RFC 1321, section 3.4)
+    uint32_t k[64];
+    for (int i = 0; i < 64; ++i) k[i] = (uint32_t)(long long)floor(fabs(sin((double)(i + 1))) * 4294967296.0);
+    CU(cudaMemcpyToSymbol(c_md5_k, k, sizeof k));
+    k_ready = true;
+  }
+  CU(cudaEventRecord(g.ev[0], st));
+  DevMem df, dfo, dr, dro, lo, hi, lo2, hi2, idx, idx2, flag, seg, tmp, run_start, run_first, run_first_s, run_id, order_run, rank_of_run,
+      d_cluster, d_digest, d_count, d_first;
+  std::vector<long long> fo(n + 1), ro(n + 1);
+  for (int i = 0; i <= n; ++i) { fo[i] = fwd_off[i] - fwd_off[0]; ro[i] = rev_off[i] - rev_off[0]; }
+  CU(df.alloc((size_t)fbytes + 16)); CU(dr.alloc((size_t)rbytes + 16));
+  CU(dfo.alloc(sizeof(long long) * (n + 1))); CU(dro.alloc(sizeof(long long) * (n + 1)));
+  if (fbytes) CU(cudaMemcpyAsync(df.p, fwd + fwd_off[0], (size_t)fbytes, cudaMemcpyHostToDevice, st));
+  if (rbytes) CU(cudaMemcpyAsync(dr.p, rev + rev_off[0], (size_t)rbytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dfo.p, fo.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dro.p, ro.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
+  const size_t n8 = sizeof(unsigned long long) * (size_t)n, n4 = sizeof(int) * (size_t)n;
+  CU(lo.alloc(n8)); CU(hi.alloc(n8)); CU(lo2.alloc(n8)); CU(hi2.alloc(n8)); CU(idx.alloc(n4)); CU(idx2.alloc(n4));
+  CU(flag.alloc(n4)); CU(seg.alloc(n4));
+  CU(cudaEventRecord(g.ev[1], st));
+  const int tb = 256, nb = (n + tb - 1) / tb;
+  Md5Params mp{};
+  mp.f = df.as<uint8_t>(); mp.f_off = dfo.as<long long>(); mp.r = dr.as<uint8_t>(); mp.r_off = dro.as<long long>(); mp.n = n;
+  mp.has5 = has_trim5; mp.trim5 = trim5; mp.has3 = has_trim3; mp.trim3 = trim3;
+  mp.lo = lo.as<unsigned long long>(); mp.hi = hi.as<unsigned long long>(); mp.index = idx.as<unsigned int>();
+  md5_pairs_kernel<<<(n + 127) / 128, 128, 0, st>>>(mp);
+  CU(cudaGetLastError());
+  // stable LSD radix sort of the 128-bit digests: by the low word, then by the high word
+  size_t t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, t1, lo.as<unsigned long long>(), lo2.as<unsigned long long>(), idx.as<unsigned int>(), idx2.as<unsigned int>(), n, 0, 64, st));
+  CU(cub::DeviceScan::InclusiveSum(nullptr, t2, flag.as<int>(), seg.as<int>(), n, st));
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, t3, run_first.as<unsigned int>(), run_first_s.as<unsigned int>(), run_id.as<int>(), order_run.as<int>(), n, 0, 32, st));
+  t4 = std::max(t1, std::max(t2, t3));
+  CU(tmp.alloc(t4));
+  size_t tt = t4;
+  CU(cub::DeviceRadixSort::SortPairs(tmp.p, tt, lo.as<unsigned long long>(), lo2.as<unsigned long long>(), idx.as<unsigned int>(), idx2.as<unsigned int>(), n, 0, 64, st));
+  gather_u64_kernel<<<nb, tb, 0, st>>>(hi.as<unsigned long long>(), idx2.as<unsigned int>(), n, hi2.as<unsigned long long>());
+  tt = t4;
+  CU(cub::DeviceRadixSort::SortPairs(tmp.p, tt, hi2.as<unsigned long long>(), hi.as<unsigned long long>(), idx2.as<unsigned int>(), idx.as<unsigned int>(), n, 0, 64, st));
+  // idx = input index of the i-th pair in sorted order; hi = sorted high words; fetch the matching low words
+  CU(cudaMemcpyAsync(lo2.p, lo.p, n8, cudaMemcpyDeviceToDevice, st));       // lo2 = low words in INPUT order
+  gather_u64_kernel<<<nb, tb, 0, st>>>(lo2.as<unsigned long long>(), idx.as<unsigned int>(), n, lo.as<unsigned long long>());
+  cluster_flag_kernel<<<nb, tb, 0, st>>>(lo.as<unsigned long long>(), hi.as<unsigned long long>(), n, flag.as<int>());
+  tt = t4;
+  CU(cub::DeviceScan::InclusiveSum(tmp.p, tt, flag.as<int>(), seg.as<int>(), n, st));
+  int n_runs = 0;
+  CU(cudaMemcpyAsync(&n_runs, seg.as<int>() + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const size_t r4 = sizeof(int) * (size_t)n_runs;
+  CU(run_start.alloc(r4)); CU(run_first.alloc(r4)); CU(run_first_s.alloc(r4)); CU(run_id.alloc(r4)); CU(order_run.alloc(r4)); CU(rank_of_run.alloc(r4));
+  CU(d_cluster.alloc(n4)); CU(d_digest.alloc((size_t)16 * n_runs)); CU(d_count.alloc(r4)); CU(d_first.alloc(r4));
+  cluster_runs_kernel<<<nb, tb, 0, st>>>(flag.as<int>(), seg.as<int>(), idx.as<unsigned int>(), n, run_start.as<int>(), run_first.as<unsigned int>(), run_id.as<int>());
+  tt = t4;
+  CU(cub::DeviceRadixSort::SortPairs(tmp.p, tt, run_first.as<unsigned int>(), run_first_s.as<unsigned int>(), run_id.as<int>(), order_run.as<int>(), n_runs, 0, 32, st));
+  cluster_emit_kernel<<<(n_runs + tb - 1) / tb, tb, 0, st>>>(order_run.as<int>(), n_runs, run_start.as<int>(), run_first_s.as<unsigned int>(), n,
+                                                            lo.as<unsigned long long>(), hi.as<unsigned long long>(), d_digest.as<unsigned char>(),
+                                                            d_count.as<int>(), d_first.as<int>(), rank_of_run.as<int>());
+  cluster_assign_kernel<<<nb, tb, 0, st>>>(seg.as<int>(), idx.as<unsigned int>(), n, rank_of_run.as<int>(), d_cluster.as<int>(), d_count.as<int>());
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(g.ev[2], st));
+  CU(cudaMemcpyAsync(cluster_of, d_cluster.p, n4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(digest, d_digest.p, (size_t)16 * n_runs, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(count, d_count.p, r4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(first, d_first.p, r4, cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(g.ev[3], st));
+  CU(cudaStreamSynchronize(st));
+  *n_clusters = n_runs;
+  float a = 0, b = 0, c = 0;
+  cudaEventElapsedTime(&a, g.ev[0], g.ev[1]);
+  cudaEventElapsedTime(&b, g.ev[1], g.ev[2]);
+  cudaEventElapsedTime(&c, g.ev[2], g.ev[3]);
+  t_timing[0] = a; t_timing[1] = b; t_timing[2] = c; t_timing[3] = 0; t_timing[4] = 11;
+  t_timing[5] = (double)fbytes + rbytes + 16.0 * (n + 1); t_timing[6] = 4.0 * n + 24.0 * n_runs; t_timing[7] = b;
+  return ABV_OK;
 }
 
 int abv_get_timing(double *out, int n) {

@@ -449,6 +449,117 @@ __global__ void assemble_kernel(AssembleParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Clustering front end: the key of a read pair is the MD5 (RFC 1321) of its trimmed
+// forward + reverse sequence, md5(f_seq[trim5:trim3] + r_seq[trim5:trim3]) (ambivert.py:259); identical
+// keys form one cluster.  One thread hashes one pair straight from the read buffers.
+struct Md5Params {
+  const uint8_t *f; const long long *f_off;
+  const uint8_t *r; const long long *r_off;
+  int n;
+  int has5, trim5;      // Python slice start: None or an int (negative counts from the end)
+  int has3, trim3;      // Python slice stop: None or -abs(trim3)
+  unsigned long long *lo, *hi;   // digest bytes 0-7 and 8-15 as little-endian words
+  unsigned int *index;           // 0..n-1 (the sort's payload)
+};
+__constant__ uint32_t c_md5_k[64];
+
+__host__ __device__ inline void py_slice(long long len, int has_start, long long start, int has_stop, long long stop,
+                                         long long &b, long long &e) {
+  b = has_start ? (start < 0 ? (start + len < 0 ? 0 : start + len) : (start > len ? len : start)) : 0;
+  e = has_stop ? (stop < 0 ? (stop + len < 0 ? 0 : stop + len) : (stop > len ? len : stop)) : len;
+  if (e < b) e = b;
+}
+
+__global__ void md5_pairs_kernel(Md5Params p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const uint8_t *f = p.f + p.f_off[i], *r = p.r + p.r_off[i];
+  long long fb, fe, rb, re;
+  py_slice(p.f_off[i + 1] - p.f_off[i], p.has5, p.trim5, p.has3, p.trim3, fb, fe);
+  py_slice(p.r_off[i + 1] - p.r_off[i], p.has5, p.trim5, p.has3, p.trim3, rb, re);
+  const long long lf = fe - fb, L = lf + (re - rb);
+  f += fb; r += rb;
+  uint32_t a0 = 0x67452301u, b0 = 0xefcdab89u, c0 = 0x98badcfeu, d0 = 0x10325476u;
+  const long long nblocks = (L + 9 + 63) / 64;
+  const unsigned long long bits = (unsigned long long)L * 8ull;
+  for (long long blk = 0; blk < nblocks; ++blk) {
+    uint32_t M[16];
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long pos = blk * 64 + w * 4 + k;
+        uint32_t byte;
+        if (pos < lf) byte = f[pos];
+        else if (pos < L) byte = r[pos - lf];
+        else if (pos == L) byte = 0x80u;
+        else if (blk == nblocks - 1 && w >= 14) byte = (uint32_t)((bits >> (8 * ((w - 14) * 4 + k))) & 0xffull);
+        else byte = 0;
+        v |= byte << (8 * k);
+      }
+      M[w] = v;
+    }
+    uint32_t A = a0, B = b0, C = c0, D = d0;
+#pragma unroll
+    for (int t = 0; t < 64; ++t) {
+      uint32_t F; int g;
+      if (t < 16) { F = (B & C) | (~B & D); g = t; }
+      else if (t < 32) { F = (D & B) | (~D & C); g = (5 * t + 1) & 15; }
+      else if (t < 48) { F = B ^ C ^ D; g = (3 * t + 5) & 15; }
+      else { F = C ^ (B | ~D); g = (7 * t) & 15; }
+      const int sh = t < 16 ? (t % 4 == 0 ? 7 : t % 4 == 1 ? 12 : t % 4 == 2 ? 17 : 22)
+                   : t < 32 ? (t % 4 == 0 ? 5 : t % 4 == 1 ? 9 : t % 4 == 2 ? 14 : 20)
+                   : t < 48 ? (t % 4 == 0 ? 4 : t % 4 == 1 ? 11 : t % 4 == 2 ? 16 : 23)
+                            : (t % 4 == 0 ? 6 : t % 4 == 1 ? 10 : t % 4 == 2 ? 15 : 21);
+      F = F + A + c_md5_k[t] + M[g];
+      A = D; D = C; C = B;
+      B = B + ((F << sh) | (F >> (32 - sh)));
+    }
+    a0 += A; b0 += B; c0 += C; d0 += D;
+  }
+  p.lo[i] = (unsigned long long)a0 | ((unsigned long long)b0 << 32);
+  p.hi[i] = (unsigned long long)c0 | ((unsigned long long)d0 << 32);
+  p.index[i] = (unsigned)i;
+}
+
+// after the two stable radix sorts (by lo, then by hi) equal digests are adjacent and, inside a run, in input order
+__global__ void cluster_flag_kernel(const unsigned long long *lo, const unsigned long long *hi, int n, int *flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  flag[i] = (i == 0 || lo[i] != lo[i - 1] || hi[i] != hi[i - 1]) ? 1 : 0;
+}
+// per run: where it starts in the sorted order and which input pair comes first
+__global__ void cluster_runs_kernel(const int *flag, const int *seg, const unsigned int *index, int n, int *run_start, unsigned int *run_first, int *run_id) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  const int s = seg[i] - 1;
+  run_start[s] = i; run_first[s] = index[i]; run_id[s] = s;
+}
+// clusters are numbered in order of first occurrence (dict insertion order of AmpliconData.data)
+__global__ void cluster_emit_kernel(const int *order_run, int n_runs, const int *run_start, const unsigned int *run_first_sorted, int n,
+                                    const unsigned long long *lo, const unsigned long long *hi,
+                                    unsigned char *digest, int *count, int *first, int *rank_of_run) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_runs) return;
+  const int s = order_run[k];
+  const int b = run_start[s];
+  // the run ends where the next run (in sorted order) starts
+  rank_of_run[s] = k;
+  first[k] = (int)run_first_sorted[k];
+  const unsigned long long l = lo[b], h = hi[b];
+  for (int j = 0; j < 8; ++j) { digest[16 * k + j] = (unsigned char)(l >> (8 * j)); digest[16 * k + 8 + j] = (unsigned char)(h >> (8 * j)); }
+  count[k] = 0;   // filled by cluster_assign_kernel
+}
+__global__ void cluster_assign_kernel(const int *seg, const unsigned int *index, int n, const int *rank_of_run, int *cluster_of, int *count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = rank_of_run[seg[i] - 1];
+  cluster_of[index[i]] = k;
+  atomicAdd(count + k, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
 // per-query selection over a score matrix: strict '>' in target order from the seed
 // (ambivert.py:478-485): first maximum wins; idx -1 when nothing beats the seed.
 __global__ void argmax_rows_kernel(const int *__restrict__ scores, int n_rows, int n_t, int seed,

@@ -231,6 +231,24 @@ def load_hash_table(self, hashfile):
                           "without specifying an existing hash file.", UserWarning)
 
 
+def _parse_fastq(handle):
+    """(name, sequence, quality) of every 4-line FASTQ record, name without its leading character; the same
+    non-validating reading as the reference's parse_fastq (sequence_utilities.py:51-69): lines end at '\n'
+    only, bytes are latin-1, the file ends at the first empty name line"""
+    with handle as fastqfile:
+        text = fastqfile.read()
+    if isinstance(text, bytes):
+        text = text.decode("latin-1")
+    lines = text.split("\n")
+    for i in range(0, len(lines), 4):
+        name = lines[i]
+        if not name:
+            return
+        seq = lines[i + 1] if i + 1 < len(lines) else ""
+        qual = lines[i + 3] if i + 3 < len(lines) else ""
+        yield (name[1:], seq, qual)
+
+
 class AmpliconData(object):
     """The state the hot path reads and writes (ambivert.py:202-228) with the on-path stages bound to
     the batched GPU implementations.  Parsing, variant calling and output stay with the reference."""
@@ -254,6 +272,25 @@ class AmpliconData(object):
         key = hashlib.md5(bytes(f_seq[self.trim5:self.trim3] + r_seq[self.trim5:self.trim3], "ascii")).hexdigest()
         self.data[key].append(((f_name, f_seq, f_qual), (r_name, r_seq, r_qual)))
         self.readpairs += 1
+
+    def add_read_pairs(self, pairs):
+        """Bulk add_reads: `pairs` is a sequence of ((f_name, f_seq, f_qual), (r_name, r_seq, r_qual)).  The md5
+        keys and the grouping are computed on the device in one call (abv_cluster_pairs); self.data ends up exactly
+        as after calling add_reads on every pair in order (same keys, same insertion order, same lists)."""
+        pairs = list(pairs)
+        if not pairs:
+            return
+        cluster_of, keys, _count, _first = B.cluster_pairs(_ascii(p[0][1] for p in pairs), _ascii(p[1][1] for p in pairs),
+                                                            self.trim5, self.trim3)
+        for pair, k in zip(pairs, cluster_of.tolist()):
+            self.data[keys[k]].append((tuple(pair[0]), tuple(pair[1])))
+        self.readpairs += len(pairs)
+
+    def process_twofile_readpairs(self, forward_file, reverse_file, parse_fastq=None):
+        """ambivert.py:264-289 with the keying done in bulk: reads both FASTQ files (4-line records, text or
+        bytes) and adds the pairs in file order."""
+        parse = parse_fastq or _parse_fastq
+        self.add_read_pairs(zip(parse(forward_file), parse(reverse_file)))
 
     get_above_threshold = get_above_threshold
     merge_overlaps = merge_overlaps

@@ -226,6 +226,36 @@ def merge_measurement(n_pairs):
             "kernel": "wf32_kernel<local,trace>", "timing": "best of 3 calls of abv_align_pairs (CUDA events inside the library for the kernel)"}
 
 
+def cluster_measurement(n_pairs):
+    """secondary: the step before the path -- md5 keys + grouping of read pairs on the device
+    (AmpliconData.add_reads, ambivert.py:244-262), beside hashlib in a Python loop on a sample"""
+    import hashlib
+    from ambivert_b200 import batch as B, synth
+    (f, fo), (r, ro) = synth.read_pairs_packed(n_pairs, seed=0xF2)
+    dup = np.random.default_rng(3).integers(0, n_pairs // 4, n_pairs)          # ~4 copies per unique pair, shuffled
+    f2, r2 = f.reshape(n_pairs, -1)[dup].reshape(-1), r.reshape(n_pairs, -1)[dup].reshape(-1)
+    B.cluster_pairs((f2[:150000], fo[:1001]), (r2[:150000], ro[:1001]))
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        cluster_of, keys, count, first = B.cluster_pairs((f2, fo), (r2, ro))
+        w = time.perf_counter() - t0
+        tm = B.timing()
+        if best is None or w < best[0]:
+            best = (w, tm["kernel_ms"], len(keys))
+    m = min(n_pairs, 100000)
+    fb, rb = f2.tobytes(), r2.tobytes()
+    t0 = time.perf_counter()
+    ref = {}
+    for i in range(m):
+        ref.setdefault(hashlib.md5(fb[150 * i:150 * i + 150] + rb[150 * i:150 * i + 150]).hexdigest(), []).append(i)
+    py_s = time.perf_counter() - t0
+    same = [keys[k] for k in cluster_of[:m]] == [k for k, v in sorted(((k, i) for k, v in ref.items() for i in v), key=lambda x: x[1])]
+    return {"workload": "md5 keying + grouping of %d read pairs (2 x 150 bp), ~4 copies per unique pair" % n_pairs,
+            "e2e_s": best[0], "device_ms": best[1], "pairs_per_s_e2e": n_pairs / best[0], "clusters": best[2],
+            "python_hashlib_pairs_per_s": m / py_s, "python_sample": m, "keys_match_hashlib_on_sample": bool(same)}
+
+
 def cuda_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -352,6 +382,7 @@ def cuda_arm(args, rank, world, local_rank):
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
         if world == 1 and args.merge_pairs > 0:
             line["merge"] = merge_measurement(args.merge_pairs)
+            line["cluster"] = cluster_measurement(args.merge_pairs)
         if world == 1 and not args.no_cpu_baseline:
             arm = cpu_arm(queries, targets, mode, args.cpu_seconds)
             sec, cells, bs, bi = arm["run"](queries[:arm["n"]])

@@ -220,6 +220,19 @@ int abv_merge_pairs(const char *fwd, const long long *fwd_off, const char *rev, 
                     long long *merged_total);
 
 /*
+ * The step before the path: the clustering of read pairs.  The key of a pair is
+ * md5(f_seq[trim5:trim3] + r_seq[trim5:trim3]) (AmpliconData.add_reads, ambivert.py:244-262; MD5 of RFC 1321,
+ * Python slice semantics: has_trim5/has_trim3 = 0 means None, trim3 is the already negated value the reference
+ * stores, ambivert.py:224); pairs with equal keys form a cluster.  Clusters are numbered in order of first
+ * occurrence (the insertion order of AmpliconData.data).  Outputs: cluster_of[n]; *n_clusters; for cluster k its raw
+ * 16-byte digest (hexdigest = hex of it) in digest[16k..], the number of pairs count[k] (what get_above_threshold
+ * compares, ambivert.py:291-299) and the index of its first pair first[k].  digest/count/first need room for n.
+ */
+int abv_cluster_pairs(const char *fwd, const long long *fwd_off, const char *rev, const long long *rev_off, int n,
+                      int has_trim5, int trim5, int has_trim3, int trim3,
+                      int *cluster_of, int *n_clusters, unsigned char *digest, int *count, int *first);
+
+/*
  * Timings of the last batched call of this thread, CUDA events on the library's stream:
  *   out[0] host->device ms, out[1] kernel ms, out[2] device->host ms, out[3] cells,
  *   out[4] kernel launches, out[5] bytes host->device, out[6] bytes device->host,
