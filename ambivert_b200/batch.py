@@ -48,6 +48,7 @@ _lib.abv_gapped_pairs.argtypes = [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int,
 _lib.abv_merge_pairs.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int,
                                  _vp, _vp, _vp, _vp, C.c_longlong, _vp]
 _lib.abv_cluster_pairs.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]
+_lib.abv_call_variants.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_longlong, _vp]
 _lib.abv_get_timing.argtypes = [_vp, C.c_int]
 _lib.abv_int_peak.argtypes = [C.c_int, C.c_int, _vp, _vp]
 
@@ -286,6 +287,37 @@ def cluster_pairs(fwds, revs, trim5=None, trim3=None):
     hexes = digest[:k].tobytes().hex()
     keys = [hexes[32 * i:32 * i + 32] for i in range(k)]
     return cluster_of, keys, count[:k], first[:k]
+
+
+VAR_X, VAR_D, VAR_I = 0, 1, 2
+VAR_ERR_LENGTH, VAR_ERR_INDEX = -1, -2
+
+
+def call_variants(samples, refs, softmask=True, gap="-"):
+    """Variant scan of aligned row pairs on the device (caller(), ambivert/call_variants.py:32-128).
+    -> (status int32[n], rec_start int64[n], rec_count int32[n], recs int32[total, 5])
+    a record is (kind, start, pos, len, run_start), see abv_call_variants in include/ambivert_align.h"""
+    a, ao = pack(samples)
+    b, bo = pack(refs)
+    n = len(ao) - 1
+    assert len(bo) - 1 == n
+    status = np.zeros(n, np.int32)
+    start = np.zeros(n, np.int64)
+    count = np.zeros(n, np.int32)
+    total = C.c_longlong(0)
+    cap = max(64, n // 2)
+    g = gap.encode("latin-1") if isinstance(gap, str) else bytes(gap)
+    if len(g) != 1:
+        raise ValueError("gap must be one character")
+    for _ in range(2):
+        recs = np.empty((cap, 5), np.int32)
+        rc = _lib.abv_call_variants(_ptr(a), _ptr(ao), _ptr(b), _ptr(bo), n, 1 if softmask else 0, g[0],
+                                    _ptr(status), _ptr(start), _ptr(count), _ptr(recs), cap, C.byref(total))
+        if rc != ERR_FRAG_CAP:
+            break
+        cap = total.value
+    _check(rc)
+    return status, start, count, recs[:total.value]
 
 
 def fragments(k, start, count, frags):

@@ -1069,6 +1069,102 @@ int abv_cluster_pairs(const char *fwd, const long long *fwd_off, const char *rev
   return ABV_OK;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Variant scan of aligned row pairs (call_variants.py:32-128) on rows that are already
+// on the device: COUNT pass, exclusive scan, EMIT pass.  d_status [n], d_count/d_start [n+1].
+static int variants_on_device(const uint8_t *d_sample, const long long *d_sample_off, const uint8_t *d_ref, const long long *d_ref_off,
+                              int n, int softmask, int gap, cudaStream_t st, DevMem &d_status, DevMem &d_count, DevMem &d_start,
+                              DevMem &d_recs, long long &total) {
+  static_assert(sizeof(VariantRec) == sizeof(abv_variant), "record layout");
+  DevMem scan_tmp;
+  CU(d_status.alloc(sizeof(int) * (size_t)n));
+  CU(d_count.alloc(sizeof(long long) * ((size_t)n + 1)));
+  CU(d_start.alloc(sizeof(long long) * ((size_t)n + 1)));
+  VariantParams p{};
+  p.sample = d_sample; p.sample_off = d_sample_off; p.ref = d_ref; p.ref_off = d_ref_off;
+  p.n = n; p.softmask = softmask; p.gap = gap;
+  p.status = d_status.as<int>(); p.count = d_count.as<long long>(); p.start = d_start.as<long long>();
+  const int tb = 128, nb = (n + tb - 1) / tb;
+  variants_kernel<false><<<nb, tb, 0, st>>>(p);
+  CU(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_count.as<long long>(), d_start.as<long long>(), n + 1, st));
+  CU(scan_tmp.alloc(tmp_bytes));
+  CU(cub::DeviceScan::ExclusiveSum(scan_tmp.p, tmp_bytes, d_count.as<long long>(), d_start.as<long long>(), n + 1, st));
+  total = 0;
+  CU(cudaMemcpyAsync(&total, d_start.as<long long>() + n, sizeof total, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (total > 0) {
+    CU(d_recs.alloc(sizeof(VariantRec) * (size_t)total));
+    p.recs = d_recs.as<VariantRec>();
+    variants_kernel<true><<<nb, tb, 0, st>>>(p);
+    CU(cudaGetLastError());
+  }
+  return ABV_OK;
+}
+
+// copies status / starts / counts / records of a finished variant scan to the caller
+static int variants_fetch(int n, cudaStream_t st, const DevMem &d_status, const DevMem &d_start, const DevMem &d_recs, long long total,
+                          int *status, long long *rec_start, int *rec_count, abv_variant *recs, long long rec_cap) {
+  std::vector<long long> starts((size_t)n + 1);
+  CU(cudaMemcpyAsync(status, d_status.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(starts.data(), d_start.p, sizeof(long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
+  const bool fits = total <= rec_cap;
+  if (fits && total > 0) CU(cudaMemcpyAsync(recs, d_recs.p, sizeof(abv_variant) * (size_t)total, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int i = 0; i < n; ++i) { rec_start[i] = starts[i]; rec_count[i] = (int)(starts[i + 1] - starts[i]); }
+  if (!fits) return fail(ABV_ERR_FRAG_CAP, "record buffer of %lld entries is too small, %lld needed", rec_cap, total);
+  return ABV_OK;
+}
+
+int abv_call_variants(const char *sample, const long long *sample_off, const char *ref, const long long *ref_off, int n,
+                      int softmask, int gap, int *status, long long *rec_start, int *rec_count,
+                      abv_variant *recs, long long rec_cap, long long *rec_total) {
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  if (n < 0) return fail(ABV_ERR_ARGS, "negative count");
+  if (rec_total) *rec_total = 0;
+  if (n == 0) return ABV_OK;
+  if (!sample_off || !ref_off || !status || !rec_start || !rec_count || rec_cap < 0 || (rec_cap > 0 && !recs))
+    return fail(ABV_ERR_ARGS, "NULL argument");
+  if (gap < 0 || gap > 255) return fail(ABV_ERR_ARGS, "gap must be one byte");
+  const long long sbytes = sample_off[n] - sample_off[0], rbytes = ref_off[n] - ref_off[0];
+  if ((sbytes > 0 && !sample) || (rbytes > 0 && !ref)) return fail(ABV_ERR_ARGS, "NULL row buffer");
+  for (int i = 0; i < n; ++i) {
+    if (sample_off[i + 1] < sample_off[i] || ref_off[i + 1] < ref_off[i]) return fail(ABV_ERR_ARGS, "offsets must not decrease");
+    if (sample_off[i + 1] - sample_off[i] > INT_MAX / 2) return fail(ABV_ERR_ARGS, "row %d is too long", i);
+  }
+  int rc;
+  if ((rc = ctx_init())) return rc;
+  for (double &v : t_timing) v = 0;
+  cudaStream_t st = g.stream;
+  CU(cudaEventRecord(g.ev[0], st));
+  DevMem ds, dso, dr, dro, d_status, d_count, d_start, d_recs;
+  std::vector<long long> so((size_t)n + 1), ro((size_t)n + 1);
+  for (int i = 0; i <= n; ++i) { so[i] = sample_off[i] - sample_off[0]; ro[i] = ref_off[i] - ref_off[0]; }
+  CU(ds.alloc((size_t)sbytes + 16)); CU(dr.alloc((size_t)rbytes + 16));
+  CU(dso.alloc(sizeof(long long) * ((size_t)n + 1))); CU(dro.alloc(sizeof(long long) * ((size_t)n + 1)));
+  if (sbytes) CU(cudaMemcpyAsync(ds.p, sample + sample_off[0], (size_t)sbytes, cudaMemcpyHostToDevice, st));
+  if (rbytes) CU(cudaMemcpyAsync(dr.p, ref + ref_off[0], (size_t)rbytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dso.p, so.data(), sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dro.p, ro.data(), sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(g.ev[1], st));
+  long long total = 0;
+  if ((rc = variants_on_device(ds.as<uint8_t>(), dso.as<long long>(), dr.as<uint8_t>(), dro.as<long long>(), n, softmask, gap, st,
+                               d_status, d_count, d_start, d_recs, total))) return rc;
+  CU(cudaEventRecord(g.ev[2], st));
+  if (rec_total) *rec_total = total;
+  rc = variants_fetch(n, st, d_status, d_start, d_recs, total, status, rec_start, rec_count, recs, rec_cap);
+  CU(cudaEventRecord(g.ev[3], st));
+  CU(cudaStreamSynchronize(st));
+  float a = 0, b = 0, c = 0;
+  cudaEventElapsedTime(&a, g.ev[0], g.ev[1]);
+  cudaEventElapsedTime(&b, g.ev[1], g.ev[2]);
+  cudaEventElapsedTime(&c, g.ev[2], g.ev[3]);
+  t_timing[0] = a; t_timing[1] = b; t_timing[2] = c; t_timing[3] = 0; t_timing[4] = total > 0 ? 4 : 3;
+  t_timing[5] = (double)sbytes + rbytes + 16.0 * (n + 1); t_timing[6] = 12.0 * n + 8.0 + 20.0 * (double)total; t_timing[7] = b;
+  return rc;
+}
+
 int abv_get_timing(double *out, int n) {
   if (!out || n <= 0) return 0;
   n = std::min(n, 8);

@@ -368,6 +368,76 @@ ABV_HD void mm16d_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Variant scan of one aligned (sample row, reference row) pair: the step after the aligner
+// (ambivert/call_variants.py:32-128, caller()).  The reference walks the
+// two gapped rows site by site with three accumulating strings (mismatch, deletion, insertion) and
+// yields (type, start in the gapped rows, one-based position in the ungapped reference, bases).  The
+// strings only ever grow over consecutive sites, so a length and the site of the first base stand
+// for each; a record is {kind, start, pos, len, run_start}: `start` and `pos` are the numbers the
+// reference yields (call_variants.py:83-127, including its end-of-row arithmetic), the bases are
+// row[run_start, run_start + len) of the sample row (X, I) or of the reference row (D).
+//   softmask rules (call_variants.py:58-76): lower-case reference = primer; leading primer sites only
+//   advance the position; a gap inside the leading primer is skipped, one that abuts unmasked sequence is
+//   scanned; the first lower-case site after unmasked sequence ends the scan.
+// Returns 0, or VAR_ERR_INDEX where the reference's look-ahead over a gap run leaves the row
+// (IndexError, call_variants.py:66).  Python's str.lower()/upper() on ASCII.
+enum { VAR_X = 0, VAR_D = 1, VAR_I = 2 };
+enum { VAR_OK = 0, VAR_ERR_LENGTH = -1, VAR_ERR_INDEX = -2 };
+
+ABV_HD bool var_is_own_lower(unsigned char c) { return !(c >= 'A' && c <= 'Z'); }        // c == c.lower()
+ABV_HD unsigned char var_upper(unsigned char c) { return (c >= 'a' && c <= 'z') ? (unsigned char)(c - 32) : c; }
+
+template <class Emit>
+ABV_HD int variants_walk(const unsigned char *v, const unsigned char *r, int n, bool softmask, unsigned char gap, Emit emit) {
+  int mm = 0, del = 0, ins = 0, mm_at = 0, del_at = 0, ins_at = 0, pos = 0, site = 0;
+  bool masked = true;
+  for (int i = 0; i < n; ++i) {
+    site = i;
+    const unsigned char rc = r[i], vc = v[i];
+    const bool r_gap = rc == gap, r_low = var_is_own_lower(rc);
+    if (softmask && masked && r_low && !r_gap) { ++pos; continue; }                  // :58-61 leading primer
+    else if (softmask && masked && r_gap) {                                           // :62-69
+      int g = 0;
+      for (;;) {
+        if (i + g >= n) return VAR_ERR_INDEX;
+        if (r[i + g] != gap) break;
+        ++g;
+      }
+      if (var_is_own_lower(r[i + g])) continue;                                       // gap within the primer
+    } else if (softmask && !masked && !r_gap && r_low) break;                         // :70-72 trailing primer
+    else masked = false;                                                              // :73-75
+
+    if (var_upper(vc) == var_upper(rc) && !r_gap && vc != gap) {                      // :77-88 match
+      ++pos;
+      if (mm) { emit(VAR_X, i - mm, pos - mm, mm, mm_at); mm = 0; }
+      else if (del) { emit(VAR_D, i - del, pos - del, del, del_at); del = 0; }
+      else if (ins) { emit(VAR_I, i - ins, pos, ins, ins_at); ins = 0; }
+    } else if (r_gap) {                                                               // :89-96 insertion grows
+      if (!ins) ins_at = i;
+      ++ins;
+      if (mm) { emit(VAR_X, i - mm, pos - mm, mm, mm_at); mm = 0; }
+      else if (del) { emit(VAR_D, i - del, pos - del + 1, del, del_at); del = 0; }
+    } else if (vc == gap) {                                                           // :97-105 deletion grows
+      if (!del) del_at = i;
+      ++del; ++pos;
+      if (mm) { emit(VAR_X, i - mm, pos - mm, mm, mm_at); mm = 0; }
+      else if (ins) { emit(VAR_I, i - ins, pos, ins, ins_at); ins = 0; }
+    } else {                                                                          // :106-117 substitution
+      ++pos;
+      if (mm) { emit(VAR_X, i - mm, pos - mm, mm, mm_at); }
+      mm = 1; mm_at = i;
+      if (ins) { emit(VAR_I, i - ins, pos, ins, ins_at); ins = 0; }
+      else if (del) { emit(VAR_D, i - del, pos - del, del, del_at); del = 0; }
+    }
+  }
+  ++pos;                                                                              // :119-128 states left at the end
+  if (mm) emit(VAR_X, site - mm + 1, pos - mm, mm, mm_at);
+  if (del) emit(VAR_D, site - del + 1, pos - del, del, del_at);
+  if (ins) emit(VAR_I, site - ins + 1, pos, ins, ins_at);
+  return VAR_OK;
+}
+
 // pair-row bookkeeping of the streaming kernel, shared by the kernel and its CPU mirror
 constexpr int MM16G_MIN_ROWS = 32;   // every pair occupies at least 32 steps: lane t switches pair t steps after lane 0
 ABV_HD int mm16g_rows(int l1, int l2) {

@@ -449,6 +449,49 @@ __global__ void assemble_kernel(AssembleParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Variant scan of aligned row pairs (call_variants.py:32-128): one thread walks one
+// pair of gapped rows with variants_walk (dp_core.cuh).  Two passes over the same walk: COUNT sizes the
+// record list of every pair (then one exclusive scan places them), EMIT writes the records.  Byte work
+// bound by HBM/L2: each row is read once per pass, 2 x row length bytes per pair; threads of a warp read
+// neighbouring rows, whose 128-byte lines stay in L1 while the thread walks them.
+struct VariantRec { int kind, start, pos, len, run_start; };
+struct VariantParams {
+  const uint8_t *sample; const long long *sample_off;     // gapped sample rows
+  const uint8_t *ref; const long long *ref_off;           // gapped reference rows
+  int n, softmask, gap;
+  int *status;                 // [n]  VAR_OK / VAR_ERR_LENGTH / VAR_ERR_INDEX
+  long long *count;            // [n+1] records per pair (COUNT pass; element n = 0 for the scan)
+  const long long *start;      // [n+1] exclusive scan of count (EMIT pass)
+  VariantRec *recs;
+};
+
+template <bool EMIT>
+__global__ void variants_kernel(VariantParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (!EMIT && i == 0) p.count[p.n] = 0;
+  if (i >= p.n) return;
+  const long long s0 = p.sample_off[i], r0 = p.ref_off[i];
+  const long long ls = p.sample_off[i + 1] - s0, lr = p.ref_off[i + 1] - r0;
+  if (ls != lr) {                                      // RuntimeError, call_variants.py:54-55
+    if (!EMIT) { p.status[i] = VAR_ERR_LENGTH; p.count[i] = 0; }
+    return;
+  }
+  if (EMIT) {
+    if (p.status[i] != VAR_OK) return;
+    VariantRec *out = p.recs + p.start[i];
+    int k = 0;
+    variants_walk(p.sample + s0, p.ref + r0, (int)ls, p.softmask != 0, (unsigned char)p.gap,
+                  [&](int kind, int start, int pos, int len, int at) { out[k++] = VariantRec{kind, start, pos, len, at}; });
+  } else {
+    int k = 0;
+    const int rc = variants_walk(p.sample + s0, p.ref + r0, (int)ls, p.softmask != 0, (unsigned char)p.gap,
+                                 [&](int, int, int, int, int) { ++k; });
+    p.status[i] = rc;
+    p.count[i] = rc == VAR_OK ? k : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Clustering front end: the key of a read pair is the MD5 (RFC 1321) of its trimmed
 // forward + reverse sequence, md5(f_seq[trim5:trim3] + r_seq[trim5:trim3]) (ambivert.py:259); identical
 // keys form one cluster.  One thread hashes one pair straight from the read buffers.

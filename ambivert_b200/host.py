@@ -249,9 +249,19 @@ def _parse_fastq(handle):
         yield (name[1:], seq, qual)
 
 
+def _from_variants(name):
+    """method of ambivert_b200.variants, looked up at call time (that module imports this one)"""
+    def method(self, *args, **kwargs):
+        from . import variants
+        return getattr(variants, name)(self, *args, **kwargs)
+    method.__name__ = name
+    return method
+
+
 class AmpliconData(object):
     """The state the hot path reads and writes (ambivert.py:202-228) with the on-path stages bound to
-    the batched GPU implementations.  Parsing, variant calling and output stay with the reference."""
+    the batched GPU implementations, and the steps either side of it (clustering, variant calling and
+    consolidation: SURVEY.md section 8f).  Manifest parsing and the SAM/FASTQ writers stay with the reference."""
 
     def __init__(self, trim5=None, trim3=None):
         self.data = defaultdict(list)      # {md5hexdigest: [((f_name, f_seq, f_qual), (r_name, r_seq, r_qual)), ...]}
@@ -262,6 +272,8 @@ class AmpliconData(object):
         self.reference = {}
         self.reference_sequences = {}      # {(name, chromosome, start, end, strand): sequence}
         self.potential_variants = []
+        self.called_variants = {}          # {md5hexdigest: [AmpliconVariant, ...]}
+        self.consolidated_variants = []
         self.trim5 = trim5
         self.trim3 = None if trim3 is None else -1 * abs(trim3)
         self.threshold = 0
@@ -298,3 +310,13 @@ class AmpliconData(object):
     align_to_reference = align_to_reference
     save_hash_table = save_hash_table
     load_hash_table = load_hash_table
+    get_amplicon_count = _from_variants("get_amplicon_count")
+    call_amplicon_variants = _from_variants("call_amplicon_variants")
+    get_variant_positions = _from_variants("get_variant_positions")
+    consolidate_variants = _from_variants("consolidate_variants")
+    get_filtered_variants = _from_variants("get_filtered_variants")
+    print_consolidated_vcf = _from_variants("print_consolidated_vcf")
+    get_amplicons_overlapping = _from_variants("get_amplicons_overlapping")
+    get_reference_overlapping = _from_variants("get_reference_overlapping")
+    get_amplicons_overlapping_without_softmasking = _from_variants("get_amplicons_overlapping_without_softmasking")
+    is_homopolymer_at_position = _from_variants("is_homopolymer_at_position")

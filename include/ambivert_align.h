@@ -233,6 +233,33 @@ int abv_cluster_pairs(const char *fwd, const long long *fwd_off, const char *rev
                       int *cluster_of, int *n_clusters, unsigned char *digest, int *count, int *first);
 
 /*
+ * The step after the path: the variant scan of aligned row pairs, replacing the
+ * per-site Python loop of caller() in ambivert/call_variants.py:32-128.  Pair k is the gapped sample row
+ * sample[sample_off[k] .. sample_off[k+1]) and the gapped reference row ref[ref_off[k] .. ref_off[k+1]) (what
+ * align_to_reference stores in AmpliconData.aligned, ambivert.py:556-573; abv_gapped_pairs produces them).
+ * softmask != 0: lower-case reference is primer sequence (the reference's default); gap: the gap character ('-').
+ * A record is what the reference yields, with the accumulated bases named by their place in the rows:
+ *   kind       ABV_VAR_X substitution, ABV_VAR_D deletion, ABV_VAR_I insertion
+ *   start      "Start": zero-based position in the gapped rows, as the reference computes it
+ *   pos        "Pos":   one-based position in the ungapped reference, as the reference computes it
+ *   len, run_start      "Bases" = row[run_start .. run_start+len) of the sample row (X, I) / reference row (D)
+ * status[k]: 0 ok; ABV_VAR_ERR_LENGTH rows of different length (RuntimeError, call_variants.py:54-55);
+ * ABV_VAR_ERR_INDEX the reference's look-ahead over a gap run leaves the row (IndexError, call_variants.py:66).
+ * rec_start[k], rec_count[k]: pair k's records in recs (caller-allocated, rec_cap entries); *rec_total = entries
+ * needed (ABV_ERR_FRAG_CAP if that exceeds rec_cap; status, rec_start and rec_count are valid even then).
+ */
+#define ABV_VAR_X 0
+#define ABV_VAR_D 1
+#define ABV_VAR_I 2
+#define ABV_VAR_ERR_LENGTH (-1)
+#define ABV_VAR_ERR_INDEX  (-2)
+typedef struct abv_variant { int kind, start, pos, len, run_start; } abv_variant;
+int abv_call_variants(const char *sample, const long long *sample_off, const char *ref, const long long *ref_off, int n,
+                      int softmask, int gap,
+                      int *status, long long *rec_start, int *rec_count,
+                      abv_variant *recs, long long rec_cap, long long *rec_total);
+
+/*
  * Timings of the last batched call of this thread, CUDA events on the library's stream:
  *   out[0] host->device ms, out[1] kernel ms, out[2] device->host ms, out[3] cells,
  *   out[4] kernel launches, out[5] bytes host->device, out[6] bytes device->host,

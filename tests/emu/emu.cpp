@@ -415,3 +415,17 @@ extern "C" int emu_mm16g(int mode, int K, const unsigned char *q, int lq, int n_
   } catch (...) { return -2; }   // an out-of-range symbol read: a pointer bookkeeping error
   return -1;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Variant scan (dp_core.cuh::variants_walk, the function variants_kernel runs per thread) on the host.
+// recs: 5 ints per record (kind, start, pos, len, run_start).  Returns the record count or a VAR_ERR_* code.
+extern "C" int emu_variants(const unsigned char *sample, int ls, const unsigned char *ref, int lr, int softmask, int gap,
+                            int *recs, int cap) {
+  if (ls != lr) return VAR_ERR_LENGTH;
+  int k = 0;
+  const int rc = variants_walk(sample, ref, ls, softmask != 0, (unsigned char)gap, [&](int kind, int start, int pos, int len, int at) {
+    if (k < cap) { int *o = recs + 5 * k; o[0] = kind; o[1] = start; o[2] = pos; o[3] = len; o[4] = at; }
+    ++k;
+  });
+  return rc == VAR_OK ? k : rc;
+}
