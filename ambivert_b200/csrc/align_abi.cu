@@ -50,6 +50,7 @@ struct Options {
   int mm16_blocks_per_sm = 0;   // 0 = what the occupancy query returns
   int split = 0;                // 0 = automatic; otherwise slices of the target pairs per query
   int global_v1 = 0;            // 1 = use the first-generation packed kernel for global mode too
+  int tb16 = 1;                 // 0 = one-to-one jobs always take the 32-bit kernel
 };
 
 struct Ctx {
@@ -617,6 +618,111 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
   return ABV_OK;
 }
 
+// ---- tb16 launcher: packed one-to-one kernel with traceback (local, global) ------------------------
+const int TB16_KS[] = {2, 4, 5, 6, 7, 8, 10};
+constexpr int TB16_NK = 7;
+constexpr int TB16_MAX_ALPHA = 7;
+
+template <int MODE, int K>
+int tb16_launch_one(cudaStream_t st, Tb16Params p, size_t dir_bytes_total, size_t tmp_entries_total) {
+  auto kern = tb16_kernel<MODE, K>;
+  const int smem = ((p.a1 * p.a1 * 4 + 15) & ~15) + TB16_WARPS * tb16_smem_per_warp<K>(p.a1, p.rows_cap);
+  if (smem > 200 * 1024) return fail(ABV_ERR_ARGS, "tb16: %d bytes of shared memory", smem);
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB16_WARPS * 32, smem));
+  if (per_sm < 1) return fail(ABV_ERR_CUDA, "tb16 kernel does not fit an SM");
+  p.dir_words_per_warp = (long long)K * TB16_PLANES * tb16_steps16(p.rows_cap) * 32;
+  long long grid = std::min<long long>(((long long)p.n_items + TB16_WARPS - 1) / TB16_WARPS, (long long)g.sms * per_sm);
+  grid = std::min<long long>(grid, (long long)(dir_bytes_total / ((size_t)p.dir_words_per_warp * 4 * TB16_WARPS)));
+  grid = std::min<long long>(grid, (long long)(tmp_entries_total / ((size_t)p.frag_tmp_cap * TB16_WARPS)));
+  if (grid < 1) return fail(ABV_ERR_NOMEM, "tb16 scratch too small");
+  kern<<<(int)grid, TB16_WARPS * 32, smem, st>>>(p);
+  CU(cudaGetLastError());
+  return ABV_OK;
+}
+template <int MODE>
+int tb16_launch_mode(int K, cudaStream_t st, const Tb16Params &p, size_t dir_bytes, size_t tmp_entries) {
+  switch (K) {
+    case 2: return tb16_launch_one<MODE, 2>(st, p, dir_bytes, tmp_entries);
+    case 4: return tb16_launch_one<MODE, 4>(st, p, dir_bytes, tmp_entries);
+    case 5: return tb16_launch_one<MODE, 5>(st, p, dir_bytes, tmp_entries);
+    case 6: return tb16_launch_one<MODE, 6>(st, p, dir_bytes, tmp_entries);
+    case 7: return tb16_launch_one<MODE, 7>(st, p, dir_bytes, tmp_entries);
+    case 8: return tb16_launch_one<MODE, 8>(st, p, dir_bytes, tmp_entries);
+    default: return tb16_launch_one<MODE, 10>(st, p, dir_bytes, tmp_entries);
+  }
+}
+
+// Pairs the packed kernel can take, bucketed by columns per lane and sorted by target length so that the two
+// pairs of a warp have similar shapes.  list = [bucket 0 items: (i0, i1) ...][bucket 1 ...]...[pairs for wf32]
+struct Tb16Plan {
+  std::vector<int> list;
+  struct Bucket { int K, offset, n_items, rows_cap, max_la, max_lb; };
+  std::vector<Bucket> buckets;
+  int rest_offset = 0, n_rest = 0, rest_max_la = 0, rest_max_lb = 0;
+  int pad_score = -1;
+};
+bool tb16_eligible(int mode, const Scoring &sc) {
+  if (!g.opt.tb16 || g.opt.path == ABV_PATH_WF32) return false;
+  if (mode != ABV_LOCAL && mode != ABV_GLOBAL) return false;
+  if (sc.alpha > TB16_MAX_ALPHA) return false;
+  if (mode == ABV_LOCAL && sc.go >= 0) return false;      // the padding argument needs a strictly negative gap_open
+  return true;
+}
+void tb16_plan(Tb16Plan &P, int mode, const long long *a_off, const long long *b_off, int n, const Scoring &sc) {
+  int maxabs = 1;
+  for (int i = 0; i < sc.alpha * sc.alpha; ++i) maxabs = std::max(maxabs, std::abs(sc.matrix[i]));
+  P.pad_score = -(maxabs + 1);
+  const int unit = std::max(std::max(-sc.go, -sc.ge), maxabs + 1);
+  const bool ok = tb16_eligible(mode, sc);
+  // counting sort by (bucket, lb)
+  std::vector<int> key((size_t)n);
+  std::vector<int> hist((size_t)(TB16_NK + 1) * (TB16_MAX_ROWS + 1) + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    const long long la = a_off[i + 1] - a_off[i], lb = b_off[i + 1] - b_off[i];
+    int b = TB16_NK;
+    if (ok && lb <= TB16_MAX_ROWS && la <= 32 * TB16_KS[TB16_NK - 1]) {
+      b = 0;
+      while (32 * TB16_KS[b] < la) ++b;
+      if ((32ll * TB16_KS[b] + lb + 2) * unit - 2ll * sc.go > b16::LIMIT) b = TB16_NK;     // values must stay in the biased range
+    }
+    key[i] = b * (TB16_MAX_ROWS + 1) + (b == TB16_NK ? 0 : (int)lb);
+    ++hist[key[i] + 1];
+  }
+  for (size_t k = 1; k < hist.size(); ++k) hist[k] += hist[k - 1];
+  std::vector<int> sorted((size_t)n);
+  {
+    std::vector<int> pos(hist.begin(), hist.end() - 1);
+    for (int i = 0; i < n; ++i) sorted[pos[key[i]]++] = i;
+  }
+  P.list.clear();
+  P.buckets.clear();
+  for (int b = 0; b < TB16_NK; ++b) {
+    const int lo = hist[(size_t)b * (TB16_MAX_ROWS + 1)], hi = hist[(size_t)(b + 1) * (TB16_MAX_ROWS + 1)];
+    if (hi == lo) continue;
+    Tb16Plan::Bucket B{TB16_KS[b], (int)P.list.size(), (hi - lo + 1) / 2, 0, 0, 0};
+    for (int j = lo; j < hi; j += 2) {
+      P.list.push_back(sorted[j]);
+      P.list.push_back(j + 1 < hi ? sorted[j + 1] : -1);
+    }
+    for (int j = lo; j < hi; ++j) {
+      B.max_la = std::max(B.max_la, (int)(a_off[sorted[j] + 1] - a_off[sorted[j]]));
+      B.max_lb = std::max(B.max_lb, (int)(b_off[sorted[j] + 1] - b_off[sorted[j]]));
+    }
+    B.rows_cap = (B.max_lb + 15) & ~15;
+    P.buckets.push_back(B);
+  }
+  const int lo = hist[(size_t)TB16_NK * (TB16_MAX_ROWS + 1)];
+  P.rest_offset = (int)P.list.size();
+  P.n_rest = n - lo;
+  for (int j = lo; j < n; ++j) {
+    P.list.push_back(sorted[j]);
+    P.rest_max_la = std::max(P.rest_max_la, (int)(a_off[sorted[j] + 1] - a_off[sorted[j]]));
+    P.rest_max_lb = std::max(P.rest_max_lb, (int)(b_off[sorted[j] + 1] - b_off[sorted[j]]));
+  }
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -647,6 +753,7 @@ int abv_set_option(const char *key, int value) {
   if (!strcmp(key, "wf32_blocks_per_sm")) { g.opt.wf32_blocks_per_sm = std::max(1, std::min(value, 8)); return ABV_OK; }
   if (!strcmp(key, "cache_mb")) { g_cache.budget = (size_t)std::max(0, value) << 20; g_cache.trim(g_cache.budget); return ABV_OK; }
   if (!strcmp(key, "split")) { g.opt.split = std::max(0, std::min(value, 64)); return ABV_OK; }
+  if (!strcmp(key, "tb16")) { g.opt.tb16 = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "global_v1")) { g.opt.global_v1 = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "mm16_blocks_per_sm")) { g.opt.mm16_blocks_per_sm = std::max(0, std::min(value, 8)); return ABV_OK; }
   return fail(ABV_ERR_ARGS, "unknown option %s", key);
@@ -760,7 +867,7 @@ int abv_score_matrix(int mode, const char *q, const long long *q_off, int n_q,
 // One-to-one alignments with traceback, results left on the device.
 struct PairsRun {
   DevMem a_codes, a_off, b_codes, b_off, a_raw, b_raw, map, matrix;
-  DevMem dir, tmp, border, scores, start, count, frags, counters;
+  DevMem dir, tmp, border, scores, start, count, frags, counters, lists, matrix_ext;
   long long pool = 0;
   unsigned long long total = 0;
   int max_la = 0, max_lb = 0;
@@ -792,37 +899,82 @@ static int pairs_run(PairsRun &R, int mode, const char *a, const long long *a_of
     R.cells = 0;
     for (int i = 0; i < n; ++i) R.cells += (double)(a_off[i + 1] - a_off[i]) * (double)(b_off[i + 1] - b_off[i]);
   }
-  const long long dwords = dir_words(R.max_la, R.max_lb);
+  // plan: pairs the packed traceback kernel takes (bucketed, partnered) and the rest for the 32-bit kernel
+  Tb16Plan plan;
+  tb16_plan(plan, mode, a_off, b_off, n, sc);
   const int tmp_cap = R.max_la + R.max_lb + 2;
+  const long long dwords = plan.n_rest ? dir_words(plan.rest_max_la, plan.rest_max_lb) : 0;
   const size_t per_warp = (size_t)dwords * 4 + (size_t)tmp_cap * sizeof(FragOut) + (size_t)R.max_lb * 8;
-  const int grid = wf32_grid(n, per_warp);
+  const int grid = plan.n_rest ? wf32_grid(plan.n_rest, per_warp) : 0;
   const long long warps = (long long)grid * WF32_WARPS;
+  size_t dir_bytes = (size_t)dwords * 4 * warps, tmp_entries = (size_t)tmp_cap * warps;
+  for (const auto &B : plan.buckets) {       // scratch for a full persistent grid of the packed kernel (32 warps per SM at most)
+    const long long w = std::min<long long>(((long long)B.n_items + TB16_WARPS - 1) / TB16_WARPS * TB16_WARPS, (long long)g.sms * 32);
+    dir_bytes = std::max(dir_bytes, (size_t)((long long)B.K * TB16_PLANES * tb16_steps16(B.rows_cap) * 32 * 4 * w));
+    tmp_entries = std::max(tmp_entries, (size_t)((long long)tmp_cap * w));
+  }
   R.pool = std::min<long long>(pool_cap, (long long)n * (R.max_la + R.max_lb + 1));
-  CU(R.dir.alloc((size_t)dwords * 4 * warps));
-  CU(R.tmp.alloc((size_t)tmp_cap * sizeof(FragOut) * warps));
-  CU(R.border.alloc((size_t)R.max_lb * 8 * warps));
+  CU(R.dir.alloc(dir_bytes));
+  CU(R.tmp.alloc(tmp_entries * sizeof(FragOut)));
+  CU(R.border.alloc((size_t)R.max_lb * 8 * std::max<long long>(warps, 1)));
   CU(R.scores.alloc(sizeof(int) * (size_t)n));
   CU(R.start.alloc(sizeof(long long) * (size_t)n));
   CU(R.count.alloc(sizeof(int) * (size_t)n));
   CU(R.frags.alloc(sizeof(FragOut) * (size_t)std::max<long long>(R.pool, 1)));
-  CU(R.counters.alloc(16));
-  CU(cudaMemsetAsync(R.counters.p, 0, 16, st));
+  CU(R.counters.alloc(8 * 16));
+  CU(cudaMemsetAsync(R.counters.p, 0, 8 * 16, st));
+  CU(R.lists.alloc(sizeof(int) * std::max<size_t>(plan.list.size(), 1)));
+  CU(cudaMemcpyAsync(R.lists.p, plan.list.data(), sizeof(int) * plan.list.size(), cudaMemcpyHostToDevice, st));
+  if (!plan.buckets.empty()) {
+    const int a1 = sc.alpha + 1;
+    std::vector<int> mext((size_t)a1 * a1, plan.pad_score);
+    for (int i = 0; i < sc.alpha; ++i)
+      for (int j = 0; j < sc.alpha; ++j) mext[(size_t)i * a1 + j] = sc.matrix[i * sc.alpha + j];
+    CU(R.matrix_ext.alloc(sizeof(int) * mext.size()));
+    CU(cudaMemcpyAsync(R.matrix_ext.p, mext.data(), sizeof(int) * mext.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));    // mext is a local
+  }
+  CU(cudaStreamSynchronize(st));      // plan.list is a local
   CU(cudaEventRecord(g.ev[1], st));
 
+  unsigned long long *counters = R.counters.as<unsigned long long>();   // [0] wf32 pairs, [1] fragment total, [2..] tb16 items per bucket
+  int bi = 0;
+  for (const auto &B : plan.buckets) {
+    Tb16Params q{};
+    q.a = R.a_codes.as<uint8_t>(); q.a_off = R.a_off.as<long long>();
+    q.b = R.b_codes.as<uint8_t>(); q.b_off = R.b_off.as<long long>();
+    q.pair_list = R.lists.as<int>() + B.offset; q.n_items = B.n_items;
+    q.matrix_ext = R.matrix_ext.as<int>(); q.a1 = sc.alpha + 1; q.go = sc.go; q.ge = sc.ge;
+    q.rows_cap = B.rows_cap;
+    q.scores = R.scores.as<int>();
+    q.dir = R.dir.as<uint32_t>();
+    q.frag_tmp = R.tmp.as<FragOut>(); q.frag_tmp_cap = tmp_cap;
+    q.frags = R.frags.as<FragOut>(); q.frag_cap = R.pool;
+    q.frag_total = counters + 1;
+    q.frag_start = R.start.as<long long>(); q.frag_count = R.count.as<int>();
+    q.item_counter = counters + 2 + bi;
+    ++bi;
+    rc = mode == ABV_LOCAL ? tb16_launch_mode<LOCAL>(B.K, st, q, dir_bytes, tmp_entries)
+                           : tb16_launch_mode<GLOBAL>(B.K, st, q, dir_bytes, tmp_entries);
+    if (rc) return rc;
+  }
   Wf32Params p{};
-  p.a = R.a_codes.as<uint8_t>(); p.a_off = R.a_off.as<long long>();
-  p.b = R.b_codes.as<uint8_t>(); p.b_off = R.b_off.as<long long>();
-  p.n_pairs = n; p.n_t = 0; p.q_base = 0; p.q_list = nullptr;
-  p.matrix = R.matrix.as<int>(); p.alpha = sc.alpha; p.go = sc.go; p.ge = sc.ge;
-  p.scores = R.scores.as<int>(); p.score_rows_by_query = 0;
-  p.dir = R.dir.as<uint32_t>(); p.dir_words_per_warp = dwords;
-  p.frag_tmp = R.tmp.as<FragOut>(); p.frag_tmp_cap = tmp_cap;
-  p.frags = R.frags.as<FragOut>(); p.frag_cap = R.pool;
-  p.frag_total = R.counters.as<unsigned long long>() + 1;
-  p.frag_start = R.start.as<long long>(); p.frag_count = R.count.as<int>();
-  p.border = R.border.as<int>(); p.border_len = R.max_lb;
-  p.pair_counter = R.counters.as<unsigned long long>();
-  if ((rc = wf32_dispatch<true>(mode, grid, st, p, R.max_lb))) return rc;
+  p.frag_total = counters + 1;
+  if (plan.n_rest) {
+    p.a = R.a_codes.as<uint8_t>(); p.a_off = R.a_off.as<long long>();
+    p.b = R.b_codes.as<uint8_t>(); p.b_off = R.b_off.as<long long>();
+    p.n_pairs = plan.n_rest; p.n_t = 0; p.q_base = 0; p.q_list = nullptr;
+    p.pair_list = R.lists.as<int>() + plan.rest_offset;
+    p.matrix = R.matrix.as<int>(); p.alpha = sc.alpha; p.go = sc.go; p.ge = sc.ge;
+    p.scores = R.scores.as<int>(); p.score_rows_by_query = 0;
+    p.dir = R.dir.as<uint32_t>(); p.dir_words_per_warp = dwords;
+    p.frag_tmp = R.tmp.as<FragOut>(); p.frag_tmp_cap = tmp_cap;
+    p.frags = R.frags.as<FragOut>(); p.frag_cap = R.pool;
+    p.frag_start = R.start.as<long long>(); p.frag_count = R.count.as<int>();
+    p.border = R.border.as<int>(); p.border_len = R.max_lb;
+    p.pair_counter = counters;
+    if ((rc = wf32_dispatch<true>(mode, grid, st, p, plan.rest_max_lb))) return rc;
+  }
   CU(cudaEventRecord(g.ev[2], st));
   CU(cudaMemcpyAsync(&R.total, p.frag_total, sizeof R.total, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));

@@ -369,6 +369,111 @@ ABV_HD void mm16d_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (
 }
 
 // ---------------------------------------------------------------------------------------------
+// tb16: one-to-one alignments WITH traceback, two pairs per warp in the 16-bit halves (local and global;
+// the merge stage and the final alignment, ambivert.py:301-331, :543-574).  Same strip geometry as the packed
+// scorer (lane t owns columns [tK, (t+1)K), rows skewed by lane) and the same biased operands (namespace
+// b16: every half holds true + 16384, so bit 15 of a half is always 0).  The decisions of a cell
+// (global_align.c:180-209, local_align.c:150-207) are taken for both halves at once WITHOUT predicates:
+//     ge(a, b) = a + 0x80008000 - b        bit 15 / bit 31 = (a >= b) in the low / high half
+// (one 3-input add; no borrow crosses the halves because a + 0x8000 >= b), and combined with 3-input logic ops:
+//   pa = ge(diag, F) (diag wins ties), pb = ge(max(diag,F), E) (both win ties over E), pc = ge(value, 0) (local: else stop),
+//   fo = ge(h + go, F + ge), eo = ge(h + go, E + ge) (opening wins ties)
+//   direction = SRC_* of wf32: bit0 = (!pa & pb) | !pc, bit1 = !pb | !pc; plus the two "gap re-opened" bits
+// Each of the four direction bits goes to its own bit PLANE: one word per column and 16 steps, bit j (low half) and
+// 16 + j (high half) = step 16*w + j.
+namespace p16 {
+#if defined(__CUDA_ARCH__)
+ABV_HD uint32_t bmax(uint32_t a, uint32_t b, bool &p_hi, bool &p_lo) { return __vibmax_s16x2(a, b, &p_hi, &p_lo); }
+#else
+ABV_HD uint32_t bmax(uint32_t a, uint32_t b, bool &p_hi, bool &p_lo) {
+  p_lo = lo(a) >= lo(b); p_hi = hi(a) >= hi(b);
+  return pack(p_lo ? lo(a) : lo(b), p_hi ? hi(a) : hi(b));
+}
+#endif
+}  // namespace p16
+
+template <int K>
+struct Tb16Cfg {
+  static constexpr int V = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1);   // words per shared-memory load of the profile
+  static constexpr int P = 32 * K;                                     // profile row length in words
+  static constexpr int MAX_LA = 32 * K;
+};
+constexpr int TB16_MAX_ROWS = 1024;
+constexpr int TB16_PLANES = 4;                    // bit0, bit1 of the source, F re-opened, E re-opened
+constexpr uint32_t TB16_H = 0x80008000u;
+ABV_HD int tb16_steps16(int rows_cap) { return (rows_cap + 31 + 15) >> 4; }
+// word of the profile row that holds column k of lane t: the lanes of one shared-memory phase read 32 distinct banks
+ABV_HD int tb16_slot(int t, int k, int V) { return ((k / V) * 32 + t) * V + k % V; }
+ABV_HD uint32_t tb16_ge(uint32_t a, uint32_t b) { return a + TB16_H - b; }
+
+// One row of one lane.  All score-like values are b16-biased.
+//   hleft : H[c0-1][r-1]        e : in E[r] entering the strip, out E[r] leaving it
+//   Hp,F  : H[.][r-1] -> H[.][r]; column gap states
+//   Slo,Shi : addend-packed substitution scores of the two pairs' columns for this row's symbols
+//   gow,gew : b16::addend(go,go), b16::addend(ge,ge);  zerob = b16::biased(0,0)
+//   j     : step % 16, the bit position in the plane words acc[k][plane] (a constant once the step loop is unrolled)
+//   LOCAL : cand[k] = running best value of column c0+k (both halves), crow[k] = its row (lo | hi << 16);
+//           rr = r | r << 16.  '>=' so that the last row wins ties within a column (local_align.c:156-160)
+template <int MODE, int K>
+ABV_HD void tb16_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], const uint32_t *Slo, const uint32_t *Shi,
+                     uint32_t gow, uint32_t gew, uint32_t zerob, int j, uint32_t (&acc)[K][TB16_PLANES],
+                     uint32_t (&cand)[K], uint32_t (&crow)[K], uint32_t rr) {
+  const int sh = 15 - j;
+  const uint32_t MJ = TB16_H >> sh;                     // where this step's bits sit in a plane word
+  uint32_t d = hleft;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const uint32_t s0 = d + Slo[k] + Shi[k];
+    d = Hp[k];
+    const uint32_t t = p16::max2(s0, F[k]);
+    const uint32_t pa = tb16_ge(s0, F[k]);
+    const uint32_t hr = p16::max2(t, e);
+    const uint32_t pb = tb16_ge(t, e);
+    uint32_t h = hr, b0, b1;
+    if (MODE == LOCAL) {
+      h = p16::max2(hr, zerob);
+      const uint32_t pc = tb16_ge(hr, zerob);
+      b0 = (~pa & pb) | ~pc;
+      b1 = ~(pb & pc);
+      bool pn_h, pn_l;
+      cand[k] = p16::bmax(hr, cand[k], pn_h, pn_l);       // a stop cell (hr < 0) never beats a candidate (>= -1)
+      if (pn_l) crow[k] = (crow[k] & 0xffff0000u) | (rr & 0x0000ffffu);
+      if (pn_h) crow[k] = (crow[k] & 0x0000ffffu) | (rr & 0xffff0000u);
+    } else {
+      b0 = ~pa & pb;
+      b1 = ~pb;
+    }
+    const uint32_t hg = h + gow, fe = F[k] + gew, ee = e + gew;
+    F[k] = p16::max2(hg, fe);
+    const uint32_t fo = tb16_ge(hg, fe);
+    e = p16::max2(hg, ee);
+    const uint32_t eo = tb16_ge(hg, ee);
+    Hp[k] = h;
+    acc[k][0] |= (b0 >> sh) & MJ;
+    acc[k][1] |= (b1 >> sh) & MJ;
+    acc[k][2] |= (fo >> sh) & MJ;
+    acc[k][3] |= (eo >> sh) & MJ;
+  }
+}
+
+// direction planes of one warp's two pairs: word(k, plane, s, t) = ((k*4 + plane)*steps16 + s/16)*32 + t,
+// bit s%16 + 16*half, where column c = t*K + k and s = row + t is the step at which lane t worked on that row
+template <int K>
+struct Tb16Reader {
+  const uint32_t *w;
+  int steps16, half;
+  ABV_HD unsigned plane_bit(int plane, int col, int row) const {
+    const int t = col / K, k = col - t * K, s = row + t;
+    const uint32_t v = w[((long long)(k * TB16_PLANES + plane) * steps16 + (s >> 4)) * 32 + t];
+    return (v >> ((s & 15) + 16 * half)) & 1u;
+  }
+  ABV_HD unsigned src(int col, int row) const { return plane_bit(0, col, row) | (plane_bit(1, col, row) << 1); }
+  ABV_HD unsigned get(int col, int row) const {       // the nibble of wf32 (for the generic walk)
+    return src(col, row) | (plane_bit(2, col, row) ? BIT_FOPEN : 0u) | (plane_bit(3, col, row) ? BIT_EOPEN : 0u);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
 // Variant scan of one aligned (sample row, reference row) pair: the step after the aligner
 // (ambivert/call_variants.py:32-128, caller()).  The reference walks the
 // two gapped rows site by site with three accumulating strings (mismatch, deletion, insertion) and

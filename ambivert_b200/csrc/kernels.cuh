@@ -64,6 +64,7 @@ struct Wf32Params {
   int *border; int border_len;
   int stage_len;                                 // STAGED kernels: per-warp shared-memory rows of this many entries (multiple of 16)
   unsigned long long *pair_counter;
+  const int *pair_list;                          // one-to-one jobs: work item i is pair pair_list[i] (NULL: pair i)
 };
 
 constexpr int WF32_WARPS = 8;
@@ -176,7 +177,10 @@ __global__ void __launch_bounds__(WF32_WARPS * 32) wf32_kernel(Wf32Params p) {
       ia = p.q_list ? (long long)p.q_list[row] : row;
       ib = (long long)(pidx % (unsigned)p.n_t);
       if (p.score_rows_by_query) out_idx = ia * p.n_t + ib;
-    } else { ia = (long long)pidx; ib = (long long)pidx; }
+    } else {
+      if (p.pair_list) pidx = (unsigned long long)p.pair_list[pidx];
+      ia = (long long)pidx; ib = (long long)pidx; out_idx = (long long)pidx;
+    }
     const uint8_t *sa = p.a + p.a_off[ia];
     const uint8_t *sb = p.b + p.b_off[ib];
     const int la = (int)(p.a_off[ia + 1] - p.a_off[ia]);
@@ -199,6 +203,279 @@ __global__ void __launch_bounds__(WF32_WARPS * 32) wf32_kernel(Wf32Params p) {
         p.frag_count[pidx] = n;
       }
       n = __shfl_sync(ABV_FULL, n, 0);
+      base = __shfl_sync(ABV_FULL, base, 0);
+      __syncwarp();
+      for (int i = lane; i < n; i += 32)
+        if ((long long)(base + i) < p.frag_cap) p.frags[base + i] = tmp[n - 1 - i];
+      __syncwarp();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tb16_kernel<MODE,K>: one-to-one alignments with traceback, TWO pairs per warp (16-bit halves), local and
+// global.  Lane t owns query columns [tK, (t+1)K) of both pairs and sweeps the target rows one row behind its
+// left neighbour; strip borders (H, E) move with two shuffles per step.  Per warp in shared memory: the two
+// pairs' substitution profiles (prof[half][symbol][column], addend-packed so that hdiag + lo + hi is two plain
+// adds), and the two targets interleaved as one 16-bit code per row.  Sequences shorter than their partner's
+// are padded with an extra symbol whose score is negative against everything: with gap_open < 0 a padded cell
+// is always strictly below the best real cell it derives from, so it never becomes the local end cell, and
+// real cells never depend on padded ones.  Directions: four bit planes per column (dp_core.cuh::Tb16Reader),
+// written as whole 128-byte lines every 16 steps.  The walk back is done by the whole warp, one pair after
+// the other: the lanes probe 32 cells of the current diagonal (or 32 cells up / left for a gap) at once and a
+// ballot finds where the run ends, so a fragment costs one or two memory round trips instead of one per cell.
+struct Tb16Params {
+  const uint8_t *a; const long long *a_off;      // encoded sequences (sa = query side, columns)
+  const uint8_t *b; const long long *b_off;      // (sb = target side, rows)
+  const int *pair_list;                          // item i = pairs pair_list[2i], pair_list[2i+1] (-1: none)
+  int n_items;
+  const int *matrix_ext;                         // (alpha+1)^2, last row/column = the padding symbol
+  int a1, go, ge;
+  int rows_cap;                                  // staged target rows per warp (multiple of 16, <= TB16_MAX_ROWS)
+  int *scores;
+  uint32_t *dir; long long dir_words_per_warp;   // K * 4 planes * steps16 * 32 words
+  FragOut *frag_tmp; int frag_tmp_cap;           // frag_tmp_cap entries per warp
+  FragOut *frags; long long frag_cap;
+  unsigned long long *frag_total;
+  long long *frag_start; int *frag_count;
+  unsigned long long *item_counter;
+};
+constexpr int TB16_WARPS = 4;
+template <int K>
+__host__ __device__ inline int tb16_smem_per_warp(int a1, int rows_cap) {
+  return (2 * a1 * Tb16Cfg<K>::P * 4 + rows_cap * 2 + 2 * Tb16Cfg<K>::P + 15) & ~15;
+}
+
+template <int K>
+__device__ __forceinline__ uint32_t tb16_pick(const uint32_t (&Hp)[K], int kstar) {
+  uint32_t v = Hp[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) v = (k == kstar) ? Hp[k] : v;
+  return v;
+}
+
+// Traceback of one half by the whole warp; same fragments, same order as dp_core.cuh::walk_back_emit
+// (global_align.c:25-92, local_align.c:23-72).  tmp receives them in REVERSE sequence order; returns the count.
+template <int MODE, int K>
+__device__ __forceinline__ int tb16_walk(const Tb16Reader<K> &rd, int col, int row, FragOut *tmp, int cap, int lane) {
+  int n = 0;
+  while (col >= 0 && row >= 0) {
+    const unsigned src0 = rd.src(col, row);                     // warp-uniform address: one broadcast load per plane
+    if (MODE == LOCAL && src0 == SRC_STOP) break;
+    FragOut f;
+    if (src0 == SRC_F) {              // back to the nearest row above where the column gap was (re)opened
+      int p = row - 1;
+      for (;;) {
+        const int pi = p - lane;
+        const unsigned hit = __ballot_sync(ABV_FULL, pi >= 0 && rd.plane_bit(2, col, pi));
+        if (hit) { p -= __ffs(hit) - 1; break; }
+        p -= 32;
+        if (p < 0) { p = -1; break; }
+      }
+      f.type = FRAG_A_GAP; f.hsp_len = row - p;
+      row = p;
+    } else if (src0 == SRC_E) {       // back to the nearest column to the left where the row gap was (re)opened
+      int p = col - 1;
+      for (;;) {
+        const int pi = p - lane;
+        const unsigned hit = __ballot_sync(ABV_FULL, pi >= 0 && rd.plane_bit(3, pi, row));
+        if (hit) { p -= __ffs(hit) - 1; break; }
+        p -= 32;
+        if (p < 0) { p = -1; break; }
+      }
+      f.type = FRAG_B_GAP; f.hsp_len = col - p;
+      col = p;
+    } else {                          // diagonal run: the start cell, then every following cell whose source is the diagonal
+      int run = 1;
+      --col; --row;
+      for (;;) {
+        const int ci = col - lane, ri = row - lane;
+        const unsigned diag = __ballot_sync(ABV_FULL, ci >= 0 && ri >= 0 && rd.src(ci, ri) == SRC_DIAG);
+        const int cnt = diag == ABV_FULL ? 32 : __ffs(~diag) - 1;
+        run += cnt; col -= cnt; row -= cnt;
+        if (cnt < 32) break;
+      }
+      f.type = FRAG_MATCH; f.hsp_len = run;
+    }
+    f.sa_start = col + 1; f.sb_start = row + 1;
+    if (lane == 0 && n < cap) tmp[n] = f;
+    ++n;
+  }
+  if (MODE == GLOBAL && (col >= 0 || row >= 0)) {   // leading end gap (global_align.c:69-86)
+    FragOut f; f.sa_start = 0; f.sb_start = 0;
+    if (col >= 0) { f.type = FRAG_B_GAP; f.hsp_len = col + 1; }
+    else          { f.type = FRAG_A_GAP; f.hsp_len = row + 1; }
+    if (lane == 0 && n < cap) tmp[n] = f;
+    ++n;
+  }
+  return n;
+}
+
+template <int MODE, int K>
+__global__ void __launch_bounds__(TB16_WARPS * 32) tb16_kernel(Tb16Params p) {
+  static_assert(MODE == LOCAL || MODE == GLOBAL, "tb16 implements local and global");
+  constexpr int V = Tb16Cfg<K>::V, P = Tb16Cfg<K>::P;
+  extern __shared__ __align__(16) unsigned char tb_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gwarp = (long long)blockIdx.x * TB16_WARPS + warp;
+  const int a1 = p.a1, go = p.go, ge = p.ge, pad = a1 - 1;
+  int *mext = reinterpret_cast<int *>(tb_smem);
+  unsigned char *mine = tb_smem + ((a1 * a1 * 4 + 15) & ~15) + (size_t)warp * tb16_smem_per_warp<K>(a1, p.rows_cap);
+  uint32_t *prof = reinterpret_cast<uint32_t *>(mine);                  // [half][symbol][P]
+  uint16_t *tb = reinterpret_cast<uint16_t *>(mine + 2 * a1 * P * 4);   // [rows_cap] lo | hi << 8
+  uint8_t *qc = mine + 2 * a1 * P * 4 + p.rows_cap * 2;                 // [half][P] query codes by column
+  for (int i = threadIdx.x; i < a1 * a1; i += blockDim.x) mext[i] = p.matrix_ext[i];
+  __syncthreads();
+
+  const uint32_t gow = b16::addend(go, go), gew = b16::addend(ge, ge), zerob = b16::biased(0, 0);
+  const int steps16 = tb16_steps16(p.rows_cap);
+  uint32_t *dir = p.dir + gwarp * p.dir_words_per_warp;
+  FragOut *tmp = p.frag_tmp + gwarp * (long long)p.frag_tmp_cap;
+  const int c0 = lane * K;
+
+  for (;;) {
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd(p.item_counter, 1ull);
+    item = __shfl_sync(ABV_FULL, item, 0);
+    if ((long long)item >= p.n_items) break;
+    const int i0 = p.pair_list[2 * item], i1 = p.pair_list[2 * item + 1];
+    const int j1 = i1 >= 0 ? i1 : i0;                           // no partner: the pair rides in both halves
+    const uint8_t *qa0 = p.a + p.a_off[i0], *qa1 = p.a + p.a_off[j1];
+    const uint8_t *tb0 = p.b + p.b_off[i0], *tb1 = p.b + p.b_off[j1];
+    const int la0 = (int)(p.a_off[i0 + 1] - p.a_off[i0]), la1 = (int)(p.a_off[j1 + 1] - p.a_off[j1]);
+    const int lb0 = (int)(p.b_off[i0 + 1] - p.b_off[i0]), lb1 = (int)(p.b_off[j1 + 1] - p.b_off[j1]);
+    const int rows = max(lb0, lb1);
+    const int tl = (max(la0, la1) - 1) / K;                     // last lane that owns a real column
+    const int nsteps = rows + tl;
+
+    __syncwarp();
+    for (int r = lane; r < rows; r += 32)
+      tb[r] = (uint16_t)((r < lb0 ? tb0[r] : pad) | ((r < lb1 ? tb1[r] : pad) << 8));
+    for (int c = lane; c < 32 * K; c += 32) {
+      qc[c] = c < la0 ? qa0[c] : (uint8_t)pad;
+      qc[P + c] = c < la1 ? qa1[c] : (uint8_t)pad;
+    }
+    __syncwarp();
+    for (int idx = lane; idx < a1 * P; idx += 32) {
+      const int sym = idx / P, pos = idx - sym * P;
+      const int j = pos % V, it = pos / V, t = it & 31, i = it >> 5;
+      const int k = i * V + j;
+      prof[idx] = b16::addend(mext[qc[t * K + k] * a1 + sym], 0);
+      prof[a1 * P + idx] = b16::addend(0, mext[qc[P + t * K + k] * a1 + sym]);
+    }
+    __syncwarp();
+
+    uint32_t Hp[K], F[K], acc[K][TB16_PLANES], cand[K], crow[K];
+    uint32_t hleft, h_out, e_out;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int c = c0 + k;
+      if (MODE == GLOBAL) { Hp[k] = b16::biased(go + ge * c, go + ge * c); F[k] = b16::biased(2 * go + ge * c, 2 * go + ge * c); }
+      else { Hp[k] = zerob; F[k] = b16::biased(go, go); }
+#pragma unroll
+      for (int q = 0; q < TB16_PLANES; ++q) acc[k][q] = 0;
+      cand[k] = b16::biased(-1, -1); crow[k] = 0;
+    }
+    if (MODE == GLOBAL) hleft = c0 ? b16::biased(go + ge * (c0 - 1), go + ge * (c0 - 1)) : zerob;
+    else hleft = zerob;
+    h_out = zerob; e_out = zerob;
+    // column -1 as seen by lane 0 at row r: H = go + ge*r, E = 2go + ge*r (global_align.c:136-140); 0, go (local_align.c:123-128)
+    const uint32_t Hv0 = MODE == GLOBAL ? b16::biased(go, go) : zerob;
+    const uint32_t Ev0 = MODE == GLOBAL ? b16::biased(2 * go, 2 * go) : b16::biased(go, go);
+    const int t0 = (la0 - 1) / K, k0 = (la0 - 1) - t0 * K, t1 = (la1 - 1) / K, k1 = (la1 - 1) - t1 * K;
+    int corner0 = 0, corner1 = 0;
+
+    for (int s16 = 0; s16 < nsteps; s16 += 16) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int s = s16 + j;
+        uint32_t h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
+        uint32_t e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+        const int r = s - lane;
+        if (lane == 0) {
+          h_sh = MODE == GLOBAL ? Hv0 + (uint32_t)r * gew : Hv0;
+          e_sh = MODE == GLOBAL ? Ev0 + (uint32_t)r * gew : Ev0;
+        }
+        if (r >= 0 && r < rows && lane <= tl) {
+          const unsigned code = tb[r];
+          uint32_t Slo[K], Shi[K];
+          const uint32_t *rlo = prof + (code & 255u) * P, *rhi = prof + (a1 + (code >> 8)) * P;
+          if (V == 4) {
+#pragma unroll
+            for (int i = 0; i < K / 4; ++i) {
+              const uint4 u = reinterpret_cast<const uint4 *>(rlo)[i * 32 + lane], w = reinterpret_cast<const uint4 *>(rhi)[i * 32 + lane];
+              Slo[4 * i] = u.x; Slo[4 * i + 1] = u.y; Slo[4 * i + 2] = u.z; Slo[4 * i + 3] = u.w;
+              Shi[4 * i] = w.x; Shi[4 * i + 1] = w.y; Shi[4 * i + 2] = w.z; Shi[4 * i + 3] = w.w;
+            }
+          } else if (V == 2) {
+#pragma unroll
+            for (int i = 0; i < K / 2; ++i) {
+              const uint2 u = reinterpret_cast<const uint2 *>(rlo)[i * 32 + lane], w = reinterpret_cast<const uint2 *>(rhi)[i * 32 + lane];
+              Slo[2 * i] = u.x; Slo[2 * i + 1] = u.y; Shi[2 * i] = w.x; Shi[2 * i + 1] = w.y;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < K; ++i) { Slo[i] = rlo[i * 32 + lane]; Shi[i] = rhi[i * 32 + lane]; }
+          }
+          uint32_t e = e_sh;
+          tb16_row<MODE, K>(hleft, e, Hp, F, Slo, Shi, gow, gew, zerob, j, acc, cand, crow, (uint32_t)r * 0x10001u);
+          hleft = h_sh; e_out = e; h_out = Hp[K - 1];
+          if (MODE == GLOBAL) {                                   // the corner cell is the score (global_align.c:217)
+            if (r == lb0 - 1 && lane == t0) corner0 = b16::lo(tb16_pick<K>(Hp, k0));
+            if (r == lb1 - 1 && lane == t1) corner1 = b16::hi(tb16_pick<K>(Hp, k1));
+          }
+        }
+      }
+      const long long wbase = (long long)(s16 >> 4) * 32 + lane;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int q = 0; q < TB16_PLANES; ++q) {
+          dir[(long long)(k * TB16_PLANES + q) * steps16 * 32 + wbase] = acc[k][q];
+          acc[k][q] = 0;
+        }
+    }
+
+    // end cell and score of each half
+    int score0, ec0, er0, score1, ec1, er1;
+    if (MODE == GLOBAL) {
+      score0 = __shfl_sync(ABV_FULL, corner0, t0); score1 = __shfl_sync(ABV_FULL, corner1, t1);
+      ec0 = la0 - 1; er0 = lb0 - 1; ec1 = la1 - 1; er1 = lb1 - 1;
+    } else {
+      // per lane: best over its columns, later columns win ties; then over lanes by (score, column)
+      int b0 = -1, bc0 = 0, br0 = 0, b1 = -1, bc1 = 0, br1 = 0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int v0 = b16::lo(cand[k]), v1 = b16::hi(cand[k]);
+        if (v0 >= 0 && v0 >= b0) { b0 = v0; bc0 = c0 + k; br0 = (int)(crow[k] & 0xffffu); }
+        if (v1 >= 0 && v1 >= b1) { b1 = v1; bc1 = c0 + k; br1 = (int)(crow[k] >> 16); }
+      }
+      long long key0 = b0 < 0 ? -1 : (((long long)b0 << 40) | ((long long)bc0 << 20) | br0);
+      long long key1 = b1 < 0 ? -1 : (((long long)b1 << 40) | ((long long)bc1 << 20) | br1);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        key0 = max(key0, __shfl_xor_sync(ABV_FULL, key0, off));
+        key1 = max(key1, __shfl_xor_sync(ABV_FULL, key1, off));
+      }
+      // max_score starts at 0 with end cell (0,0) (local_align.c:119-121)
+      if (key0 < 0) { score0 = 0; ec0 = 0; er0 = 0; } else { score0 = (int)(key0 >> 40); ec0 = (int)((key0 >> 20) & 0xfffff); er0 = (int)(key0 & 0xfffff); }
+      if (key1 < 0) { score1 = 0; ec1 = 0; er1 = 0; } else { score1 = (int)(key1 >> 40); ec1 = (int)((key1 >> 20) & 0xfffff); er1 = (int)(key1 & 0xfffff); }
+    }
+    if (lane == 0) { p.scores[i0] = score0; if (i1 >= 0) p.scores[i1] = score1; }
+    __syncwarp();      // the direction words of all lanes are visible to the whole warp
+
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && i1 < 0) break;
+      Tb16Reader<K> rd; rd.w = dir; rd.steps16 = steps16; rd.half = h;
+      const int n = tb16_walk<MODE, K>(rd, h ? ec1 : ec0, h ? er1 : er0, tmp, p.frag_tmp_cap, lane);
+      unsigned long long base = 0;
+      if (lane == 0) {
+        base = atomicAdd(p.frag_total, (unsigned long long)n);
+        const int pi = h ? i1 : i0;
+        p.frag_start[pi] = (long long)base;
+        p.frag_count[pi] = n;
+      }
       base = __shfl_sync(ABV_FULL, base, 0);
       __syncwarp();
       for (int i = lane; i < n; i += 32)

@@ -458,3 +458,38 @@ def test_legacy_single_calls_fuzz(A, oracle_port, mode):
         go, ge = rng.choice([(-7, -1), (-7, -1), (0, -2), (-3, 0)])
         want = oracle_port.align(mode, a.encode(), b.encode(), go=go, ge=ge)
         assert legacy(A, mode, a.encode(), b.encode(), go=go, ge=ge) == want, (it, la, len(b), go, ge)
+
+
+@pytest.mark.parametrize("mode", [O.LOCAL, O.GLOBAL])
+def test_packed_traceback_kernel_vs_32bit_kernel_sweep(B, oracle_port, mode):
+    """tb16 (two pairs per warp in 16-bit halves, DPX max with predicates) against the 32-bit wavefront kernel on
+    6000 ragged pairs: identical scores and fragment lists; a sample also against the oracle.  Lengths cross every
+    strip bucket (K = 2..10), the partner of a pair has a different shape, odd counts leave a pair without partner."""
+    rng = random.Random(77 + mode)
+    a_list, b_list = [], []
+    for i in range(6001):
+        la = rng.choice([1, 2, 31, 33, 64, 65, 128, 129, 150, 160, 161, 192, 224, 225, 256, 257, 320, rng.randint(1, 330)])
+        a = rand_dna(rng, la, "ACGTN" if rng.random() < 0.1 else "ACGT")
+        x = rng.random()
+        if x < 0.5:
+            b = mutate(rng, a, rng.randint(0, 10))
+        elif x < 0.7:                         # overlap-merge shape: suffix of a + new sequence
+            cut = rng.randrange(len(a))
+            b = a[cut:] + rand_dna(rng, rng.randint(1, 100))
+        elif x < 0.8:
+            b = rand_dna(rng, rng.randint(1, 6), "AC") * rng.randint(1, 40)      # repeats: ties everywhere
+            a = rand_dna(rng, rng.randint(1, 6), "AC") * rng.randint(1, 40)
+        else:
+            b = rand_dna(rng, rng.choice([1, 2, 3, rng.randint(4, 400), 1024, 1030]) if rng.random() < 0.9 else 1)
+        a_list.append(a.encode()); b_list.append(b.encode())
+    got = B.align_pairs(a_list, b_list, mode)
+    B.set_option("tb16", 0)
+    try:
+        want = B.align_pairs(a_list, b_list, mode)
+    finally:
+        B.set_option("tb16", 1)
+    assert (got[0] == want[0]).all() and (got[2] == want[2]).all()
+    for k in range(len(a_list)):
+        assert B.fragments(k, got[1], got[2], got[3]) == B.fragments(k, want[1], want[2], want[3]), (k, a_list[k], b_list[k])
+    for k in range(0, len(a_list), 23):
+        assert (int(got[0][k]), B.fragments(k, got[1], got[2], got[3])) == oracle_port.align(mode, a_list[k], b_list[k]), k
