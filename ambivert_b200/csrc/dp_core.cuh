@@ -411,15 +411,13 @@ ABV_HD uint32_t tb16_ge(uint32_t a, uint32_t b) { return a + TB16_H - b; }
 //   Hp,F  : H[.][r-1] -> H[.][r]; column gap states
 //   Slo,Shi : addend-packed substitution scores of the two pairs' columns for this row's symbols
 //   gow,gew : b16::addend(go,go), b16::addend(ge,ge);  zerob = b16::biased(0,0)
-//   j     : step % 16, the bit position in the plane words acc[k][plane] (a constant once the step loop is unrolled)
+//   sh,MJ : 15 - step % 16 and 0x80008000 >> sh: where this step's bits go in the plane words acc[k][plane]
 //   LOCAL : cand[k] = running best value of column c0+k (both halves), crow[k] = its row (lo | hi << 16);
 //           rr = r | r << 16.  '>=' so that the last row wins ties within a column (local_align.c:156-160)
 template <int MODE, int K>
 ABV_HD void tb16_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], const uint32_t *Slo, const uint32_t *Shi,
-                     uint32_t gow, uint32_t gew, uint32_t zerob, int j, uint32_t (&acc)[K][TB16_PLANES],
+                     uint32_t gow, uint32_t gew, uint32_t zerob, int sh, uint32_t MJ, uint32_t (&acc)[K][TB16_PLANES],
                      uint32_t (&cand)[K], uint32_t (&crow)[K], uint32_t rr) {
-  const int sh = 15 - j;
-  const uint32_t MJ = TB16_H >> sh;                     // where this step's bits sit in a plane word
   uint32_t d = hleft;
 #pragma unroll
   for (int k = 0; k < K; ++k) {

@@ -4,6 +4,10 @@
 //   wf32_kernel          general kernel: one warp per (sa, sb) pair, 32-bit, anti-diagonal wavefront
 //                        over 32-column blocks with shuffle exchange; all four modes with the reference's
 //                        tie rules; optional 4-bit direction matrix + traceback (bit-exact fragment lists)
+//   tb16_kernel          one-to-one alignments WITH traceback, two pairs per warp in 16x2 DPX words (local, global):
+//                        predicate-free tie decisions, bit-plane direction matrices, warp-parallel walk back
+//   variants_kernel      variant scan of aligned row pairs (call_variants.py caller()), one thread per pair
+//   md5_pairs_kernel     MD5 keys of read pairs (the clustering front end), grouped by radix sort
 //   assemble_*_kernel    gapped rows / merged reads built from the fragment pool (the string work that
 //                        follows the aligner in merge_overlaps and align_to_reference)
 //   mm16g_kernel         THE BULK KERNEL: many-to-many score-only, global and glocal.  One warp per
@@ -241,6 +245,10 @@ struct Tb16Params {
   unsigned long long *item_counter;
 };
 constexpr int TB16_WARPS = 4;
+#ifndef TB16_UNROLL
+#define TB16_UNROLL 2
+#endif
+constexpr int kTb16Unroll = TB16_UNROLL;   // steps of the fill loop unrolled together (the whole 16 thrash the instruction cache)
 template <int K>
 __host__ __device__ inline int tb16_smem_per_warp(int a1, int rows_cap) {
   return (2 * a1 * Tb16Cfg<K>::P * 4 + rows_cap * 2 + 2 * Tb16Cfg<K>::P + 15) & ~15;
@@ -386,7 +394,7 @@ __global__ void __launch_bounds__(TB16_WARPS * 32) tb16_kernel(Tb16Params p) {
     int corner0 = 0, corner1 = 0;
 
     for (int s16 = 0; s16 < nsteps; s16 += 16) {
-#pragma unroll
+#pragma unroll kTb16Unroll
       for (int j = 0; j < 16; ++j) {
         const int s = s16 + j;
         uint32_t h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
@@ -418,7 +426,7 @@ __global__ void __launch_bounds__(TB16_WARPS * 32) tb16_kernel(Tb16Params p) {
             for (int i = 0; i < K; ++i) { Slo[i] = rlo[i * 32 + lane]; Shi[i] = rhi[i * 32 + lane]; }
           }
           uint32_t e = e_sh;
-          tb16_row<MODE, K>(hleft, e, Hp, F, Slo, Shi, gow, gew, zerob, j, acc, cand, crow, (uint32_t)r * 0x10001u);
+          tb16_row<MODE, K>(hleft, e, Hp, F, Slo, Shi, gow, gew, zerob, 15 - j, TB16_H >> (15 - j), acc, cand, crow, (uint32_t)r * 0x10001u);
           hleft = h_sh; e_out = e; h_out = Hp[K - 1];
           if (MODE == GLOBAL) {                                   // the corner cell is the score (global_align.c:217)
             if (r == lb0 - 1 && lane == t0) corner0 = b16::lo(tb16_pick<K>(Hp, k0));

@@ -1,5 +1,7 @@
 """Synthetic amplicon data of the shapes BASELINE.json names.  Seeded and
 deterministic, so every rank of a multi-GPU run builds the same set and takes its own shard."""
+import random
+
 import numpy as np
 
 _ACGT = np.frombuffer(b"ACGT", np.uint8)
@@ -138,3 +140,25 @@ def panel_pipeline_inputs(n_targets=300, n_unique=20000, read_len=150, seed=0xB2
             continue
         pairs.append((q[:read_len].decode(), reverse_complement(q[-read_len:]).decode(), int(rng.integers(1, 4))))
     return refs, pairs
+
+
+def aligned_rows(n, seed=0xF4):
+    """aligned rows of config-4-like amplicons: 27 bp lower-case primer flanks, ~200 bp core, a few events each"""
+    rng = random.Random(seed)
+    rows = []
+    for _ in range(n):
+        core = rng.randint(150, 210)
+        ref = [rng.choice("acgt") for _ in range(27)] + [rng.choice("ACGT") for _ in range(core)] + [rng.choice("acgt") for _ in range(27)]
+        s, r = [], []
+        for b in ref:
+            x = rng.random()
+            if x < 0.004:
+                s.append("-"); r.append(b)
+            elif x < 0.008:
+                s.append(rng.choice("ACGT")); r.append("-"); s.append(b.upper()); r.append(b)
+            elif x < 0.02:
+                s.append(rng.choice("ACGTN")); r.append(b)
+            else:
+                s.append(b.upper()); r.append(b)
+        rows.append(("".join(s), "".join(r)))
+    return rows

@@ -198,7 +198,10 @@ def merge_measurement(n_pairs):
     """secondary: BASELINE.json configs[1], the overlap merge of unique F/R read pairs -- one batched local
     alignment WITH traceback per pair (ambivert.py:320-328), host buffers in, scores + fragment lists out"""
     from ambivert_b200 import batch as B, synth
+    import torch
     a, b = synth.read_pairs_packed(n_pairs)
+    pin = lambda x: torch.from_numpy(x).pin_memory().numpy()            # host buffers are pinned, as for the headline e2e
+    a, b = (pin(a[0]), a[1]), (pin(b[0]), b[1])
     B.align_pairs((a[0][:150 * 1000], a[1][:1001]), (b[0][:150 * 1000], b[1][:1001]), B.LOCAL)      # warm-up
     best = None
     for _ in range(3):
@@ -223,7 +226,7 @@ def merge_measurement(n_pairs):
             "h2d_bytes": tm["h2d_bytes"], "d2h_bytes": tm["d2h_bytes"], "fragments": nfr, "pairs_with_alignment": naligned,
             "stage_with_merged_reads": {"e2e_s": stage[0], "pairs_per_s_e2e": n_pairs / stage[0], "merged": stage[1], "merged_bytes": stage[2],
                                         "api": "abv_merge_pairs: alignment + traceback + merged read assembly on the device"},
-            "kernel": "wf32_kernel<local,trace>", "timing": "best of 3 calls of abv_align_pairs (CUDA events inside the library for the kernel)"}
+            "kernel": "tb16_kernel<local,K=5> (two pairs per warp, 16-bit halves, traceback)", "timing": "best of 3 calls of abv_align_pairs (CUDA events inside the library for the kernel)"}
 
 
 def cluster_measurement(n_pairs):
@@ -254,6 +257,38 @@ def cluster_measurement(n_pairs):
     return {"workload": "md5 keying + grouping of %d read pairs (2 x 150 bp), ~4 copies per unique pair" % n_pairs,
             "e2e_s": best[0], "device_ms": best[1], "pairs_per_s_e2e": n_pairs / best[0], "clusters": best[2],
             "python_hashlib_pairs_per_s": m / py_s, "python_sample": m, "keys_match_hashlib_on_sample": bool(same)}
+
+
+def variants_measurement(n):
+    """secondary: the step after the path -- the variant scan of n aligned amplicons on the device
+    (caller(), ambivert/call_variants.py:32-128) beside the oracle restatement of that Python loop on a sample"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import variants_oracle as VO
+    from ambivert_b200 import batch as B, synth
+    base = synth.aligned_rows(4000, 0xF4)
+    rows = [base[i % len(base)] for i in range(n)]
+    s = B.pack([r[0].encode() for r in rows])
+    r = B.pack([x[1].encode() for x in rows])
+    B.call_variants(s, r)
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        status, start, count, recs = B.call_variants(s, r)
+        w = time.perf_counter() - t0
+        tm = B.timing()
+        if best is None or w < best[0]:
+            best = (w, tm["kernel_ms"], int(len(recs)))
+    m = 2000
+    t0 = time.perf_counter()
+    same = True
+    for k in range(m):
+        want = VO.scan(rows[k][0], rows[k][1])
+        got = recs[start[k]:start[k] + count[k]].tolist()
+        same = same and [("XDI"[a], b, c, (rows[k][1] if a == 1 else rows[k][0])[e:e + d]) for a, b, c, d, e in got] == want
+    py_s = time.perf_counter() - t0
+    return {"workload": "variant scan of %d aligned amplicons (~235 sites each)" % n, "e2e_s": best[0], "device_ms": best[1],
+            "amplicons_per_s_e2e": n / best[0], "records": best[2], "python_port_amplicons_per_s": m / py_s, "python_sample": m,
+            "records_match_port_on_sample": bool(same)}
 
 
 def cuda_arm(args, rank, world, local_rank):
@@ -383,6 +418,7 @@ def cuda_arm(args, rank, world, local_rank):
         if world == 1 and args.merge_pairs > 0:
             line["merge"] = merge_measurement(args.merge_pairs)
             line["cluster"] = cluster_measurement(args.merge_pairs)
+            line["variants"] = variants_measurement(100000)
         if world == 1 and not args.no_cpu_baseline:
             arm = cpu_arm(queries, targets, mode, args.cpu_seconds)
             sec, cells, bs, bi = arm["run"](queries[:arm["n"]])

@@ -429,3 +429,132 @@ extern "C" int emu_variants(const unsigned char *sample, int ls, const unsigned 
   });
   return rc == VAR_OK ? k : rc;
 }
+
+// ---------------------------------------------------------------------------------------------
+// tb16 (kernels.cuh::tb16_kernel): two pairs in the 16-bit halves, lane t owns columns [tK, (t+1)K), rows skewed
+// by lane.  Mirrors the kernel's item loop for ONE item with the device row function (dp_core.cuh::tb16_row) and
+// the device plane layout (Tb16Reader); the walk back uses the generic walk over the reader's nibble view.
+template <int MODE, int K>
+static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *tb0, int lb0,
+                       const unsigned char *qa1, int la1, const unsigned char *tb1, int lb1,
+                       int alpha, const int *M, int go, int ge, int pad_score,
+                       int *score, int *nfrag, FragOut *frags0, FragOut *frags1, int cap) {
+  constexpr int V = Tb16Cfg<K>::V, P = Tb16Cfg<K>::P;
+  const int a1 = alpha + 1, pad = alpha;
+  std::vector<int> mext((size_t)a1 * a1, pad_score);
+  for (int i = 0; i < alpha; ++i) for (int j = 0; j < alpha; ++j) mext[i * a1 + j] = M[i * alpha + j];
+  const int rows = std::max(lb0, lb1), tl = (std::max(la0, la1) - 1) / K, nsteps = rows + tl;
+  const int rows_cap = (rows + 15) & ~15, steps16 = tb16_steps16(rows_cap);
+  std::vector<uint16_t> tb(rows);
+  for (int r = 0; r < rows; ++r) tb[r] = (uint16_t)((r < lb0 ? tb0[r] : pad) | ((r < lb1 ? tb1[r] : pad) << 8));
+  std::vector<uint8_t> qc(2 * P, (uint8_t)pad);
+  for (int c = 0; c < 32 * K; ++c) { qc[c] = c < la0 ? qa0[c] : pad; qc[P + c] = c < la1 ? qa1[c] : pad; }
+  std::vector<uint32_t> prof((size_t)2 * a1 * P);
+  for (int idx = 0; idx < a1 * P; ++idx) {
+    const int sym = idx / P, pos = idx - sym * P;
+    const int j = pos % V, it = pos / V, t = it & 31, i = it >> 5, k = i * V + j;
+    prof[idx] = b16::addend(mext[qc[t * K + k] * a1 + sym], 0);
+    prof[a1 * P + idx] = b16::addend(0, mext[qc[P + t * K + k] * a1 + sym]);
+  }
+  const uint32_t gow = b16::addend(go, go), gew = b16::addend(ge, ge), zerob = b16::biased(0, 0);
+  std::vector<uint32_t> dir((size_t)K * TB16_PLANES * steps16 * 32, 0xdeadbeefu);
+  struct Lane { uint32_t Hp[K], F[K], acc[K][TB16_PLANES], cand[K], crow[K], hleft, h_out, e_out; };
+  std::vector<Lane> L(32);
+  for (int t = 0; t < 32; ++t) {
+    const int c0 = t * K;
+    for (int k = 0; k < K; ++k) {
+      const int c = c0 + k;
+      if (MODE == GLOBAL) { L[t].Hp[k] = b16::biased(go + ge * c, go + ge * c); L[t].F[k] = b16::biased(2 * go + ge * c, 2 * go + ge * c); }
+      else { L[t].Hp[k] = zerob; L[t].F[k] = b16::biased(go, go); }
+      for (int q = 0; q < TB16_PLANES; ++q) L[t].acc[k][q] = 0;
+      L[t].cand[k] = b16::biased(-1, -1); L[t].crow[k] = 0;
+    }
+    L[t].hleft = (MODE == GLOBAL && c0) ? b16::biased(go + ge * (c0 - 1), go + ge * (c0 - 1)) : zerob;
+    L[t].h_out = zerob; L[t].e_out = zerob;
+  }
+  const uint32_t Hv0 = MODE == GLOBAL ? b16::biased(go, go) : zerob;
+  const uint32_t Ev0 = MODE == GLOBAL ? b16::biased(2 * go, 2 * go) : b16::biased(go, go);
+  const int t0 = (la0 - 1) / K, k0 = (la0 - 1) - t0 * K, t1 = (la1 - 1) / K, k1 = (la1 - 1) - t1 * K;
+  int corner0 = 0, corner1 = 0;
+  for (int s16 = 0; s16 < nsteps; s16 += 16) {
+    for (int j = 0; j < 16; ++j) {
+      const int s = s16 + j;
+      uint32_t h_sh[32], e_sh[32];
+      for (int t = 0; t < 32; ++t) { h_sh[t] = L[t ? t - 1 : 0].h_out; e_sh[t] = L[t ? t - 1 : 0].e_out; }
+      for (int t = 0; t < 32; ++t) {
+        const int r = s - t;
+        if (t == 0) {
+          h_sh[0] = MODE == GLOBAL ? Hv0 + (uint32_t)r * gew : Hv0;
+          e_sh[0] = MODE == GLOBAL ? Ev0 + (uint32_t)r * gew : Ev0;
+        }
+        if (r >= 0 && r < rows && t <= tl) {
+          const unsigned code = tb[r];
+          uint32_t Slo[K], Shi[K];
+          for (int k = 0; k < K; ++k) {
+            Slo[k] = prof[(code & 255u) * P + tb16_slot(t, k, V)];
+            Shi[k] = prof[(a1 + (code >> 8)) * P + tb16_slot(t, k, V)];
+          }
+          uint32_t e = e_sh[t];
+          tb16_row<MODE, K>(L[t].hleft, e, L[t].Hp, L[t].F, Slo, Shi, gow, gew, zerob, 15 - j, TB16_H >> (15 - j), L[t].acc, L[t].cand, L[t].crow,
+                            (uint32_t)r * 0x10001u);
+          L[t].hleft = h_sh[t]; L[t].e_out = e; L[t].h_out = L[t].Hp[K - 1];
+          if (MODE == GLOBAL) {
+            if (r == lb0 - 1 && t == t0) corner0 = b16::lo(L[t].Hp[k0]);
+            if (r == lb1 - 1 && t == t1) corner1 = b16::hi(L[t].Hp[k1]);
+          }
+        }
+      }
+    }
+    for (int t = 0; t < 32; ++t)
+      for (int k = 0; k < K; ++k)
+        for (int q = 0; q < TB16_PLANES; ++q) {
+          dir[((size_t)(k * TB16_PLANES + q) * steps16 + (s16 >> 4)) * 32 + t] = L[t].acc[k][q];
+          L[t].acc[k][q] = 0;
+        }
+  }
+  int sc[2], ec[2], er[2];
+  if (MODE == GLOBAL) { sc[0] = corner0; sc[1] = corner1; ec[0] = la0 - 1; er[0] = lb0 - 1; ec[1] = la1 - 1; er[1] = lb1 - 1; }
+  else {
+    long long key[2] = {-1, -1};
+    for (int t = 0; t < 32; ++t) {
+      int b[2] = {-1, -1}, bc[2] = {0, 0}, br[2] = {0, 0};
+      for (int k = 0; k < K; ++k) {
+        const int v0 = b16::lo(L[t].cand[k]), v1 = b16::hi(L[t].cand[k]);
+        if (v0 >= 0 && v0 >= b[0]) { b[0] = v0; bc[0] = t * K + k; br[0] = (int)(L[t].crow[k] & 0xffffu); }
+        if (v1 >= 0 && v1 >= b[1]) { b[1] = v1; bc[1] = t * K + k; br[1] = (int)(L[t].crow[k] >> 16); }
+      }
+      for (int h = 0; h < 2; ++h)
+        key[h] = std::max(key[h], b[h] < 0 ? -1ll : (((long long)b[h] << 40) | ((long long)bc[h] << 20) | br[h]));
+    }
+    for (int h = 0; h < 2; ++h) {
+      if (key[h] < 0) { sc[h] = 0; ec[h] = 0; er[h] = 0; }
+      else { sc[h] = (int)(key[h] >> 40); ec[h] = (int)((key[h] >> 20) & 0xfffff); er[h] = (int)(key[h] & 0xfffff); }
+    }
+  }
+  for (int h = 0; h < 2; ++h) {
+    Tb16Reader<K> rd; rd.w = dir.data(); rd.steps16 = steps16; rd.half = h;
+    score[h] = sc[h];
+    nfrag[h] = walk_back<MODE>(rd, ec[h], er[h], h ? frags1 : frags0, cap);
+  }
+}
+
+template <int MODE>
+static int emu_tb16_k(int K, const unsigned char *qa0, int la0, const unsigned char *tb0, int lb0,
+                      const unsigned char *qa1, int la1, const unsigned char *tb1, int lb1,
+                      int alpha, const int *M, int go, int ge, int pad_score, int *score, int *nfrag, FragOut *f0, FragOut *f1, int cap) {
+#define ABV_TB16_CASE(KK) case KK: emu_tb16_t<MODE, KK>(qa0, la0, tb0, lb0, qa1, la1, tb1, lb1, alpha, M, go, ge, pad_score, score, nfrag, f0, f1, cap); return 0;
+  switch (K) {
+    ABV_TB16_CASE(2) ABV_TB16_CASE(4) ABV_TB16_CASE(5) ABV_TB16_CASE(6) ABV_TB16_CASE(7) ABV_TB16_CASE(8) ABV_TB16_CASE(10)
+    default: return -1;
+  }
+#undef ABV_TB16_CASE
+}
+
+// fragments come back in REVERSE sequence order (as the kernel's scratch holds them)
+extern "C" int emu_tb16(int mode, int K, const unsigned char *qa0, int la0, const unsigned char *tb0, int lb0,
+                        const unsigned char *qa1, int la1, const unsigned char *tb1, int lb1,
+                        int alpha, const int *M, int go, int ge, int pad_score, int *score, int *nfrag, FragOut *f0, FragOut *f1, int cap) {
+  if (mode == LOCAL) return emu_tb16_k<LOCAL>(K, qa0, la0, tb0, lb0, qa1, la1, tb1, lb1, alpha, M, go, ge, pad_score, score, nfrag, f0, f1, cap);
+  if (mode == GLOBAL) return emu_tb16_k<GLOBAL>(K, qa0, la0, tb0, lb0, qa1, la1, tb1, lb1, alpha, M, go, ge, pad_score, score, nfrag, f0, f1, cap);
+  return -1;
+}

@@ -99,25 +99,8 @@ def test_bundled_pipeline_after_alignment_matches_reference(gold, name):
 
 
 def _synthetic_rows(n, seed):
-    """aligned rows of config-4-like amplicons: 27 bp lower-case primer flanks, ~200 bp core, a few events each"""
-    rng = random.Random(seed)
-    rows = []
-    for _ in range(n):
-        core = rng.randint(150, 210)
-        ref = [rng.choice("acgt") for _ in range(27)] + [rng.choice("ACGT") for _ in range(core)] + [rng.choice("acgt") for _ in range(27)]
-        s, r = [], []
-        for b in ref:
-            x = rng.random()
-            if x < 0.004:
-                s.append("-"); r.append(b)
-            elif x < 0.008:
-                s.append(rng.choice("ACGT")); r.append("-"); s.append(b.upper()); r.append(b)
-            elif x < 0.02:
-                s.append(rng.choice("ACGTN")); r.append(b)
-            else:
-                s.append(b.upper()); r.append(b)
-        rows.append(("".join(s), "".join(r)))
-    return rows
+    from ambivert_b200 import synth
+    return synth.aligned_rows(n, seed)
 
 
 def test_full_size_scan_properties_and_oracle_sample():

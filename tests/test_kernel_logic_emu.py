@@ -197,3 +197,70 @@ def test_streaming_logic_vs_oracle(emu, oracle_port, mode):
             assert s1[i] == chk.align_raw(mode, q, t1[i], 5, M, go, ge)[0], (it, K, lq, i, list(l1), list(l2), go, ge)
             if len(t2[i]):
                 assert s2[i] == chk.align_raw(mode, q, t2[i], 5, M, go, ge)[0], (it, K, lq, i, list(l1), list(l2), go, ge)
+
+
+TB16_KS = [2, 4, 5, 6, 7, 8, 10]
+
+
+def emu_tb16(lib, mode, K, pair0, pair1, alpha, M, go, ge):
+    """-> [(score, frags) of pair 0, (score, frags) of pair 1]; frags in sequence order"""
+    M = np.ascontiguousarray(M, dtype=np.int32)
+    pad_score = -(int(np.abs(M).max()) + 1)
+    cap = max(len(pair0[0]) + len(pair0[1]), len(pair1[0]) + len(pair1[1])) + 2
+    f0, f1 = np.zeros(cap * 4, np.int32), np.zeros(cap * 4, np.int32)
+    sc, nf = (C.c_int * 2)(), (C.c_int * 2)()
+    lib.emu_tb16.restype = C.c_int
+    rc = lib.emu_tb16(C.c_int(mode), C.c_int(K), pair0[0], C.c_int(len(pair0[0])), pair0[1], C.c_int(len(pair0[1])),
+                      pair1[0], C.c_int(len(pair1[0])), pair1[1], C.c_int(len(pair1[1])), C.c_int(alpha), M.ctypes.data_as(C.c_void_p),
+                      C.c_int(go), C.c_int(ge), C.c_int(pad_score), sc, nf, f0.ctypes.data_as(C.c_void_p), f1.ctypes.data_as(C.c_void_p), C.c_int(cap))
+    assert rc == 0
+    out = []
+    for h, f in enumerate((f0, f1)):
+        n = nf[h]
+        assert 0 <= n <= cap
+        out.append((sc[h], [tuple(int(x) for x in f[4 * i:4 * i + 4]) for i in range(n)][::-1]))
+    return out
+
+
+def test_tb16_logic_vs_oracle(emu, oracle_port):
+    """the packed traceback kernel's row function, plane layout and end-cell rules on the CPU: two pairs of different
+    shapes per word, every strip width, local and global, ties (repeats), N, other penalties and matrices"""
+    rng = random.Random(1616)
+    chk = oracle_port
+
+    def pair(K, alpha, alphabet_n):
+        la = rng.randint(max(1, 32 * K - 40), 32 * K) if rng.random() < 0.5 else rng.randint(1, 32 * K)
+        if rng.random() < 0.15:
+            unit = bytes(rng.randrange(2) for _ in range(rng.randint(1, 4)))
+            sa = (unit * (la // len(unit) + 1))[:la]
+        else:
+            sa = bytes(rng.randrange(alphabet_n) for _ in range(la))
+        x = rng.random()
+        if x < 0.5:
+            sb = bytearray(sa)
+            for _ in range(rng.randint(0, 6)):
+                if len(sb) > 2 and rng.random() < 0.5:
+                    p = rng.randrange(len(sb)); del sb[p:p + rng.randint(1, 6)]
+                else:
+                    p = rng.randrange(len(sb) + 1); sb[p:p] = bytes(rng.randrange(alphabet_n) for _ in range(rng.randint(1, 6)))
+            sb = bytes(sb) or b"\x00"
+        elif x < 0.7:
+            cut = rng.randrange(len(sa))
+            sb = sa[cut:] + bytes(rng.randrange(alphabet_n) for _ in range(rng.randint(1, 60)))
+        else:
+            sb = bytes(rng.randrange(alphabet_n) for _ in range(rng.choice([1, 2, 3, rng.randint(1, 200)])))
+        return sa, sb
+
+    for it in range(400):
+        mode = rng.choice([O.LOCAL, O.GLOBAL])
+        K = rng.choice(TB16_KS)
+        if rng.random() < 0.6:
+            alpha, M, go, ge = 5, O.DNA_SCORE, -7, -1
+        else:
+            alpha = rng.choice([2, 4, 5, 7])
+            M = np.array([rng.randint(-5, 5) for _ in range(alpha * alpha)], np.int32)
+            go, ge = -rng.randint(1, 9), -rng.randint(0, 3)
+        p0, p1 = pair(K, alpha, alpha), pair(K, alpha, alpha)
+        got = emu_tb16(emu, mode, K, p0, p1, alpha, M, go, ge)
+        for h, (sa, sb) in enumerate((p0, p1)):
+            assert got[h] == chk.align_raw(mode, sa, sb, alpha, M, go, ge), (it, mode, K, h, sa, sb, go, ge)

@@ -7,10 +7,10 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.
 import numpy as np
 import variants_oracle as VO
 from ambivert_b200 import batch as B
-from test_gpu_variants import _synthetic_rows
+from ambivert_b200 import synth
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
-base = _synthetic_rows(5000, 0xF4)
+base = synth.aligned_rows(5000, 0xF4)
 rows = [base[i % len(base)] for i in range(n)]
 s = B.pack([r[0].encode() for r in rows]); r = B.pack([x[1].encode() for x in rows])
 B.call_variants(s, r)
