@@ -378,7 +378,7 @@ ABV_HD void mm16d_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (
 // (one 3-input add; no borrow crosses the halves because a + 0x8000 >= b), and combined with 3-input logic ops:
 //   pa = ge(diag, F) (diag wins ties), pb = ge(max(diag,F), E) (both win ties over E), pc = ge(value, 0) (local: else stop),
 //   fo = ge(h + go, F + ge), eo = ge(h + go, E + ge) (opening wins ties)
-//   direction = SRC_* of wf32: bit0 = (!pa & pb) | !pc, bit1 = !pb | !pc; plus the two "gap re-opened" bits
+//   direction = SRC_* of wf32: bit0 = (!pa & pb) | !pc, bit1 = !(pb & pc) (stored complemented); plus the two "gap re-opened" bits
 // Each of the four direction bits goes to its own bit PLANE: one word per column and 16 steps, bit j (low half) and
 // 16 + j (high half) = step 16*w + j.
 namespace p16 {
@@ -405,6 +405,16 @@ ABV_HD int tb16_steps16(int rows_cap) { return (rows_cap + 31 + 15) >> 4; }
 // word of the profile row that holds column k of lane t: the lanes of one shared-memory phase read 32 distinct banks
 ABV_HD int tb16_slot(int t, int k, int V) { return ((k / V) * 32 + t) * V + k % V; }
 ABV_HD uint32_t tb16_ge(uint32_t a, uint32_t b) { return a + TB16_H - b; }
+// acc | (x & m) as ONE 3-input logic op (left to itself the compiler masks with the immediate first: 3 ops per plane)
+ABV_HD uint32_t tb16_insert(uint32_t acc, uint32_t x, uint32_t m) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(x), "r"(m), "r"(acc));
+  return d;
+#else
+  return acc | (x & m);
+#endif
+}
 
 // One row of one lane.  All score-like values are b16-biased.
 //   hleft : H[c0-1][r-1]        e : in E[r] entering the strip, out E[r] leaving it
@@ -424,33 +434,33 @@ ABV_HD void tb16_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&
     const uint32_t s0 = d + Slo[k] + Shi[k];
     d = Hp[k];
     const uint32_t t = p16::max2(s0, F[k]);
-    const uint32_t pa = tb16_ge(s0, F[k]);
+    const uint32_t pa = tb16_ge(s0, F[k]);                // s0 >= F: the diagonal wins ties
     const uint32_t hr = p16::max2(t, e);
-    const uint32_t pb = tb16_ge(t, e);
+    const uint32_t pb = tb16_ge(t, e);                    // max(diag, F) >= E
     uint32_t h = hr, b0, b1;
     if (MODE == LOCAL) {
       h = p16::max2(hr, zerob);
-      const uint32_t pc = tb16_ge(hr, zerob);
+      const uint32_t pc = tb16_ge(hr, zerob);             // value >= 0, else the cell is a stop
       b0 = (~pa & pb) | ~pc;
-      b1 = ~(pb & pc);
+      b1 = pb & pc;                                       // plane 1 holds the COMPLEMENT of source bit 1
       bool pn_h, pn_l;
       cand[k] = p16::bmax(hr, cand[k], pn_h, pn_l);       // a stop cell (hr < 0) never beats a candidate (>= -1)
       if (pn_l) crow[k] = (crow[k] & 0xffff0000u) | (rr & 0x0000ffffu);
       if (pn_h) crow[k] = (crow[k] & 0x0000ffffu) | (rr & 0xffff0000u);
     } else {
       b0 = ~pa & pb;
-      b1 = ~pb;
+      b1 = pb;
     }
     const uint32_t hg = h + gow, fe = F[k] + gew, ee = e + gew;
     F[k] = p16::max2(hg, fe);
-    const uint32_t fo = tb16_ge(hg, fe);
+    const uint32_t fo = tb16_ge(hg, fe);                  // opening wins ties
     e = p16::max2(hg, ee);
     const uint32_t eo = tb16_ge(hg, ee);
     Hp[k] = h;
-    acc[k][0] |= (b0 >> sh) & MJ;
-    acc[k][1] |= (b1 >> sh) & MJ;
-    acc[k][2] |= (fo >> sh) & MJ;
-    acc[k][3] |= (eo >> sh) & MJ;
+    acc[k][0] = tb16_insert(acc[k][0], b0 >> sh, MJ);
+    acc[k][1] = tb16_insert(acc[k][1], b1 >> sh, MJ);
+    acc[k][2] = tb16_insert(acc[k][2], fo >> sh, MJ);
+    acc[k][3] = tb16_insert(acc[k][3], eo >> sh, MJ);
   }
 }
 
@@ -465,7 +475,7 @@ struct Tb16Reader {
     const uint32_t v = w[((long long)(k * TB16_PLANES + plane) * steps16 + (s >> 4)) * 32 + t];
     return (v >> ((s & 15) + 16 * half)) & 1u;
   }
-  ABV_HD unsigned src(int col, int row) const { return plane_bit(0, col, row) | (plane_bit(1, col, row) << 1); }
+  ABV_HD unsigned src(int col, int row) const { return plane_bit(0, col, row) | ((plane_bit(1, col, row) ^ 1u) << 1); }
   ABV_HD unsigned get(int col, int row) const {       // the nibble of wf32 (for the generic walk)
     return src(col, row) | (plane_bit(2, col, row) ? BIT_FOPEN : 0u) | (plane_bit(3, col, row) ? BIT_EOPEN : 0u);
   }

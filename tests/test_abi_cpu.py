@@ -74,6 +74,14 @@ def test_no_cpu_fallback_without_gpu():
     assert e.value.code == B.ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
     with pytest.raises(B.AlignError):
         B.align_pairs([b"ACGT"], [b"ACGT"], B.LOCAL)
+    for call in (lambda: B.call_variants([b"ACGT"], [b"ACGA"]), lambda: B.cluster_pairs([b"ACGT"], [b"ACGA"]),
+                 lambda: B.merge_pairs([b"ACGT"], [b"ACGT"])):
+        with pytest.raises(B.AlignError) as e:      # the steps either side of the path have no CPU implementation either
+            call()
+        assert e.value.code == B.ERR_NO_DEVICE
+    from ambivert_b200 import call_variants as CV
+    with pytest.raises(B.AlignError):
+        list(CV.caller("AAAA", "AAGA"))
 
 
 def test_argument_validation_needs_no_gpu():
