@@ -50,6 +50,10 @@ _lib.abv_merge_pairs.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp,
 _lib.abv_cluster_pairs.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]
 _lib.abv_call_variants.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_longlong, _vp]
 _lib.abv_get_timing.argtypes = [_vp, C.c_int]
+_lib.abv_pinned_alloc.argtypes = [C.c_ulonglong]
+_lib.abv_pinned_alloc.restype = _vp
+_lib.abv_pinned_free.argtypes = [_vp]
+_lib.abv_pinned_free.restype = None
 _lib.abv_int_peak.argtypes = [C.c_int, C.c_int, _vp, _vp]
 
 
@@ -78,6 +82,29 @@ def version():
 
 def set_option(key, value):
     _check(_lib.abv_set_option(key.encode(), int(value)))
+
+
+class _Pinned(object):
+    """owner of one page-locked allocation; numpy arrays made from it keep it alive"""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        self.ptr = _lib.abv_pinned_alloc(max(self.nbytes, 16))
+        if not self.ptr:
+            raise AlignError(ERR_NOMEM, "cannot allocate %d bytes of page-locked memory" % self.nbytes)
+        self.__array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self, _free=_lib.abv_pinned_free):       # bound at definition: module globals may be gone at interpreter exit
+        if getattr(self, "ptr", None):
+            _free(self.ptr)
+            self.ptr = None
+
+
+def pinned_empty(count, dtype=np.uint8):
+    """uninitialised numpy array in page-locked host memory (abv_pinned_alloc): copies to / from it are asynchronous and
+    run at full bus speed.  Use it for the big inputs (packed sequences) and for `out=` buffers of merge_pairs/gapped_pairs."""
+    dt = np.dtype(dtype)
+    return np.asarray(_Pinned(int(count) * dt.itemsize)).view(dt)[:int(count)]
 
 
 def pack(seqs):
@@ -248,10 +275,11 @@ def gapped_pairs(seqs_a, seqs_b, mode, alpha_len=DNA_MAP[0], map256=DNA_MAP[1], 
 
 
 def merge_pairs(fwds, revs, minimum_overlap=10, alpha_len=DNA_MAP[0], map256=DNA_MAP[1], matrix=DNA_SCORE,
-                gap_open=GAP_OPEN, gap_extend=GAP_EXTEND):
+                gap_open=GAP_OPEN, gap_extend=GAP_EXTEND, out=None):
     """Local alignment + merged read of every (forward read, reverse-complemented reverse read) pair, built on
     the device (ambivert.py:320-327).  -> (scores, status, merged_off int64[n+1], merged uint8[total]);
-    status: 1 merged, 0 unmergable (overlap below minimum_overlap), -1 empty alignment, -2 bad base pair"""
+    status: 1 merged, 0 unmergable (overlap below minimum_overlap), -1 empty alignment, -2 bad base pair.
+    out: optional uint8 buffer for the merged reads (e.g. pinned_empty(...)), at least len(fwd bytes) + len(rev bytes) + 16"""
     a, ao = pack(fwds)
     b, bo = pack(revs)
     n = len(ao) - 1
@@ -260,7 +288,13 @@ def merge_pairs(fwds, revs, minimum_overlap=10, alpha_len=DNA_MAP[0], map256=DNA
     scores, status = np.empty(n, np.int32), np.empty(n, np.int32)
     off = np.zeros(n + 1, np.int64)
     cap = int(a.size + b.size) + 16          # a merged read is never longer than both reads together
-    merged = np.empty(cap, np.uint8)
+    if out is not None:
+        merged = out
+        if merged.dtype != np.uint8 or not merged.flags.c_contiguous or merged.size < cap:
+            raise ValueError("out must be a contiguous uint8 array of at least %d bytes" % cap)
+        cap = int(merged.size)
+    else:
+        merged = np.empty(cap, np.uint8)
     total = C.c_longlong(0)
     _check(_lib.abv_merge_pairs(_ptr(a), _ptr(ao), _ptr(b), _ptr(bo), n, alpha_len, _ptr(mp), _ptr(m), gap_open, gap_extend,
                                 int(minimum_overlap), _ptr(scores), _ptr(status), _ptr(off), _ptr(merged), cap, C.byref(total)))

@@ -185,35 +185,44 @@ int check_mode_lengths(int mode, int min_la, int min_lb) {
 }
 
 // upload a concatenated sequence set and encode it on the device
+// Host buffers an upload reads asynchronously; they must outlive the stream work (the caller syncs before dropping them).
+struct UploadKeep {
+  std::vector<long long> rel[4];
+  unsigned char clamped[256];
+  int used = 0;
+};
+
+// Sequences -> device: raw bytes + offsets, then to_raw on the device (helpers.h:26-32).  With `keep` nothing here waits
+// for the stream (pinned caller buffers then copy while the host goes on planning); without it the call returns synchronised.
 int upload_encoded(const char *buf, const long long *off, int n, const Scoring &sc, cudaStream_t st,
-                   DevMem &d_codes, DevMem &d_off, DevMem &d_map, double &h2d_bytes, DevMem *keep_raw = nullptr) {
+                   DevMem &d_codes, DevMem &d_off, DevMem &d_map, double &h2d_bytes, DevMem *keep_raw = nullptr, UploadKeep *keep = nullptr) {
+  UploadKeep local;
+  UploadKeep &K = keep ? *keep : local;
   const long long total = n ? off[n] - off[0] : 0;
-  std::vector<long long> rel(n + 1);
+  std::vector<long long> &rel = K.rel[K.used++ & 3];
+  rel.resize((size_t)n + 1);
   for (int i = 0; i <= n; ++i) rel[i] = n ? off[i] - off[0] : 0;
   CU(d_off.alloc(sizeof(long long) * (n + 1)));
   CU(cudaMemcpyAsync(d_off.p, rel.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
-  CU(cudaStreamSynchronize(st));   // rel is a local
   CU(d_codes.alloc((size_t)total + 16));
   DevMem raw;
   unsigned char ident[256];
   const unsigned char *m = sc.map256;
   if (!m) { for (int i = 0; i < 256; ++i) ident[i] = (unsigned char)i; m = ident; }
-  unsigned char clamped[256];
-  for (int i = 0; i < 256; ++i) clamped[i] = (unsigned char)std::min<int>(m[i], sc.alpha - 1);
+  for (int i = 0; i < 256; ++i) K.clamped[i] = (unsigned char)std::min<int>(m[i], sc.alpha - 1);
   if (!d_map.p) CU(d_map.alloc(256));
-  CU(cudaMemcpyAsync(d_map.p, clamped, 256, cudaMemcpyHostToDevice, st));
-  CU(cudaStreamSynchronize(st));
+  CU(cudaMemcpyAsync(d_map.p, K.clamped, 256, cudaMemcpyHostToDevice, st));
   if (total > 0) {
     CU(raw.alloc((size_t)total));
     CU(cudaMemcpyAsync(raw.p, buf + off[0], (size_t)total, cudaMemcpyHostToDevice, st));
     int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
     encode_kernel<<<blocks, 256, 0, st>>>(raw.as<uint8_t>(), d_codes.as<uint8_t>(), total, d_map.as<uint8_t>());
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(st));
     if (keep_raw) { keep_raw->release(); keep_raw->p = raw.p; keep_raw->bytes = raw.bytes; raw.p = nullptr; raw.bytes = 0; }
   }
+  if (!keep) CU(cudaStreamSynchronize(st));     // the staging vectors are locals
   h2d_bytes += (double)total + sizeof(long long) * (n + 1) + 256;
-  return ABV_OK;
+  return ABV_OK;                                // `raw` returns to the allocation cache; its reuse is ordered on the same stream
 }
 
 // ---- wf32 launcher ----------------------------------------------------------------------------
@@ -657,7 +666,7 @@ int tb16_launch_mode(int K, cudaStream_t st, const Tb16Params &p, size_t dir_byt
 // Pairs the packed kernel can take, bucketed by columns per lane and sorted by target length so that the two
 // pairs of a warp have similar shapes.  list = [bucket 0 items: (i0, i1) ...][bucket 1 ...]...[pairs for wf32]
 struct Tb16Plan {
-  std::vector<int> list;
+  std::vector<int> list, key, mext;
   struct Bucket { int K, offset, n_items, rows_cap, max_la, max_lb; };
   std::vector<Bucket> buckets;
   int rest_offset = 0, n_rest = 0, rest_max_la = 0, rest_max_lb = 0;
@@ -676,50 +685,54 @@ void tb16_plan(Tb16Plan &P, int mode, const long long *a_off, const long long *b
   P.pad_score = -(maxabs + 1);
   const int unit = std::max(std::max(-sc.go, -sc.ge), maxabs + 1);
   const bool ok = tb16_eligible(mode, sc);
-  // counting sort by (bucket, lb)
-  std::vector<int> key((size_t)n);
-  std::vector<int> hist((size_t)(TB16_NK + 1) * (TB16_MAX_ROWS + 1) + 1, 0);
-  for (int i = 0; i < n; ++i) {
-    const long long la = a_off[i + 1] - a_off[i], lb = b_off[i + 1] - b_off[i];
-    int b = TB16_NK;
-    if (ok && lb <= TB16_MAX_ROWS && la <= 32 * TB16_KS[TB16_NK - 1]) {
-      b = 0;
-      while (32 * TB16_KS[b] < la) ++b;
-      if ((32ll * TB16_KS[b] + lb + 2) * unit - 2ll * sc.go > b16::LIMIT) b = TB16_NK;     // values must stay in the biased range
-    }
-    key[i] = b * (TB16_MAX_ROWS + 1) + (b == TB16_NK ? 0 : (int)lb);
-    ++hist[key[i] + 1];
-  }
-  for (size_t k = 1; k < hist.size(); ++k) hist[k] += hist[k - 1];
-  std::vector<int> sorted((size_t)n);
-  {
-    std::vector<int> pos(hist.begin(), hist.end() - 1);
-    for (int i = 0; i < n; ++i) sorted[pos[key[i]]++] = i;
-  }
-  P.list.clear();
-  P.buckets.clear();
+  // counting sort by (bucket, lb), two passes over the pairs; the sorted order is written straight into the list
+  constexpr int NKEY = (TB16_NK + 1) * (TB16_MAX_ROWS + 1);
+  P.key.resize((size_t)n);
+  std::vector<int> hist((size_t)NKEY + 1, 0);
+  int max_la[TB16_NK + 1] = {0};
+  int la_limit[TB16_NK], lb_limit[TB16_NK];          // per bucket: longest query, longest target that keeps values in range
   for (int b = 0; b < TB16_NK; ++b) {
-    const int lo = hist[(size_t)b * (TB16_MAX_ROWS + 1)], hi = hist[(size_t)(b + 1) * (TB16_MAX_ROWS + 1)];
-    if (hi == lo) continue;
-    Tb16Plan::Bucket B{TB16_KS[b], (int)P.list.size(), (hi - lo + 1) / 2, 0, 0, 0};
-    for (int j = lo; j < hi; j += 2) {
-      P.list.push_back(sorted[j]);
-      P.list.push_back(j + 1 < hi ? sorted[j + 1] : -1);
-    }
-    for (int j = lo; j < hi; ++j) {
-      B.max_la = std::max(B.max_la, (int)(a_off[sorted[j] + 1] - a_off[sorted[j]]));
-      B.max_lb = std::max(B.max_lb, (int)(b_off[sorted[j] + 1] - b_off[sorted[j]]));
-    }
-    B.rows_cap = (B.max_lb + 15) & ~15;
-    P.buckets.push_back(B);
+    la_limit[b] = 32 * TB16_KS[b];
+    lb_limit[b] = (int)std::min<long long>(TB16_MAX_ROWS, (b16::LIMIT + 2ll * sc.go) / unit - 32ll * TB16_KS[b] - 2);
   }
-  const int lo = hist[(size_t)TB16_NK * (TB16_MAX_ROWS + 1)];
-  P.rest_offset = (int)P.list.size();
-  P.n_rest = n - lo;
-  for (int j = lo; j < n; ++j) {
-    P.list.push_back(sorted[j]);
-    P.rest_max_la = std::max(P.rest_max_la, (int)(a_off[sorted[j] + 1] - a_off[sorted[j]]));
-    P.rest_max_lb = std::max(P.rest_max_lb, (int)(b_off[sorted[j] + 1] - b_off[sorted[j]]));
+  P.rest_max_la = P.rest_max_lb = 0;
+  for (int i = 0; i < n; ++i) {
+    const int la = (int)std::min<long long>(a_off[i + 1] - a_off[i], INT_MAX), lb = (int)std::min<long long>(b_off[i + 1] - b_off[i], INT_MAX);
+    int b = TB16_NK;
+    if (ok && la <= la_limit[TB16_NK - 1]) {
+      b = 0;
+      while (la_limit[b] < la) ++b;
+      if (lb > lb_limit[b]) b = TB16_NK;
+    }
+    if (b == TB16_NK) { P.rest_max_la = std::max(P.rest_max_la, la); P.rest_max_lb = std::max(P.rest_max_lb, lb); }
+    else max_la[b] = std::max(max_la[b], la);
+    const int k = b * (TB16_MAX_ROWS + 1) + (b == TB16_NK ? 0 : lb);
+    P.key[i] = k;
+    ++hist[k + 1];
+  }
+  for (int k = 1; k <= NKEY; ++k) hist[k] += hist[k - 1];
+  // list position of the first pair of every bucket (an odd bucket gets one -1 partner at its end)
+  P.buckets.clear();
+  int shift[TB16_NK + 1];
+  int extra = 0;
+  for (int b = 0; b < TB16_NK; ++b) {
+    shift[b] = extra;
+    const int lo = hist[b * (TB16_MAX_ROWS + 1)], hi = hist[(b + 1) * (TB16_MAX_ROWS + 1)];
+    if (hi == lo) continue;
+    int max_lb = 0;
+    for (int lb = TB16_MAX_ROWS; lb >= 0; --lb)
+      if (hist[b * (TB16_MAX_ROWS + 1) + lb + 1] > hist[b * (TB16_MAX_ROWS + 1) + lb]) { max_lb = lb; break; }
+    P.buckets.push_back(Tb16Plan::Bucket{TB16_KS[b], lo + extra, (hi - lo + 1) / 2, (max_lb + 15) & ~15, max_la[b], max_lb});
+    extra += (hi - lo) & 1;
+  }
+  shift[TB16_NK] = extra;
+  const int lo_rest = hist[TB16_NK * (TB16_MAX_ROWS + 1)];
+  P.rest_offset = lo_rest + extra;
+  P.n_rest = n - lo_rest;
+  P.list.assign((size_t)n + extra, -1);
+  for (int i = 0; i < n; ++i) {
+    const int k = P.key[i];
+    P.list[(size_t)(hist[k]++) + shift[k / (TB16_MAX_ROWS + 1)]] = i;
   }
 }
 
@@ -868,6 +881,7 @@ int abv_score_matrix(int mode, const char *q, const long long *q_off, int n_q,
 struct PairsRun {
   DevMem a_codes, a_off, b_codes, b_off, a_raw, b_raw, map, matrix;
   DevMem dir, tmp, border, scores, start, count, frags, counters, lists, matrix_ext;
+  UploadKeep keep;
   long long pool = 0;
   unsigned long long total = 0;
   int max_la = 0, max_lb = 0;
@@ -892,15 +906,15 @@ static int pairs_run(PairsRun &R, int mode, const char *a, const long long *a_of
   cudaStream_t st = g.stream;
   CU(cudaEventRecord(g.ev[0], st));
   if (!R.a_codes.p) {   // first attempt: the inputs are not on the device yet
-    if ((rc = upload_encoded(a, a_off, n, sc, st, R.a_codes, R.a_off, R.map, R.h2d, keep_raw ? &R.a_raw : nullptr))) return rc;
-    if ((rc = upload_encoded(b, b_off, n, sc, st, R.b_codes, R.b_off, R.map, R.h2d, keep_raw ? &R.b_raw : nullptr))) return rc;
+    if ((rc = upload_encoded(a, a_off, n, sc, st, R.a_codes, R.a_off, R.map, R.h2d, keep_raw ? &R.a_raw : nullptr, &R.keep))) return rc;
+    if ((rc = upload_encoded(b, b_off, n, sc, st, R.b_codes, R.b_off, R.map, R.h2d, keep_raw ? &R.b_raw : nullptr, &R.keep))) return rc;
     CU(R.matrix.alloc(sizeof(int) * sc.alpha * sc.alpha));
     CU(cudaMemcpyAsync(R.matrix.p, sc.matrix, sizeof(int) * sc.alpha * sc.alpha, cudaMemcpyHostToDevice, st));
     R.cells = 0;
     for (int i = 0; i < n; ++i) R.cells += (double)(a_off[i + 1] - a_off[i]) * (double)(b_off[i + 1] - b_off[i]);
   }
   // plan: pairs the packed traceback kernel takes (bucketed, partnered) and the rest for the 32-bit kernel
-  Tb16Plan plan;
+  static thread_local Tb16Plan plan;      // keeps its vectors' capacity from call to call
   tb16_plan(plan, mode, a_off, b_off, n, sc);
   const int tmp_cap = R.max_la + R.max_lb + 2;
   const long long dwords = plan.n_rest ? dir_words(plan.rest_max_la, plan.rest_max_lb) : 0;
@@ -927,14 +941,13 @@ static int pairs_run(PairsRun &R, int mode, const char *a, const long long *a_of
   CU(cudaMemcpyAsync(R.lists.p, plan.list.data(), sizeof(int) * plan.list.size(), cudaMemcpyHostToDevice, st));
   if (!plan.buckets.empty()) {
     const int a1 = sc.alpha + 1;
-    std::vector<int> mext((size_t)a1 * a1, plan.pad_score);
+    plan.mext.assign((size_t)a1 * a1, plan.pad_score);
     for (int i = 0; i < sc.alpha; ++i)
-      for (int j = 0; j < sc.alpha; ++j) mext[(size_t)i * a1 + j] = sc.matrix[i * sc.alpha + j];
-    CU(R.matrix_ext.alloc(sizeof(int) * mext.size()));
-    CU(cudaMemcpyAsync(R.matrix_ext.p, mext.data(), sizeof(int) * mext.size(), cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));    // mext is a local
+      for (int j = 0; j < sc.alpha; ++j) plan.mext[(size_t)i * a1 + j] = sc.matrix[i * sc.alpha + j];
+    CU(R.matrix_ext.alloc(sizeof(int) * plan.mext.size()));
+    CU(cudaMemcpyAsync(R.matrix_ext.p, plan.mext.data(), sizeof(int) * plan.mext.size(), cudaMemcpyHostToDevice, st));
   }
-  CU(cudaStreamSynchronize(st));      // plan.list is a local
+  // no wait here: plan is thread-local and this function synchronises the stream before it returns
   CU(cudaEventRecord(g.ev[1], st));
 
   unsigned long long *counters = R.counters.as<unsigned long long>();   // [0] wf32 pairs, [1] fragment total, [2..] tb16 items per bucket
@@ -1315,6 +1328,17 @@ int abv_call_variants(const char *sample, const long long *sample_off, const cha
   t_timing[0] = a; t_timing[1] = b; t_timing[2] = c; t_timing[3] = 0; t_timing[4] = total > 0 ? 4 : 3;
   t_timing[5] = (double)sbytes + rbytes + 16.0 * (n + 1); t_timing[6] = 12.0 * n + 8.0 + 20.0 * (double)total; t_timing[7] = b;
   return rc;
+}
+
+void *abv_pinned_alloc(unsigned long long bytes) {
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  if (ctx_init() != ABV_OK) return nullptr;
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, (size_t)std::max<unsigned long long>(bytes, 16), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void abv_pinned_free(void *p) {
+  if (p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();
 }
 
 int abv_get_timing(double *out, int n) {

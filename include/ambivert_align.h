@@ -260,6 +260,14 @@ int abv_call_variants(const char *sample, const long long *sample_off, const cha
                       abv_variant *recs, long long rec_cap, long long *rec_total);
 
 /*
+ * Page-locked host memory for buffers handed to the batched calls (cudaHostAlloc): copies from / to such buffers run at
+ * full PCIe / NVLink-C2C speed and overlap the host-side planning.  Any host memory is accepted by every call; pinned
+ * buffers are only faster.  abv_pinned_alloc returns NULL on failure or without a usable CUDA device.
+ */
+void *abv_pinned_alloc(unsigned long long bytes);
+void abv_pinned_free(void *p);
+
+/*
  * Timings of the last batched call of this thread, CUDA events on the library's stream:
  *   out[0] host->device ms, out[1] kernel ms, out[2] device->host ms, out[3] cells,
  *   out[4] kernel launches, out[5] bytes host->device, out[6] bytes device->host,
