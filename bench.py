@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--targets", type=int, default=2000)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work of one cpu_baseline sample / reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-glocal", action="store_true", help="skip the secondary glocal-mode measurement of the same job")
     ap.add_argument("--merge-pairs", type=int, default=1000000, help="read pairs of the secondary overlap-merge measurement (0 = skip)")
     return ap.parse_args()
 
@@ -391,6 +392,23 @@ def cuda_arm(args, rank, world, local_rank):
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
 
+        # ---------------- the same job in the mode BASELINE.json's config names (glocal), device-resident --------
+        glocal = None
+        if world == 1 and args.mode == "global" and not args.no_glocal:
+            sh2 = ShardedBestHits(queries, targets, 0, 1, mode=MODE_NAMES["glocal"])
+            flush.zero_(); sh2.step(None); torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(2):
+                flush.zero_()
+                sh2.step(None)
+            g1.record()
+            torch.cuda.synchronize()
+            gms = g0.elapsed_time(g1) / 2
+            glocal = {"mode": "glocal", "value": total_cells / (gms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": gms, "steps": 2, "warmup": 1,
+                      "note": "same workload, glocal_align semantics (glocal_align.c:73-202); the pipeline itself scores with global_align (ambivert.py:157-199)"}
+            sh2.close()
+
     if rank == 0:
         assert (host[0].numpy() == gpu_score).all() and (host[1].numpy() == gpu_idx).all()
         value = total_cells * args.steps / (elapsed_ms * 1e-3) / 1e9
@@ -416,6 +434,8 @@ def cuda_arm(args, rank, world, local_rank):
                 "e2e": {"value": total_cells * args.steps / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "s_per_step": e2e_s / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+        if glocal:
+            line["glocal"] = glocal
         if world == 1 and args.merge_pairs > 0:
             line["merge"] = merge_measurement(args.merge_pairs)
             line["cluster"] = cluster_measurement(args.merge_pairs)

@@ -73,6 +73,36 @@ def main():
         buf = io.BytesIO(); buf.close = lambda: None
         amp.save_hash_table(buf)
         out["hash_table_pickle_sha256"] = hashlib.sha256(buf.getvalue()).hexdigest()
+        # the step after the path: call_variants on every potential variant, one by one, so that
+        # amplicons on which the reference raises (its own assert, call_variants.py:139) are recorded instead of stopping
+        from ambivert.call_variants import call_variants
+        called = []
+        errors = {}
+        for key in amp.potential_variants:
+            sample, ref = amp.aligned[key]
+            name, chromosome, position, end, strand = amp.reference[key]
+            try:
+                called.append((key, str(call_variants(sample, ref, chromosome, int(position)))))
+            except Exception as e:
+                errors[key] = type(e).__name__
+        out["n_called"] = len(called)
+        out["md5_called_variants"] = md5(str(sorted(called)))
+        out["call_variants_errors"] = {"count": len(errors), "types": sorted(set(errors.values())),
+                                       "md5_keys": md5(str(sorted(errors.items()))), "first_in_pipeline_order":
+                                       next((k for k in amp.potential_variants if k in errors), None)}
+        # consolidation over the amplicons the reference can call (the failing ones left out)
+        amp.called_variants = {k: call_variants(amp.aligned[k][0], amp.aligned[k][1], amp.reference[k][1], int(amp.reference[k][2]))
+                               for k in amp.potential_variants if k not in errors}
+        t4 = time.time(); amp.consolidate_variants(); t5 = time.time()
+        out["reference_cpu_seconds"]["consolidate"] = t5 - t4
+        out["n_consolidated"] = len(amp.consolidated_variants)
+        out["md5_consolidated"] = md5(str(sorted(amp.consolidated_variants)))
+        out["md5_filtered"] = md5(str(list(amp.get_filtered_variants())))
+        vcf_ok = io.StringIO()
+        amp.print_consolidated_vcf(outfile=vcf_ok)
+        out["vcf_of_callable_sha256"] = hashlib.sha256(vcf_ok.getvalue().encode()).hexdigest()
+        out["vcf_of_callable_lines"] = vcf_ok.getvalue().count("\n")
+        amp.called_variants, amp.consolidated_variants = {}, []
         vcf = io.StringIO()
         try:
             amp.print_consolidated_vcf(outfile=vcf)

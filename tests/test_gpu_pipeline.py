@@ -94,3 +94,36 @@ def test_wrappers_follow_reference_error_behaviour():
     assert H.needleman_wunsch("ACGT", "acgt") == ("ACGT", "acgt", 0, 0)
     a1, a2, s1, s2 = H.smith_waterman("TTTTACGTACGTAC", "ggACGTACGTACgg")
     assert (a1, a2.upper(), s1, s2) == ("ACGTACGTAC", "ACGTACGTAC", 4, 2)
+
+
+def test_read_pairs_to_vcf_bundled_data(G):
+    """the whole chain on the reference's bundled data, every stage on the device: cluster (md5 keys) -> merge -> match ->
+    align -> variant scan -> consolidation -> VCF text, against the literal VCF the reference's own test asserts
+    (tests/test_ambivert.py:532-557, stored by oracle/make_golden_variants.py) -- process_amplicon_data(threshold=50, overlap=20)"""
+    import gzip
+    import json
+    import os
+    from ambivert_b200.host import AmpliconData
+    with gzip.open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "variants.json.gz"), "rb") as f:
+        V = json.loads(f.read().decode())["bundled"]["threshold50_overlap20"]
+    amp = AmpliconData()
+    pairs = []
+    for p in G["pairs"]:
+        pairs += [(("r", p["fwd"], "I" * len(p["fwd"])), ("r", p["rev"], "I" * len(p["rev"])))] * p["count"]
+    amp.add_read_pairs(pairs)                                     # keys computed on the device
+    assert list(amp.data) == [p["key"] for p in G["pairs"]] and {k: len(v) for k, v in amp.data.items()} == V["counts"]
+    for t in G["targets"]:
+        amp.reference_sequences[tuple(t["key"])] = t["seq"]
+    amp.merge_overlaps(threshold=50, minimum_overlap=20)
+    amp.match_to_reference()
+    amp.align_to_reference()
+    assert {k: list(v) for k, v in amp.aligned.items()} == V["aligned"]
+    assert amp.potential_variants == V["potential_variants"]
+    amp.call_amplicon_variants()
+    assert str(sorted(amp.called_variants.items())) == V["str_sorted_called_variants"]
+    amp.consolidate_variants()
+    assert str(sorted(amp.consolidated_variants)) == V["str_sorted_consolidated"]
+    out = io.StringIO()
+    amp.print_consolidated_vcf(outfile=out)
+    assert out.getvalue() == V["vcf"]
+    assert "chr17\t41244435\t.\tT\tC\t.\tPASS\tDP=193;AC=122;AF=0.632;ALTAMPS=1186cf52bcce24d9e5446675e896b90c,268014b6f669772a4e97b99427563d6b;REFAMPS=c3ee13ce7e3e7973b37714187bd2019d\n" in out.getvalue()
