@@ -1322,6 +1322,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
       // lanes like the pair switches: lane t reaches row r at step r + t of the pair's own time line)
       const int NOEV = 1 << 20;
       int pend_e1 = NOEV, pend_e2 = NOEV, pend_r1 = 0, pend_r2 = 0;
+      uint32_t lm0 = NEGb, lm1 = NEGb;       // glocal: this lane's last-row maxima of the pairs of even / odd parity (both halves)
 
       auto exchange = [&](uint32_t &h_sh, uint32_t &e_sh) {
         h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
@@ -1354,8 +1355,9 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
           for (int k = 0; k < K; ++k)
             if (k <= kstar) m = p16::max2(m, S[k] + d0 + (uint32_t)k * gew);
         }
-        if (h1) atomicMax(slots + 2 * parity, b16::lo(m));
-        if (h2) atomicMax(slots + 2 * parity + 1, b16::hi(m));
+        // the lane's own maximum of this (pair, half): one event per lane, folded over the lanes at the capture
+        const uint32_t mm = (h1 ? (m & 0xffffu) : (NEGb & 0xffffu)) | (h2 ? (m & 0xffff0000u) : (NEGb & 0xffff0000u));
+        if (parity) lm1 = p16::max2(lm1, mm); else lm0 = p16::max2(lm0, mm);
       };
       // lane t is on the last row of half h of a pair at step ev_h + t of that pair's time line
       auto last_rows_at = [&](int s, int e1, int e2, int r1, int r2, int parity) {
@@ -1364,13 +1366,12 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
       };
       auto capture = [&](int half, int idx, int drift, int parity) {
         if (GL) {
-          __syncwarp();
-          const int v = slots[2 * parity + half];
-          const int sc = max(0, v);                                      // max starts at 0 (glocal_align.c:115)
+          const uint32_t v = warp_max2(parity ? lm1 : lm0);                // every lane has passed this half's last row
+          const int sc = max(0, half ? b16::hi(v) : b16::lo(v));           // max starts at 0 (glocal_align.c:115)
           if (sc > wbest || (sc == wbest && idx < widx)) { wbest = sc; widx = idx; }
           if (p.all_scores && lane == 0) p.all_scores[(long long)qi * p.n_t + idx] = sc;
-          __syncwarp();
-          if (lane == 0) slots[2 * parity + half] = INT_MIN;
+          const uint32_t keep = half ? 0x0000ffffu : 0xffff0000u;           // this half starts over for the pair after next
+          if (parity) lm1 = (lm1 & keep) | (NEGb & ~keep); else lm0 = (lm0 & keep) | (NEGb & ~keep);
         } else if (lane == tstar) {
           const uint32_t hs = mm16_pick<K>(Hp, kstar);
           const int sc = (half ? b16::hi(hs) : b16::lo(hs)) + drift;     // undo the drift: + g*(c + r) of the corner
@@ -1409,6 +1410,8 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
           }
         };
         if (GL) {
+          // undo of the drift on the previous pair's last rows, per half: + g*(c0 + r)
+          const uint32_t dpend = b16::addend(ge * (c0 + pend_r1), ge * (c0 + pend_r2));
           // the first 32 steps: lane s switches to this pair at step s
           for (int s = 0; s < MM16G_MIN_ROWS; ++s) {
             if (lane == s) tb_off = bufoff - lane;
@@ -1428,7 +1431,21 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
               hleft = h_sh; e_out = NEGb; h_out = Hp[K - 1];
             } else {
               row(s, h_sh, e_sh);
-              last_rows_at(s, pend_e1, pend_e2, pend_r1, pend_r2, par ^ 1);
+              // last rows of the PREVIOUS pair: lane t is on them at steps pend_e1 + t / pend_e2 + t, all inside these 32
+              // steps.  Handling each event in its own divergent branch costs the whole warp ~45 instructions per event
+              // (64 events per pair); instead every lane that owns only real columns folds the forced diagonal of the row
+              // it is on (glocal_align.c:172-183: what S[] holds after the row's first pass) and keeps it if the row is
+              // a last row.  The one lane with padding columns takes the masked path.
+              const bool h1 = lane == s - pend_e1, h2 = lane == s - pend_e2;
+              if (lane < tstar) {
+                uint32_t m = NEGb;
+#pragma unroll
+                for (int k = 0; k < K; ++k) m = p16::max2(m, S[k] + dpend + (uint32_t)k * gew);
+                const uint32_t mm = (h1 ? (m & 0xffffu) : (NEGb & 0xffffu)) | (h2 ? (m & 0xffff0000u) : (NEGb & 0xffff0000u));
+                if (par) lm0 = p16::max2(lm0, mm); else lm1 = p16::max2(lm1, mm);       // parity of the previous pair
+              } else if (h1 || h2) {
+                last_row(h1, h2, h1 ? pend_r1 : pend_r2, par ^ 1);
+              }
               last_rows_at(s, ev1, ev2, meta.x - 1, meta.y - 1, par);
             }
             if (s == pend_s1) capture(0, pend_i1, pend_d1, par ^ 1);
