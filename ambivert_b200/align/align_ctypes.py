@@ -16,6 +16,9 @@ _HERE = _os.path.dirname(_os.path.abspath(__file__))
 
 
 def _load():
+    override = _os.environ.get("AMBIVERT_B200_LIB")       # tuning builds of the SAME library (tools/sweep_builds.sh); no fallback
+    if override:
+        return _C.cdll.LoadLibrary(override), _os.path.basename(override)
     names = sorted(f for f in _os.listdir(_HERE) if 'align_c.' in f)
     if not names:
         raise OSError("ambivert_b200: CUDA alignment library align_c.*.so not found in %s (contents: %s); "

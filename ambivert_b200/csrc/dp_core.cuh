@@ -355,18 +355,29 @@ struct StripCfg {
 };
 
 template <int K, int KP>
-ABV_HD void mm16d_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], uint32_t (&S)[KP], uint32_t gop2) {
+ABV_HD void mm16d_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], uint32_t (&S)[KP], uint32_t gop2, uint32_t gope) {
 #pragma unroll
   for (int k = K - 1; k >= 1; --k) S[k] += Hp[k - 1];
   S[0] += hleft;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const uint32_t h = p16::max3(S[k], e, F[k]);
-    e = p16::addmax(h, gop2, e);
+    e = p16::addmax(h, gope, e);
     F[k] = p16::addmax(h, gop2, F[k]);
     Hp[k] = h;
   }
 }
+template <int K, int KP>
+ABV_HD void mm16d_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], uint32_t (&S)[KP], uint32_t gop2) {
+  mm16d_row<K, KP>(hleft, e, Hp, F, S, gop2, gop2);
+}
+
+// glocal row 0 through the common row (glocal_align.c:128-136: H[c][0] = S, F = H + go, no row gap).  The lane that
+// starts a pair sets, in drift form, H~[c][-1] := g*(1 - c) (so that the diagonal alone gives S - g*c), F~ := -inf,
+// takes E~ = -inf from the left and runs the row with the E-chain addend MM16G_NO_EGAP: h + (-32000) stays below the
+// -inf sentinel for every representable h, so no row gap is opened and E leaves the strip as -inf, while F is
+// opened normally (F~' = h + go - g).
+constexpr int MM16G_NO_EGAP = -32000;
 
 // ---------------------------------------------------------------------------------------------
 // tb16: one-to-one alignments WITH traceback, two pairs per warp in the 16-bit halves (local and global;

@@ -32,6 +32,10 @@ namespace abv {
 #define ABV_UNROLL 8
 #endif
 constexpr int kHotUnroll = ABV_UNROLL;   // steps of the steady-state loop unrolled together
+#ifndef ABV_SWITCH_UNROLL
+#define ABV_SWITCH_UNROLL 2
+#endif
+constexpr int kSwitchUnroll = ABV_SWITCH_UNROLL;   // steps of the pair-switching segments unrolled together (code size: instruction cache)
 #ifndef ABV_MINB8
 #define ABV_MINB8 3   // measured on B200: 3 CTAs (24 warps, <= 85 registers) beat 4 (32 warps, 64 registers) by 4 %; 2 and 5 are slower
 #endif
@@ -1267,6 +1271,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
   const uint32_t Hc = GL ? NEGb : b16::biased(go + ge, go + ge);
   const uint32_t Ec = GL ? NEGb : b16::biased(2 * go, 2 * go);
   const uint32_t H00 = b16::biased(2 * ge, 2 * ge);       // global: H~[-1][-1]
+  const uint32_t NOEGAP = p16::pack(MM16G_NO_EGAP, MM16G_NO_EGAP);
 
   for (int i = threadIdx.x; i < ncodes; i += blockDim.x) mext[i] = p.matrix_ext[i];
   if (threadIdx.x < 16) reinterpret_cast<uint32_t *>(smem + L.zero)[threadIdx.x] = 0u;
@@ -1300,6 +1305,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
 
     const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;
     const int c0 = lane * K;
+    const uint32_t G0 = b16::biased(ge * (1 - c0), ge * (1 - c0));      // glocal: H~[c0][-1] of a starting pair (dp_core.cuh, MM16G_NO_EGAP)
     const int n_mine = pair_hi - pair_lo;                          // this item's slice of the target pairs
     const int n_i = warp < n_mine ? (n_mine - warp + W - 1) / W : 0;
     const int pbase = pair_lo + warp;                              // this warp takes pairs pbase + i*W
@@ -1329,13 +1335,14 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
         if (lane == 0) { h_sh = Hc; e_sh = Ec; }
       };
-      auto row = [&](int s, uint32_t h_sh, uint32_t e_sh) {   // one ordinary row of this lane
+      auto row_e = [&](int s, uint32_t h_sh, uint32_t e_sh, uint32_t gope) {   // one row of this lane; gope: addend of the row-gap chain
         const int code = smem[tb_off + s];
         mm16_load_S<KP>(lut + code * P, lane, S);
         uint32_t e = e_sh;
-        mm16d_row<K, KP>(hleft, e, Hp, F, S, gop2);
+        mm16d_row<K, KP>(hleft, e, Hp, F, S, gop2, gope);
         hleft = h_sh; e_out = e; h_out = Hp[K - 1];
       };
+      auto row = [&](int s, uint32_t h_sh, uint32_t e_sh) { row_e(s, h_sh, e_sh, gop2); };   // one ordinary row
       auto body = [&](int s) {
         uint32_t h_sh, e_sh;
         exchange(h_sh, e_sh);
@@ -1412,57 +1419,68 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         if (GL) {
           // undo of the drift on the previous pair's last rows, per half: + g*(c0 + r)
           const uint32_t dpend = b16::addend(ge * (c0 + pend_r1), ge * (c0 + pend_r2));
-          // the first 32 steps: lane s switches to this pair at step s
-          for (int s = 0; s < MM16G_MIN_ROWS; ++s) {
-            if (lane == s) tb_off = bufoff - lane;
-            uint32_t h_sh, e_sh;
-            exchange(h_sh, e_sh);
-            if (lane == s) {
-              // row 0 of the new pair has no dependencies: H[c][0] = S(q[c], t[0]), F = H + go
-              // (glocal_align.c:128-136); in drift form H~ = (S - 2g) + g*(2 - c)
-              const int code = smem[tb_off + s];
-              mm16_load_S<KP>(lut + code * P, lane, S);
-              const uint32_t ri0 = b16::addend(ge * (2 - c0), ge * (2 - c0)) + b16::biased(0, 0);
-#pragma unroll
-              for (int k = 0; k < K; ++k) {
-                Hp[k] = S[k] + ri0 - (uint32_t)k * gew;
-                F[k] = Hp[k] + gopw;
-              }
-              hleft = h_sh; e_out = NEGb; h_out = Hp[K - 1];
-            } else {
-              row(s, h_sh, e_sh);
-              // last rows of the PREVIOUS pair: lane t is on them at steps pend_e1 + t / pend_e2 + t, all inside these 32
-              // steps.  Handling each event in its own divergent branch costs the whole warp ~45 instructions per event
-              // (64 events per pair); instead every lane that owns only real columns folds the forced diagonal of the row
-              // it is on (glocal_align.c:172-183: what S[] holds after the row's first pass) and keeps it if the row is
-              // a last row.  The one lane with padding columns takes the masked path.
-              const bool h1 = lane == s - pend_e1, h2 = lane == s - pend_e2;
-              if (lane < tstar) {
-                uint32_t m = NEGb;
-#pragma unroll
-                for (int k = 0; k < K; ++k) m = p16::max2(m, S[k] + dpend + (uint32_t)k * gew);
-                const uint32_t mm = (h1 ? (m & 0xffffu) : (NEGb & 0xffffu)) | (h2 ? (m & 0xffff0000u) : (NEGb & 0xffff0000u));
-                if (par) lm0 = p16::max2(lm0, mm); else lm1 = p16::max2(lm1, mm);       // parity of the previous pair
-              } else if (h1 || h2) {
-                last_row(h1, h2, h1 ? pend_r1 : pend_r2, par ^ 1);
-              }
-              last_rows_at(s, ev1, ev2, meta.x - 1, meta.y - 1, par);
+          const bool early = min(ev1, ev2) < 2 * MM16G_MIN_ROWS;     // a short target: its last rows start inside the switching steps
+          // Segments end at the warp-uniform capture steps, so the loops carry no capture tests and unroll (as in global).
+          // Steps 0..31: lane s switches to this pair at step s and computes its row 0 through the common row
+          // (dp_core.cuh, MM16G_NO_EGAP); the lanes still on the previous pair fold its last rows.
+          int s = 0;
+          const int s_chk = min(rows, max(MM16G_MIN_ROWS, min(ev1, ev2)));      // from here on lanes reach this pair's last rows
+          while (s < rows) {
+            const bool switching = s < MM16G_MIN_ROWS;
+            int stop = switching ? MM16G_MIN_ROWS : (s < s_chk ? s_chk : rows);
+            if (switching) {
+              if (pend_s1 >= s && pend_s1 < stop) stop = pend_s1 + 1;
+              if (pend_s2 >= s && pend_s2 < stop) stop = pend_s2 + 1;
             }
-            if (s == pend_s1) capture(0, pend_i1, pend_d1, par ^ 1);
-            if (s == pend_s2) capture(1, pend_i2, pend_d2, par ^ 1);
-            if (s == cs1) capture(0, meta.z, dr1, par);
-            if (s == cs2) capture(1, meta.w, dr2, par);
-          }
-          issue_next_copy();
-          int s = MM16G_MIN_ROWS;
-          const int s_chk = min(rows, max(MM16G_MIN_ROWS, min(ev1, ev2)));
+            if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
+            if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
+            if (switching) {
+#pragma unroll 1
+              for (; s < stop; ++s) {
+                const bool sw = lane == s;
+                if (sw) {
+#pragma unroll
+                  for (int k = 0; k < K; ++k) { Hp[k] = G0 - (uint32_t)k * gew; F[k] = NEGb; }
+                  hleft = G0 + gew;
+                  tb_off = bufoff - lane;
+                }
+                uint32_t h_sh, e_sh;
+                exchange(h_sh, e_sh);
+                if (sw) e_sh = NEGb;
+                row_e(s, h_sh, e_sh, sw ? NOEGAP : gop2);
+                // last rows of the PREVIOUS pair: lane t is on them at steps pend_e1 + t / pend_e2 + t, all inside these 32
+                // steps.  Every lane that owns only real columns folds the forced diagonal of the row it is on
+                // (glocal_align.c:172-183: what S[] holds after the row's first pass) and keeps it if the row is a last
+                // row; the one lane with padding columns takes the masked path.
+                const bool h1 = lane == s - pend_e1, h2 = lane == s - pend_e2;
+                if (lane < tstar) {
+                  uint32_t m = NEGb;
+#pragma unroll
+                  for (int k = 0; k < K; ++k) m = p16::max2(m, S[k] + dpend + (uint32_t)k * gew);
+                  const uint32_t mm = (h1 ? (m & 0xffffu) : (NEGb & 0xffffu)) | (h2 ? (m & 0xffff0000u) : (NEGb & 0xffff0000u));
+                  if (par) lm0 = p16::max2(lm0, mm); else lm1 = p16::max2(lm1, mm);       // parity of the previous pair
+                } else if (h1 || h2) {
+                  last_row(h1, h2, h1 ? pend_r1 : pend_r2, par ^ 1);
+                }
+                if (early) last_rows_at(s, ev1, ev2, meta.x - 1, meta.y - 1, par);
+              }
+            } else if (s < s_chk) {
 #pragma unroll kHotUnroll
-          for (; s < s_chk; ++s) body(s);                      // no lane is on a last row yet
-          for (; s < rows; ++s) {
-            body(s);
-            last_rows_at(s, ev1, ev2, meta.x - 1, meta.y - 1, par);
-            if (s == cs1) capture(0, meta.z, dr1, par);
-            if (s == cs2) capture(1, meta.w, dr2, par);
+              for (; s < stop; ++s) body(s);                    // no lane is on a last row yet
+            } else {
+              for (; s < stop; ++s) {
+                body(s);
+                last_rows_at(s, ev1, ev2, meta.x - 1, meta.y - 1, par);
+              }
+            }
+            const int done = s - 1;
+            if (done < MM16G_MIN_ROWS) {
+              if (done == pend_s1) capture(0, pend_i1, pend_d1, par ^ 1);
+              if (done == pend_s2) capture(1, pend_i2, pend_d2, par ^ 1);
+            }
+            if (done == cs1) capture(0, meta.z, dr1, par);
+            if (done == cs2) capture(1, meta.w, dr2, par);
+            if (s == MM16G_MIN_ROWS) issue_next_copy();
           }
         } else {
           // The pair's steps run in segments that end where a corner cell has to be captured (a warp-uniform
@@ -1479,7 +1497,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
             if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
             if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
             if (switching) {
-#pragma unroll kHotUnroll
+#pragma unroll kSwitchUnroll
               for (; s < stop; ++s) {
                 if (lane == s) {
 #pragma unroll

@@ -317,15 +317,17 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
       const int code = sm.at(tb_off[t] + s);
       if (code >= ncodes) throw 1;
       load_S<KP>(&lut[(size_t)code * P], t, S[t]);
-      if (GL && t == sw) {
+      uint32_t gope = gop2;
+      if (GL && t == sw) {      // row 0 of a starting pair through the common row (dp_core.cuh, MM16G_NO_EGAP), as the kernel does
         const int c0 = t * K;
-        const uint32_t ri0 = b16::addend(ge * (2 - c0), ge * (2 - c0)) + b16::biased(0, 0);
-        for (int k = 0; k < K; ++k) { Hp[t][k] = S[t][k] + ri0 - (uint32_t)k * gew; F[t][k] = Hp[t][k] + gopw; }
-        hleft[t] = h_sh[t]; e_out[t] = NEGb; h_out[t] = Hp[t][K - 1];
-        continue;
+        const uint32_t G0 = b16::biased(ge * (1 - c0), ge * (1 - c0));
+        for (int k = 0; k < K; ++k) { Hp[t][k] = G0 - (uint32_t)k * gew; F[t][k] = NEGb; }
+        hleft[t] = G0 + gew;
+        e_sh[t] = NEGb;
+        gope = p16::pack(MM16G_NO_EGAP, MM16G_NO_EGAP);
       }
       uint32_t e = e_sh[t];
-      mm16d_row<K, KP>(hleft[t], e, Hp[t], F[t], S[t], gop2);
+      mm16d_row<K, KP>(hleft[t], e, Hp[t], F[t], S[t], gop2, gope);
       hleft[t] = h_sh[t]; e_out[t] = e; h_out[t] = Hp[t][K - 1];
       if (GL) {
         if (with_pending && t == s - pend_e1) last_row(t, 0, pend_r1, par ^ 1);
