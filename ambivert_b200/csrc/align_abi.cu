@@ -271,8 +271,8 @@ int wf32_grid(long long n_pairs, size_t scratch_per_warp) {
 }
 
 // ---- mm16 launcher ----------------------------------------------------------------------------
-const int MM16_KS[] = {2, 4, 6, 7, 8, 10, 12, 16};   // 7: streaming global kernel only
-constexpr int MM16_NK = 8;
+const int MM16_KS[] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16};   // odd K: streaming kernel (global, glocal) only
+constexpr int MM16_NK = 11;
 
 // Work items per launch: a query is cut into `split` slices of the target pairs when there are too few
 // queries to keep the tail of the persistent grid short (each slice keeps >= 4 pairs per warp).
@@ -324,10 +324,13 @@ template <int MODE>
 int mm16g_launch_mode(int K, cudaStream_t st, const Mm16Params &p, int &launched) {
   switch (K) {
     case 2: return mm16g_launch_one<MODE, 2>(st, p, launched);
+    case 3: return mm16g_launch_one<MODE, 3>(st, p, launched);
     case 4: return mm16g_launch_one<MODE, 4>(st, p, launched);
+    case 5: return mm16g_launch_one<MODE, 5>(st, p, launched);
     case 6: return mm16g_launch_one<MODE, 6>(st, p, launched);
     case 7: return mm16g_launch_one<MODE, 7>(st, p, launched);
     case 8: return mm16g_launch_one<MODE, 8>(st, p, launched);
+    case 9: return mm16g_launch_one<MODE, 9>(st, p, launched);
     case 10: return mm16g_launch_one<MODE, 10>(st, p, launched);
     case 12: return mm16g_launch_one<MODE, 12>(st, p, launched);
     case 16: return mm16g_launch_one<MODE, 16>(st, p, launched);

@@ -1272,6 +1272,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
   const uint32_t Ec = GL ? NEGb : b16::biased(2 * go, 2 * go);
   const uint32_t H00 = b16::biased(2 * ge, 2 * ge);       // global: H~[-1][-1]
   const uint32_t NOEGAP = p16::pack(MM16G_NO_EGAP, MM16G_NO_EGAP);
+  const uint32_t negg = p16::pack(-ge, -ge);             // glocal: step of the last-row maximum chain
 
   for (int i = threadIdx.x; i < ncodes; i += blockDim.x) mext[i] = p.matrix_ext[i];
   if (threadIdx.x < 16) reinterpret_cast<uint32_t *>(smem + L.zero)[threadIdx.x] = 0u;
@@ -1352,15 +1353,18 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
       // is what S[] holds after the row's first pass; every real query column competes for the end
       auto last_row = [&](bool h1, bool h2, int r, int parity) {
         if (lane > tstar) return;                                           // only padding columns
+        // max_k (S[k] + g*k) as the chain n_k = max(n_{k-1} - g, S[k]) (one add-max per column), then + g*k_last
         uint32_t m = NEGb;
         const uint32_t d0 = b16::addend(ge * (c0 + r), ge * (c0 + r));          // undo the drift: + g*(c + r)
         if (lane < tstar) {
 #pragma unroll
-          for (int k = 0; k < K; ++k) m = p16::max2(m, S[k] + d0 + (uint32_t)k * gew);
+          for (int k = 0; k < K; ++k) m = p16::addmax(m, negg, S[k]);
+          m += d0 + (uint32_t)(K - 1) * gew;
         } else {
 #pragma unroll
           for (int k = 0; k < K; ++k)
-            if (k <= kstar) m = p16::max2(m, S[k] + d0 + (uint32_t)k * gew);
+            if (k <= kstar) m = p16::addmax(m, negg, S[k]);
+          m += d0 + (uint32_t)kstar * gew;
         }
         // the lane's own maximum of this (pair, half): one event per lane, folded over the lanes at the capture
         const uint32_t mm = (h1 ? (m & 0xffffu) : (NEGb & 0xffffu)) | (h2 ? (m & 0xffff0000u) : (NEGb & 0xffff0000u));
@@ -1418,7 +1422,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         };
         if (GL) {
           // undo of the drift on the previous pair's last rows, per half: + g*(c0 + r)
-          const uint32_t dpend = b16::addend(ge * (c0 + pend_r1), ge * (c0 + pend_r2));
+          const uint32_t dpend = b16::addend(ge * (c0 + K - 1 + pend_r1), ge * (c0 + K - 1 + pend_r2));
           const bool early = min(ev1, ev2) < 2 * MM16G_MIN_ROWS;     // a short target: its last rows start inside the switching steps
           // Segments end at the warp-uniform capture steps, so the loops carry no capture tests and unroll (as in global).
           // Steps 0..31: lane s switches to this pair at step s and computes its row 0 through the common row
@@ -1456,7 +1460,8 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
                 if (lane < tstar) {
                   uint32_t m = NEGb;
 #pragma unroll
-                  for (int k = 0; k < K; ++k) m = p16::max2(m, S[k] + dpend + (uint32_t)k * gew);
+                  for (int k = 0; k < K; ++k) m = p16::addmax(m, negg, S[k]);      // n_k = max(n_{k-1} - g, S[k])
+                  m += dpend;                                                         // + g*(c0 + K-1 + r) per half
                   const uint32_t mm = (h1 ? (m & 0xffffu) : (NEGb & 0xffffu)) | (h2 ? (m & 0xffff0000u) : (NEGb & 0xffff0000u));
                   if (par) lm0 = p16::max2(lm0, mm); else lm1 = p16::max2(lm1, mm);       // parity of the previous pair
                 } else if (h1 || h2) {
