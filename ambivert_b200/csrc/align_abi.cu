@@ -50,6 +50,7 @@ struct Options {
   int mm16_blocks_per_sm = 0;   // 0 = what the occupancy query returns
   int split = 0;                // 0 = automatic; otherwise slices of the target pairs per query
   int global_v1 = 0;            // 1 = use the first-generation packed kernel for global mode too
+  int no_levels = 0;            // 1 = streaming global kernel resets every pair explicitly (no level staircase, mm16g_levels)
   int tb16 = 1;                 // 0 = one-to-one jobs always take the 32-bit kernel
 };
 
@@ -377,7 +378,7 @@ struct abv_job {
   // device data
   DevMem q_codes, q_off, t_codes, t_off, map, matrix, matrix_ext, tp_codes, tp_meta, lists, counters;
   DevMem best_score, best_idx, all_scores, chunk_scores, border, best_key;
-  int tp_stride = 0, n_pairs = 0, a1 = 0, max_lt = 0, max_lq = 0;
+  int tp_stride = 0, n_pairs = 0, a1 = 0, max_lt = 0, max_lq = 0, maxabs = 1, maxpos = 0;
   struct Bucket { int K, n, offset; double cells; cudaEvent_t e0, e1; bool streaming; };
   std::vector<Bucket> buckets;     // packed-kernel launches (one per K class), lists at `offset`
   ~abv_job() { for (auto &b : buckets) { if (b.e0) cudaEventDestroy(b.e0); if (b.e1) cudaEventDestroy(b.e1); } }
@@ -443,10 +444,14 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   int maxabs = std::max(std::abs(sc.go), std::abs(sc.ge));
   for (int i = 0; i < sc.alpha * sc.alpha; ++i) maxabs = std::max(maxabs, std::abs(sc.matrix[i]));
   maxabs = std::max(maxabs, 1);
+  int maxpos = 0;
+  for (int i = 0; i < sc.alpha * sc.alpha; ++i) maxpos = std::max(maxpos, sc.matrix[i]);
+  J.maxabs = maxabs; J.maxpos = maxpos;
   const int a1 = sc.alpha + 1;
   bool packed_ok = g.opt.path != ABV_PATH_WF32 && n_t > 0 && a1 * a1 <= 64 &&
                    (mode == ABV_GLOBAL || mode == ABV_LOCAL || mode == ABV_GLOCAL);
-  const int tp_stride = std::max(32, (max_lt + 15) & ~15);   // >= 32: the streaming kernel sweeps at least 32 rows per pair
+  // >= 32: the streaming kernel sweeps at least 32 rows per pair; > max_lt: one pad row after every pair (its separator row, mm16g_levels)
+  const int tp_stride = std::max(32, (max_lt + 1 + 15) & ~15);
   std::vector<std::vector<int>> lists(MM16_NK);
   std::vector<int> wf32_list;
   for (int i = 0; i < n_q; ++i) {
@@ -583,6 +588,11 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
     p.all_scores = J.want_all_scores ? J.all_scores.as<int>() : nullptr; p.n_t = J.n_t;
     p.q_counter = reinterpret_cast<unsigned int *>(J.counters.as<unsigned long long>() + ci++);
     p.best_key = J.best_key.as<unsigned long long>(); p.split = 1;
+    {
+      const Mm16gLevels lv = (b.streaming && J.mode == ABV_GLOBAL && !g.opt.no_levels)
+                                 ? mm16g_levels(32 * b.K, J.tp_stride, J.go, J.ge, J.maxabs, J.maxpos) : Mm16gLevels{1, 0, 0};
+      p.lv_n = lv.n; p.lv0 = lv.lvl0; p.lv_step = lv.step;
+    }
     CU(cudaEventRecord(b.e0, st));
     if ((rc = mm16_launch(J.mode, b.K, b.streaming, st, p, launched))) return rc;
     CU(cudaEventRecord(b.e1, st));
@@ -771,6 +781,7 @@ int abv_set_option(const char *key, int value) {
   if (!strcmp(key, "split")) { g.opt.split = std::max(0, std::min(value, 64)); return ABV_OK; }
   if (!strcmp(key, "tb16")) { g.opt.tb16 = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "global_v1")) { g.opt.global_v1 = value ? 1 : 0; return ABV_OK; }
+  if (!strcmp(key, "no_levels")) { g.opt.no_levels = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "mm16_blocks_per_sm")) { g.opt.mm16_blocks_per_sm = std::max(0, std::min(value, 8)); return ABV_OK; }
   return fail(ABV_ERR_ARGS, "unknown option %s", key);
 }

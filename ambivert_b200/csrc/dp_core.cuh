@@ -569,4 +569,33 @@ ABV_HD int mm16g_rows(int l1, int l2) {
   return m < MM16G_MIN_ROWS ? MM16G_MIN_ROWS : m;
 }
 
+// Level plan of the streaming GLOBAL kernel: "reset by injection".
+// A lane that starts a pair needs H~[c][-1] = Hc and F~[c][0] = Ec = Hc + (go - g) in all of its K columns
+// (global_align.c:136-148 in drift form).  Writing 2K registers under a one-lane branch in each of the 32
+// switching steps costs a third of such a step.  Instead, a pair that is FOLLOWED by an "injected" pair sweeps one
+// extra row (the separator, a pad row at index `rows` of its buffer) on which lane 0 feeds E~ = C from the left,
+// with C above everything the warp holds: the common row then leaves h = C in every column, E~ = C for the next
+// lane, and F~ = max(F~, C + go - g) = C + go - g.  That IS the boundary state of a pair whose values are stored
+// `level` higher, level' + go + g = C.  So pairs climb a staircase of levels and only every n-th pair is reset
+// explicitly (back to the lowest level); the corner capture subtracts the pair's level.
+//   W: |true drifted value| bound of a pair (the host's exactness bound, align_abi.cu packed_exact_streaming)
+//   U: upper bound of every stored value above its level: d diagonal steps add at most d*(maxpos + 2|g|) and
+//      gap steps add nothing in drift form; d <= min(P, rows) + 1, plus the row's own diagonal term
+struct Mm16gLevels { int n, lvl0, step; };
+ABV_HD Mm16gLevels mm16g_levels(int P, int max_rows, int go, int ge, int maxabs, int maxpos) {
+  Mm16gLevels L{1, 0, 0};
+  const int age = ge < 0 ? -ge : ge;
+  const long long W = (long long)(P + max_rows + 12) * (maxabs + age);
+  if (W > 16000 || go > ge) return L;                      // not the 16-bit streaming kernel, or go - g > 0: E~ would grow along the separator
+  const int d = (P < max_rows + 1 ? P : max_rows + 1) + 3;
+  const long long U = (long long)d * (maxpos + 2 * age);
+  const long long step = U + (ge - go) + (-go - ge) + 4;   // C >= level + U + |go - g|,  level' = C - (go + g)
+  const long long lvl0 = W - 16000;
+  if (lvl0 + U > 16000) return L;
+  const long long n = 1 + (16000 - U - lvl0) / step;
+  if (n < 2) return L;
+  L.n = (int)(n > 1024 ? 1024 : n); L.lvl0 = (int)lvl0; L.step = (int)step;
+  return L;
+}
+
 }  // namespace abv

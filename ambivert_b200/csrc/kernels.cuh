@@ -953,6 +953,7 @@ struct Mm16Params {
   unsigned int *q_counter;
   unsigned long long *best_key;               // per query: packed (score, target) of the best hit so far, see best_key_pack
   int split;                                  // work item = (query, one of `split` slices of the target pairs)
+  int lv_n, lv0, lv_step;                     // streaming global kernel: level plan (dp_core.cuh, mm16g_levels); lv_n <= 1: every pair is reset explicitly
 };
 
 // Per-query best hits are combined across work items with one 64-bit atomicMax: higher score wins, then
@@ -1268,9 +1269,11 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
   const uint32_t NEGb = b16::biased(p16::NEG16, p16::NEG16);
   // values handed to column 0 by the virtual column -1 (drift-normalised, see mm16d_row):
   //   global: H~ = go + g, E~ = 2go (global_align.c:136-140); glocal: minus infinity (glocal_align.c:119-123)
-  const uint32_t Hc = GL ? NEGb : b16::biased(go + ge, go + ge);
-  const uint32_t Ec = GL ? NEGb : b16::biased(2 * go, 2 * go);
-  const uint32_t H00 = b16::biased(2 * ge, 2 * ge);       // global: H~[-1][-1]
+  // (global: the constants of level 0; a pair on level v holds every value v higher, see mm16g_levels)
+  const uint32_t Hc0 = GL ? NEGb : b16::biased(go + ge, go + ge);
+  const uint32_t Ec0 = GL ? NEGb : b16::biased(2 * go, 2 * go);
+  const uint32_t H000 = b16::biased(2 * ge, 2 * ge);      // global: H~[-1][-1]
+  const int lv_n = GL ? 1 : max(p.lv_n, 1);
   const uint32_t NOEGAP = p16::pack(MM16G_NO_EGAP, MM16G_NO_EGAP);
   const uint32_t negg = p16::pack(-ge, -ge);             // glocal: step of the last-row maximum chain
 
@@ -1331,6 +1334,8 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
       int pend_e1 = NOEV, pend_e2 = NOEV, pend_r1 = 0, pend_r2 = 0;
       uint32_t lm0 = NEGb, lm1 = NEGb;       // glocal: this lane's last-row maxima of the pairs of even / odd parity (both halves)
 
+      uint32_t Hc = Hc0, Ec = Ec0, H00 = H000;       // boundary constants of the pair lane 0 is on (its level added)
+      int lv_i = 0;                                  // position of the current pair on the staircase of levels
       auto exchange = [&](uint32_t &h_sh, uint32_t &e_sh) {
         h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
         e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
@@ -1411,7 +1416,16 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         const int ev1 = (GL && real) ? meta.x - 1 : NOEV;
         const int ev2 = (GL && real && meta.w >= 0) ? meta.y - 1 : NOEV;
         tb_off += prev_rows;
-        const int dr1 = ge * (lq - 1 + meta.x - 1), dr2 = ge * (lq - 1 + meta.y - 1);
+        // global: this pair's level; pair 0 of the item, every lv_n-th pair and the draining dummy pair are reset explicitly
+        lv_i = (i == 0 || !real || lv_i + 1 >= lv_n) ? 0 : lv_i + 1;
+        const bool inj = !GL && lv_i != 0;
+        const bool inj_next = !GL && i + 1 < n_i && lv_i + 1 < lv_n;
+        const int lvl = GL ? 0 : p.lv0 + lv_i * p.lv_step;
+        if (!GL) {
+          const uint32_t lw = b16::addend(lvl, lvl);
+          Hc = Hc0 + lw; Ec = Ec0 + lw; H00 = H000 + lw;
+        }
+        const int dr1 = ge * (lq - 1 + meta.x - 1) - lvl, dr2 = ge * (lq - 1 + meta.y - 1) - lvl;   // undo drift and level at the corner
         const int par = i & 1;
         auto issue_next_copy = [&]() {       // every lane has left pair i-1: its buffer can take pair i+2
           __syncwarp();
@@ -1490,7 +1504,17 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         } else {
           // The pair's steps run in segments that end where a corner cell has to be captured (a warp-uniform
           // step), so that the loops themselves carry no capture tests and unroll; in the first 32 steps lane
-          // s switches to this pair at step s (state reset to the global boundary, global_align.c:136-148).
+          // s switches to this pair at step s: by an explicit reset of its state to the global boundary
+          // (global_align.c:136-148), or, on an injected pair, by moving its row pointer only: the separator row
+          // it has just swept left the boundary state of this pair's level in its registers (mm16g_levels).
+          auto captures = [&](int done) {
+            if (done < MM16G_MIN_ROWS) {
+              if (done == pend_s1) capture(0, pend_i1, pend_d1, par ^ 1);
+              if (done == pend_s2) capture(1, pend_i2, pend_d2, par ^ 1);
+            }
+            if (done == cs1) capture(0, meta.z, dr1, par);
+            if (done == cs2) capture(1, meta.w, dr2, par);
+          };
           int s = 0;
           while (s < rows) {
             const bool switching = s < MM16G_MIN_ROWS;
@@ -1501,7 +1525,13 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
             }
             if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
             if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
-            if (switching) {
+            if (switching && inj) {
+#pragma unroll kSwitchUnroll
+              for (; s < stop; ++s) {
+                if (lane == s) tb_off = bufoff - lane;
+                body(s);
+              }
+            } else if (switching) {
 #pragma unroll kSwitchUnroll
               for (; s < stop; ++s) {
                 if (lane == s) {
@@ -1516,14 +1546,19 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
 #pragma unroll kHotUnroll
               for (; s < stop; ++s) body(s);
             }
-            const int done = s - 1;
-            if (done < MM16G_MIN_ROWS) {
-              if (done == pend_s1) capture(0, pend_i1, pend_d1, par ^ 1);
-              if (done == pend_s2) capture(1, pend_i2, pend_d2, par ^ 1);
-            }
-            if (done == cs1) capture(0, meta.z, dr1, par);
-            if (done == cs2) capture(1, meta.w, dr2, par);
+            captures(s - 1);
             if (s == MM16G_MIN_ROWS) issue_next_copy();
+          }
+          if (inj_next) {
+            // the separator row (the pad row after the pair's last row): lane 0 takes E~ = Hc of the next level from the
+            // left, and as its diagonal for the next pair's row 0 that level's H~[-1][-1]
+            const uint32_t up = b16::addend(p.lv_step, p.lv_step);
+            uint32_t h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
+            uint32_t e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+            if (lane == 0) { h_sh = H00 + up; e_sh = Hc + up; }
+            row(s, h_sh, e_sh);
+            captures(s);
+            rows += 1;
           }
         }
         pend_s1 = cs1 >= rows ? cs1 - rows : -1; pend_i1 = meta.z; pend_d1 = dr1;

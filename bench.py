@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work of one cpu_baseline sample / reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-glocal", action="store_true", help="skip the secondary glocal-mode measurement of the same job")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="library tuning option (abv_set_option), e.g. no_levels=1")
     ap.add_argument("--merge-pairs", type=int, default=1000000, help="read pairs of the secondary overlap-merge measurement (0 = skip)")
     return ap.parse_args()
 
@@ -303,6 +304,8 @@ def cuda_arm(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     B.set_device(local_rank)
+    for kv in args.opt:
+        B.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)

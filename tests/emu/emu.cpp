@@ -238,6 +238,9 @@ int emu_mm16(int mode, int K, const unsigned char *q, int lq, const unsigned cha
 }
 }
 
+static int g_level_cap = 1 << 20;   // test hook: shorter level staircases, so that few pairs already wrap around
+extern "C" void emu_set_level_cap(int cap) { g_level_cap = cap < 1 ? 1 : cap; }
+
 // ---- the streaming kernel (mm16g_kernel<GLOBAL|GLOCAL>): ONE warp sweeping a list of target pairs ----
 // Mirrors the control flow of the kernel: three row buffers, 32 switch steps per pair, pending corner
 // captures, the zero-symbol prefix before the first pair and the dummy pair that drains the pipeline;
@@ -263,7 +266,7 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
   }
   int max_lt = 1;
   for (int i = 0; i < n_pairs; ++i) max_lt = std::max(max_lt, std::max(l1s[i], l2s[i]));
-  const int stride = std::max(32, (max_lt + 15) & ~15);
+  const int stride = std::max(32, (max_lt + 1 + 15) & ~15);
   std::vector<unsigned char> sm(64 + 3 * stride, 0);
   const int zero = 0, tbuf0 = 64;
   auto fill = [&](int buf, int pi) {
@@ -274,8 +277,14 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
   };
   const uint32_t gop2 = p16::pack(go - ge, go - ge), gopw = b16::addend(go - ge, go - ge), gew = b16::addend(ge, ge);
   const uint32_t NEGb = b16::biased(p16::NEG16, p16::NEG16);
-  const uint32_t Hc = GL ? NEGb : b16::biased(go + ge, go + ge), Ec = GL ? NEGb : b16::biased(2 * go, 2 * go);
-  const uint32_t H00 = b16::biased(2 * ge, 2 * ge);
+  const uint32_t Hc0 = GL ? NEGb : b16::biased(go + ge, go + ge), Ec0 = GL ? NEGb : b16::biased(2 * go, 2 * go);
+  const uint32_t H000 = b16::biased(2 * ge, 2 * ge);
+  uint32_t Hc = Hc0, Ec = Ec0, H00 = H000;       // boundary constants of the current pair's level (global, mm16g_levels)
+  int maxabs = std::max(std::abs(go), std::abs(ge)), maxpos = 0;
+  for (int x = 0; x < alpha * alpha; ++x) { maxabs = std::max(maxabs, std::abs(M[x])); maxpos = std::max(maxpos, M[x]); }
+  Mm16gLevels lv = GL ? Mm16gLevels{1, 0, 0} : mm16g_levels(P, stride, go, ge, std::max(maxabs, 1), maxpos);
+  lv.n = std::min(lv.n, g_level_cap);
+  bool explicit_reset = true, inject = false;    // how lanes enter the current pair; lane 0 on a separator row
   const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;
   uint32_t Hp[32][K], F[32][K], S[32][KP], hleft[32], h_out[32], e_out[32];
   int tb_off[32];
@@ -305,7 +314,7 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
     if (sw >= 0) {
       const int t = sw;
       tb_off[t] = bufoff - t;
-      if (!GL) {
+      if (!GL && explicit_reset) {
         for (int k = 0; k < K; ++k) { Hp[t][k] = Hc; F[t][k] = Ec; }
         hleft[t] = t ? Hc : H00;
       }
@@ -313,6 +322,7 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
     uint32_t h_sh[32], e_sh[32];
     for (int t = 0; t < 32; ++t) { h_sh[t] = t ? h_out[t - 1] : h_out[0]; e_sh[t] = t ? e_out[t - 1] : e_out[0]; }
     h_sh[0] = Hc; e_sh[0] = Ec;
+    if (inject) { const uint32_t up = b16::addend(lv.step, lv.step); h_sh[0] = H00 + up; e_sh[0] = Hc + up; }
     for (int t = 0; t < 32; ++t) {
       const int code = sm.at(tb_off[t] + s);
       if (code >= ncodes) throw 1;
@@ -337,7 +347,8 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
       }
     }
   };
-  auto capture = [&](int half, int idx, int par) {
+  int lvl = 0, pend_lvl = 0, lv_i = 0;
+  auto capture = [&](int half, int idx, int par, int level) {
     if (GL) {
       const int v = slots[2 * par + half];
       (half ? sc2_out : sc1_out)[idx] = std::max(0, v);
@@ -345,7 +356,7 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
     } else {
       const uint32_t hs = Hp[tstar][kstar];
       const int drift = ge * (lq - 1 + (half ? l2s[idx] : l1s[idx]) - 1);
-      (half ? sc2_out : sc1_out)[idx] = (half ? b16::hi(hs) : b16::lo(hs)) + drift;
+      (half ? sc2_out : sc1_out)[idx] = (half ? b16::hi(hs) : b16::lo(hs)) + drift - level;
     }
   };
   for (int i = 0; i <= n_i; ++i) {
@@ -356,12 +367,18 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
     const int ev1 = (GL && real) ? l1 - 1 : NOEV, ev2 = (GL && real && has2) ? l2 - 1 : NOEV;
     for (int t = 0; t < 32; ++t) tb_off[t] += prev_rows;
     const int par = i & 1;
+    lv_i = (i == 0 || !real || lv_i + 1 >= lv.n) ? 0 : lv_i + 1;
+    explicit_reset = lv_i == 0;
+    const bool inj_next = !GL && i + 1 < n_i && lv_i + 1 < lv.n;
+    pend_lvl = lvl;
+    lvl = GL ? 0 : lv.lvl0 + lv_i * lv.step;
+    if (!GL) { const uint32_t lw = b16::addend(lvl, lvl); Hc = Hc0 + lw; Ec = Ec0 + lw; H00 = H000 + lw; }
     for (int s = 0; s < MM16G_MIN_ROWS; ++s) {
       step(s, s, bufoff, ev1, l1 - 1, ev2, l2 - 1, true, par);
-      if (s == pend_s1) capture(0, pend_i1, par ^ 1);
-      if (s == pend_s2) capture(1, pend_i2, par ^ 1);
-      if (s == cs1) capture(0, i, par);
-      if (s == cs2) capture(1, i, par);
+      if (s == pend_s1) capture(0, pend_i1, par ^ 1, pend_lvl);
+      if (s == pend_s2) capture(1, pend_i2, par ^ 1, pend_lvl);
+      if (s == cs1) capture(0, i, par, lvl);
+      if (s == cs2) capture(1, i, par, lvl);
     }
     if (i + 2 < n_i) fill((i + 2) % 3, i + 2);
     int s = MM16G_MIN_ROWS;
@@ -370,8 +387,8 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
       for (; s < s_chk; ++s) step(s, -1, 0, NOEV, 0, NOEV, 0, false, par);
       for (; s < rows; ++s) {
         step(s, -1, 0, ev1, l1 - 1, ev2, l2 - 1, false, par);
-        if (s == cs1) capture(0, i, par);
-        if (s == cs2) capture(1, i, par);
+        if (s == cs1) capture(0, i, par, lvl);
+        if (s == cs2) capture(1, i, par, lvl);
       }
     } else {
       while (s < rows) {
@@ -379,8 +396,16 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
         if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
         if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
         for (; s < stop; ++s) step(s, -1, 0, NOEV, 0, NOEV, 0, false, par);
-        if (s - 1 == cs1) capture(0, i, par);
-        if (s - 1 == cs2) capture(1, i, par);
+        if (s - 1 == cs1) capture(0, i, par, lvl);
+        if (s - 1 == cs2) capture(1, i, par, lvl);
+      }
+      if (inj_next) {      // the separator row of lane 0: the next pair's level is injected from the left
+        inject = true;
+        step(s, -1, 0, NOEV, 0, NOEV, 0, false, par);
+        inject = false;
+        if (s == cs1) capture(0, i, par, lvl);
+        if (s == cs2) capture(1, i, par, lvl);
+        rows += 1;
       }
     }
     pend_s1 = cs1 >= rows ? cs1 - rows : -1; pend_i1 = i;
@@ -396,10 +421,13 @@ static int emu_mm16g_k(int K, const unsigned char *q, int lq, int n_pairs, const
                        const unsigned char *const *t2s, const int *l2s, int alpha, const int *M, int go, int ge, int *sc1, int *sc2) {
   switch (K) {
     case 2: emu_mm16g_t<GL, 2>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 3: emu_mm16g_t<GL, 3>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
     case 4: emu_mm16g_t<GL, 4>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 5: emu_mm16g_t<GL, 5>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
     case 6: emu_mm16g_t<GL, 6>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
     case 7: emu_mm16g_t<GL, 7>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
     case 8: emu_mm16g_t<GL, 8>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 9: emu_mm16g_t<GL, 9>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
     case 10: emu_mm16g_t<GL, 10>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
     case 12: emu_mm16g_t<GL, 12>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
     case 16: emu_mm16g_t<GL, 16>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;

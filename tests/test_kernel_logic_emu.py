@@ -157,10 +157,13 @@ def test_streaming_logic_vs_oracle(emu, oracle_port, mode):
     chk = oracle_port
     lmin = 2 if mode == O.GLOCAL else 1
     for it in range(150):
-        K = rng.choice(KS + [7, 7])
+        # global: pairs climb a staircase of levels and every n-th is reset explicitly (dp_core.cuh, mm16g_levels);
+        # short staircases make a handful of pairs wrap around, 1 = every pair reset explicitly
+        emu.emu_set_level_cap(C.c_int(rng.choice([1, 2, 3, 5, 1 << 20])))
+        K = rng.choice(KS + [7, 7, 3, 5, 9])
         lq = rng.randint(max(1, 32 * K - 70), 32 * K) if rng.random() < 0.7 else rng.randint(1, 32 * K)
         q = bytes(rng.choice([0, 1, 2, 3, 0, 1, 2, 3, 4]) for _ in range(lq))
-        n_pairs = rng.choice([1, 2, 3, 4, 7])
+        n_pairs = rng.choice([1, 2, 3, 4, 7, 12])
         lens = sorted([rng.choice([lmin, 2, 5, 31, 32, 33, rng.randint(lmin, 300), rng.randint(150, 300)]) for _ in range(2 * n_pairs)], reverse=True)
         if rng.random() < 0.3:
             lens[1] = lens[0]                                # equal lengths: both halves end on the same row
