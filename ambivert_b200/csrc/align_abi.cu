@@ -305,7 +305,7 @@ int mm16_launch_one(int grid_cap, cudaStream_t st, const Mm16Params &p, int &lau
 
 template <int MODE, int K>
 int mm16g_launch_one(cudaStream_t st, const Mm16Params &p, int &launched) {
-  const Mm16gSmem L = mm16g_smem_layout(K, p.a1, p.tp_stride);
+  const Mm16gSmem L = mm16g_smem_layout(K, p.a1, p.tp_stride, mm16g_defer(MODE == GLOCAL, K));
   auto kern = mm16g_kernel<MODE, K>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   int per_sm = 0;
@@ -397,8 +397,8 @@ bool packed_exact(int mode, int P, int max_lt, int maxabs) {
 }
 
 int mm_validate(int mode, const char *q, const long long *q_off, int n_q, const char *t, const long long *t_off, int n_t,
-                const Scoring &sc, int &max_lq, int &max_lt) {
-  int rc, min_lq, min_lt;
+                const Scoring &sc, int &max_lq, int &max_lt, int &min_lt) {
+  int rc, min_lq;
   if ((rc = check_scoring(sc))) return rc;
   if (mode < 0 || mode > 3) return fail(ABV_ERR_ARGS, "unknown mode %d", mode);
   if ((rc = check_seqs(q, q_off, n_q, "query", max_lq, min_lq))) return rc;
@@ -409,15 +409,16 @@ int mm_validate(int mode, const char *q, const long long *q_off, int n_q, const 
 
 // drift-normalised values carry an extra |ge| per column and row (dp_core.cuh, mm16d_row); glocal
 // keeps half the range free for its minus-infinity sentinel
-bool packed_exact_streaming(int mode, int P, int max_lt, int maxabs, int ge) {
+bool packed_exact_streaming(int mode, int P, int max_lt, int maxabs, int ge, int min_lt) {
   if (mode != ABV_GLOBAL && mode != ABV_GLOCAL) return false;
+  if (mode == ABV_GLOCAL && min_lt < MM16G_MIN_ROWS) return false;   // deferred last rows: a pair's capture precedes the next pair's last rows (kernels.cuh)
   return (long long)(P + max_lt + 12) * (maxabs + std::abs(ge)) <= (mode == ABV_GLOCAL ? p16::P16_LIMIT : b16::LIMIT);
 }
 
 int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int n_q,
                 const char *t, const long long *t_off, int n_t, const Scoring &sc, int seed, bool all_scores) {
-  int rc, max_lq, max_lt;
-  if ((rc = mm_validate(mode, q, q_off, n_q, t, t_off, n_t, sc, max_lq, max_lt))) return rc;
+  int rc, max_lq, max_lt, min_lt = 0;
+  if ((rc = mm_validate(mode, q, q_off, n_q, t, t_off, n_t, sc, max_lq, max_lt, min_lt))) return rc;
   if ((rc = ctx_init())) return rc;
   cudaStream_t st = g.stream;
   J.mode = mode; J.n_q = n_q; J.n_t = n_t; J.seed = seed; J.alpha = sc.alpha; J.go = sc.go; J.ge = sc.ge;
@@ -460,13 +461,13 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
     if (packed_ok) {
       for (int k = 0; k < MM16_NK; ++k) {
         const int K = MM16_KS[k];
-        if (K % 2 && !(!g.opt.global_v1 && packed_exact_streaming(mode, 32 * K, tp_stride, maxabs, sc.ge))) continue;
+        if (K % 2 && !(!g.opt.global_v1 && packed_exact_streaming(mode, 32 * K, tp_stride, maxabs, sc.ge, min_lt))) continue;
         if (32 * K >= lq) { slot = k; break; }
       }
       if (slot >= 0) {
         const int K = MM16_KS[slot];
         if (!packed_exact(mode, 32 * K, tp_stride, maxabs)) slot = -1;
-        else if (std::max(mm16_smem_layout(K, a1, tp_stride).total, mm16g_smem_layout(K, a1, tp_stride).total) > 100 * 1024) slot = -1;
+        else if (std::max(mm16_smem_layout(K, a1, tp_stride).total, mm16g_smem_layout(K, a1, tp_stride, mm16g_defer(mode == ABV_GLOCAL, K)).total) > 100 * 1024) slot = -1;
       }
     }
     if (slot >= 0) lists[slot].push_back(i); else wf32_list.push_back(i);
@@ -480,7 +481,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
       double qlen = 0;
       for (int i : lists[k]) qlen += (double)(q_off[i + 1] - q_off[i]);
       abv_job::Bucket b{MM16_KS[k], (int)lists[k].size(), (int)flat.size(), qlen * (double)(t_off[n_t] - t_off[0]), nullptr, nullptr,
-                        !g.opt.global_v1 && packed_exact_streaming(mode, 32 * MM16_KS[k], tp_stride, maxabs, sc.ge)};
+                        !g.opt.global_v1 && packed_exact_streaming(mode, 32 * MM16_KS[k], tp_stride, maxabs, sc.ge, min_lt)};
       CU(cudaEventCreate(&b.e0));
       CU(cudaEventCreate(&b.e1));
       J.buckets.push_back(b);
@@ -843,7 +844,7 @@ static int best_hits_impl(int mode, const char *q, const long long *q_off, int n
   std::lock_guard<std::recursive_mutex> lk(g.mu);
   int rc;
   Scoring sc{alpha_len, gap_open, gap_extend, map256, score_matrix};
-  { int a, b; if ((rc = mm_validate(mode, q, q_off, n_q, t, t_off, n_t, sc, a, b))) return rc; }
+  { int a, b, c; if ((rc = mm_validate(mode, q, q_off, n_q, t, t_off, n_t, sc, a, b, c))) return rc; }
   if ((rc = ctx_init())) return rc;
   for (double &v : t_timing) v = 0;
   abv_job J;

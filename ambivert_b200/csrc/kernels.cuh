@@ -1224,9 +1224,12 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16_
 //     (one lane per step), corner captures at warp-uniform steps outside the inner loop;
 //   * three row buffers per warp; the copy for pair i+2 is issued once every lane has left pair i-1.
 struct Mm16gSmem {
-  int lut, tbuf, mbar, mext, wres, misc, zero, slots, qcodes, total;
+  int lut, tbuf, mbar, mext, wres, misc, zero, slots, qcodes, evs, total;
 };
-__host__ __device__ inline Mm16gSmem mm16g_smem_layout(int K, int a1, int tp_stride) {
+// glocal, K <= 9: the diagonal sums of a lane's last target row are parked in shared memory at the step the lane
+// passes that row and folded once per pair at the capture ("deferred" last rows); wider strips keep the in-loop fold
+__host__ __device__ constexpr bool mm16g_defer(bool glocal, int K) { return glocal && K <= 9; }
+__host__ __device__ inline Mm16gSmem mm16g_smem_layout(int K, int a1, int tp_stride, bool defer) {
   Mm16gSmem L;
   int off = 0;
   const int KP = (K % 2) ? ((K + 3) & ~3) : K;             // StripCfg<K>::KP
@@ -1239,6 +1242,8 @@ __host__ __device__ inline Mm16gSmem mm16g_smem_layout(int K, int a1, int tp_str
   L.zero = off; off += 64;
   L.slots = off; off += MM16_WARPS * 4 * 4;
   L.qcodes = off; off += 32 * KP;
+  off = (off + 15) & ~15;
+  L.evs = off; off += defer ? MM16_WARPS * 2 * 32 * KP * 4 : 0;     // per warp: [half][vector][lane] words
   L.total = (off + 15) & ~15;
   return L;
 }
@@ -1247,12 +1252,13 @@ template <int MODE, int K>
 __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g_kernel(Mm16Params p) {
   static_assert(MODE == GLOBAL || MODE == GLOCAL, "the streaming kernel implements global and glocal");
   constexpr bool GL = (MODE == GLOCAL);
+  constexpr bool DEFER = mm16g_defer(GL, K);
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int KP = StripCfg<K>::KP;
   constexpr int P = StripCfg<K>::P;
   constexpr int V = StripCfg<K>::V;
   constexpr int W = MM16_WARPS;
-  const Mm16gSmem L = mm16g_smem_layout(K, p.a1, p.tp_stride);
+  const Mm16gSmem L = mm16g_smem_layout(K, p.a1, p.tp_stride, DEFER);
   uint32_t *lut = reinterpret_cast<uint32_t *>(smem + L.lut);
   uint8_t *qcodes = smem + L.qcodes;
   int *mext = reinterpret_cast<int *>(smem + L.mext);
@@ -1434,7 +1440,106 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
             bulk_load(smem + tbuf0 + b2 * p.tp_stride, p.tp_codes + (long long)(pbase + (i + 2) * W) * p.tp_stride, p.tp_stride, &bar[b2]);
           }
         };
-        if (GL) {
+        if (DEFER) {
+          // glocal with deferred last rows.  The last target row of a half is a forced diagonal (glocal_align.c:172-183):
+          // its cells are what S[] holds after the row's first pass.  Lane t passes that row at step ev + t, a different step
+          // for every lane, so the lane only parks S[] in shared memory there (predicated vector stores, no ALU work) and the
+          // warp folds all parked rows once, at the warp-uniform capture step.  A lane overwrites its slot when it passes
+          // the NEXT pair's last row, at step >= 31 + t of that pair, while the capture of this pair falls on one of its
+          // first 31 steps: no target shorter than 32 is allowed on this path (align_abi.cu, job_prepare).
+          uint32_t *evw = reinterpret_cast<uint32_t *>(smem + L.evs) + warp * (2 * 32 * KP);
+          auto park = [&](int half) {
+            uint32_t *dst = evw + half * (32 * KP);
+            if (V == 4) {
+#pragma unroll
+              for (int v = 0; v < KP / 4; ++v) reinterpret_cast<uint4 *>(dst)[v * 32 + lane] = make_uint4(S[4 * v], S[4 * v + 1], S[4 * v + 2], S[4 * v + 3]);
+            } else {
+#pragma unroll
+              for (int v = 0; v < KP / 2; ++v) reinterpret_cast<uint2 *>(dst)[v * 32 + lane] = make_uint2(S[2 * v], S[2 * v + 1]);
+            }
+          };
+          auto park_at = [&](int s, int e1, int e2) {
+            if (lane == s - e1) park(0);
+            if (lane == s - e2) park(1);
+          };
+          // max over the real query columns c of (S~[c] + g*(c + r)), r = the half's last row: per lane the chain
+          // n_k = max(n_{k-1} - g, S~[k]) (one add-max per column); the drift is undone in two non-negative steps (no borrow
+          // between the halves whatever the other half holds): + |g|*(32K - c) per lane before the warp maximum, g*(32K + r) after
+          auto fold = [&](int half, int idx, int r) {
+            uint32_t m = NEGb;
+            if (lane <= tstar) {
+              uint32_t T[KP];
+              const uint32_t *src = evw + half * (32 * KP);
+              if (V == 4) {
+#pragma unroll
+                for (int v = 0; v < KP / 4; ++v) { const uint4 x = reinterpret_cast<const uint4 *>(src)[v * 32 + lane]; T[4 * v] = x.x; T[4 * v + 1] = x.y; T[4 * v + 2] = x.z; T[4 * v + 3] = x.w; }
+              } else {
+#pragma unroll
+                for (int v = 0; v < KP / 2; ++v) { const uint2 x = reinterpret_cast<const uint2 *>(src)[v * 32 + lane]; T[2 * v] = x.x; T[2 * v + 1] = x.y; }
+              }
+              const int klast = lane < tstar ? K - 1 : kstar;
+#pragma unroll
+              for (int k = 0; k < K; ++k)
+                if (k <= klast) m = p16::addmax(m, negg, T[k]);
+              const int up = -ge * (P - c0 - klast);
+              m += p16::pack(up, up);
+            }
+            const uint32_t v = warp_max2(m);
+            const int sc = max(0, (half ? b16::hi(v) : b16::lo(v)) + ge * (P + r));     // max starts at 0 (glocal_align.c:115)
+            if (sc > wbest || (sc == wbest && idx < widx)) { wbest = sc; widx = idx; }
+            if (p.all_scores && lane == 0) p.all_scores[(long long)qi * p.n_t + idx] = sc;
+          };
+          auto captures = [&](int done) {
+            if (done < MM16G_MIN_ROWS) {
+              if (done == pend_s1) fold(0, pend_i1, pend_r1);
+              if (done == pend_s2) fold(1, pend_i2, pend_r2);
+            }
+            if (done == cs1) fold(0, meta.z, meta.x - 1);
+            if (done == cs2) fold(1, meta.w, meta.y - 1);
+          };
+          const bool early = min(ev1, ev2) < MM16G_MIN_ROWS;         // this pair's own last rows start inside the switching steps
+          const int s_chk = min(rows, max(MM16G_MIN_ROWS, min(ev1, ev2)));      // from here on lanes reach this pair's last rows
+          int s = 0;
+          while (s < rows) {
+            const bool switching = s < MM16G_MIN_ROWS;
+            int stop = switching ? MM16G_MIN_ROWS : (s < s_chk ? s_chk : rows);
+            if (switching) {
+              if (pend_s1 >= s && pend_s1 < stop) stop = pend_s1 + 1;
+              if (pend_s2 >= s && pend_s2 < stop) stop = pend_s2 + 1;
+            }
+            if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
+            if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
+            if (switching) {
+              // lane s switches to this pair at step s and computes its row 0 through the common row (dp_core.cuh,
+              // MM16G_NO_EGAP); the lanes still on the previous pair park its last rows
+#pragma unroll 1
+              for (; s < stop; ++s) {
+                uint32_t h_sh, e_sh, gope = gop2;
+                exchange(h_sh, e_sh);
+                if (lane == s) {
+#pragma unroll
+                  for (int k = 0; k < K; ++k) { Hp[k] = G0 - (uint32_t)k * gew; F[k] = NEGb; }
+                  hleft = G0 + gew;
+                  tb_off = bufoff - lane;
+                  e_sh = NEGb; gope = NOEGAP;
+                }
+                row_e(s, h_sh, e_sh, gope);
+                park_at(s, pend_e1, pend_e2);
+                if (early) park_at(s, ev1, ev2);
+              }
+            } else if (s < s_chk) {
+#pragma unroll kHotUnroll
+              for (; s < stop; ++s) body(s);                    // no lane is on a last row yet
+            } else {
+              for (; s < stop; ++s) {
+                body(s);
+                park_at(s, ev1, ev2);
+              }
+            }
+            captures(s - 1);
+            if (s == MM16G_MIN_ROWS) issue_next_copy();
+          }
+        } else if (GL) {
           // undo of the drift on the previous pair's last rows, per half: + g*(c0 + r)
           const uint32_t dpend = b16::addend(ge * (c0 + K - 1 + pend_r1), ge * (c0 + K - 1 + pend_r2));
           const bool early = min(ev1, ev2) < 2 * MM16G_MIN_ROWS;     // a short target: its last rows start inside the switching steps

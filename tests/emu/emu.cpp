@@ -300,13 +300,25 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
   int prev_rows = 0, pend_s1 = -1, pend_s2 = -1, pend_i1 = -1, pend_i2 = -1;
   const int NOEV = 1 << 20;
   int pend_e1 = NOEV, pend_e2 = NOEV, pend_r1 = 0, pend_r2 = 0;
-  auto last_row = [&](int t, int half, int r, int parity) {
-    const int c0 = t * K;
-    uint32_t m = NEGb;
-    const uint32_t d0 = b16::addend(ge * (c0 + r), ge * (c0 + r));
-    for (int k = 0; k < K; ++k)
-      if (c0 + k < lq) m = p16::max2(m, S[t][k] + d0 + (uint32_t)k * gew);
-    slots[2 * parity + half] = std::max(slots[2 * parity + half], half ? b16::hi(m) : b16::lo(m));
+  // glocal, deferred last rows (kernels.cuh): a lane parks the diagonal sums of the last target row of a half at the step it
+  // passes that row; the warp folds the parked rows at the capture step.  One slot per (half, lane): a capture must come before
+  // the lane's next event overwrites it (targets of at least 32 rows, align_abi.cu job_prepare)
+  std::vector<uint32_t> evs((size_t)2 * 32 * KP, 0);
+  const uint32_t negg = p16::pack(-ge, -ge);
+  auto last_row = [&](int t, int half, int, int) {
+    for (int k = 0; k < KP; ++k) evs[((size_t)half * 32 + t) * KP + k] = S[t][k];
+  };
+  auto fold = [&](int half, int r) {
+    uint32_t best = NEGb;
+    for (int t = 0; t <= tstar; ++t) {
+      const int klast = t < tstar ? K - 1 : kstar;
+      uint32_t m = NEGb;
+      for (int k = 0; k <= klast; ++k) m = p16::addmax(m, negg, evs[((size_t)half * 32 + t) * KP + k]);
+      const int up = -ge * (P - t * K - klast);
+      m += p16::pack(up, up);
+      best = p16::max2(best, m);
+    }
+    return std::max(0, (half ? b16::hi(best) : b16::lo(best)) + ge * (P + r));
   };
   // one step of the warp; `sw` = lane that switches pair in this step (-1: none), with its new buffer;
   // ev*/pe*: glocal last-row events of the current / previous pair (lane t fires at step ev + t)
@@ -350,9 +362,7 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
   int lvl = 0, pend_lvl = 0, lv_i = 0;
   auto capture = [&](int half, int idx, int par, int level) {
     if (GL) {
-      const int v = slots[2 * par + half];
-      (half ? sc2_out : sc1_out)[idx] = std::max(0, v);
-      slots[2 * par + half] = INT_MIN;
+      (half ? sc2_out : sc1_out)[idx] = fold(half, (half ? l2s[idx] : l1s[idx]) - 1);
     } else {
       const uint32_t hs = Hp[tstar][kstar];
       const int drift = ge * (lq - 1 + (half ? l2s[idx] : l1s[idx]) - 1);
