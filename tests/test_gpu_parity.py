@@ -443,6 +443,56 @@ def test_packed_vs_wf32_random_sweep(B):
         assert (got_hits[0] == want_hits[0]).all() and (got_hits[1] == want_hits[1]).all(), (it, mode, seed)
 
 
+def test_streaming_kernels_many_pairs_vs_wf32(B):
+    """the streaming kernels on jobs where every warp sweeps many target pairs: global climbs several staircases of
+    levels (a pair enters by injection, every n-th one by an explicit reset; dp_core.cuh mm16g_levels), glocal parks the
+    last rows of its targets (>= 32 rows) in shared memory and folds them once per pair; ragged lengths, every strip
+    width including the odd ones, the bundled DNA scoring and random matrices / penalties"""
+    rng = random.Random(31337)
+    for it in range(10):
+        dna = it < 6
+        alpha = 5 if dna else rng.choice([4, 5, 7])
+        alphabet = "ACGTNRY"[:alpha]
+        _, mp = O.make_map(alphabet, alphabet[-1], True)
+        if dna:
+            M, go, ge = O.DNA_SCORE, -7, -1
+        else:
+            M = np.array([rng.randint(-5, 5) for _ in range(alpha * alpha)], np.int32)
+            ge = -rng.randint(0, 3)
+            go = ge - rng.randint(0, 8)
+        lmax = rng.choice([40, 64, 120, 300])
+        n_t = rng.choice([91, 400, 900]) if lmax <= 120 else rng.choice([91, 400])
+        targets = [rand_dna(rng, rng.randint(32, lmax), alphabet) for _ in range(n_t)]
+        queries = []
+        for lo, hi in ((1, 64), (65, 96), (97, 128), (129, 160), (161, 192), (200, 224), (225, 256), (257, 288), (289, 320)):
+            L = rng.randint(lo, hi)
+            queries.append(mutate(rng, rand_dna(rng, L, alphabet), 2, alphabet) if rng.random() < 0.5 else
+                           (targets[rng.randrange(n_t)] * 9)[:L])
+        q = [s.encode() for s in queries]
+        t = [s.encode() for s in targets]
+        for mode in (O.GLOBAL, O.GLOCAL):
+            B.set_option("path", B.PATH_WF32)
+            try:
+                want = B.score_matrix(q, t, mode, alpha, mp, M, go, ge)
+            finally:
+                B.set_option("path", B.PATH_AUTO)
+            got = B.score_matrix(q, t, mode, alpha, mp, M, go, ge)
+            bad = np.argwhere(got != want)
+            assert bad.size == 0, (it, mode, alpha, go, ge, bad[:3], got[tuple(bad[0])], want[tuple(bad[0])],
+                                   len(queries[bad[0][0]]), len(targets[bad[0][1]]))
+            if dna:     # the 16-bit bounds hold: the streaming kernels served these queries (odd strip widths exist only there)
+                with B.BestHitsJob(q, t, mode, 0, alpha, mp, M, go, ge) as job:
+                    job.launch()
+                    bs, bi = job.fetch()
+                    ks = {r["K"] for r in job.profile()}
+                assert ks & {3, 5, 7, 9}, (it, mode, ks)
+                col = np.arange(n_t)[None, :]
+                best = want.max(axis=1)
+                first = np.where(want == best[:, None], col, n_t).min(axis=1)
+                hit = best > 0
+                assert (bs == np.where(hit, best, 0)).all() and (bi == np.where(hit, first, -1)).all(), (it, mode)
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_legacy_single_calls_fuzz(A, oracle_port, mode):
     """the lean one-launch path behind the reference's own symbols: the column blocks of the one pair are
