@@ -1367,7 +1367,7 @@ int abv_int_peak(int which, int iters, double *lane_ops_per_s, double *sm_clock_
   std::lock_guard<std::recursive_mutex> lk(g.mu);
   int rc;
   if ((rc = ctx_init())) return rc;
-  if (which < 0 || which > 8 || iters <= 0) return fail(ABV_ERR_ARGS, "bad microbenchmark arguments");
+  if (which < 0 || which > 11 || iters <= 0) return fail(ABV_ERR_ARGS, "bad microbenchmark arguments");
   const int threads = 256, grid = g.sms * 8;
   DevMem out;
   CU(out.alloc(sizeof(uint32_t) * (size_t)grid * threads));
@@ -1381,6 +1381,9 @@ int abv_int_peak(int which, int iters, double *lane_ops_per_s, double *sm_clock_
       case 5: int_peak_kernel<5><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
       case 6: int_peak_kernel<6><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
       case 7: int_peak_kernel<7><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
+      case 9: int_peak_kernel<9><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
+      case 10: int_peak_kernel<10><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
+      case 11: int_peak_kernel<11><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
       default: int_peak_kernel<8><<<grid, threads, 0, g.stream>>>(out.as<uint32_t>(), it, 12345u); break;
     }
   };

@@ -1699,6 +1699,8 @@ __global__ void int_peak_kernel(uint32_t *out, int iters, uint32_t seed) {
     b[i] = seed * 3 + i * 5 + (threadIdx.x & 3);
     c[i] = seed ^ (i * 0x10001u);
   }
+  uint32_t gopr = 0xfffafffau;
+  asm volatile("" : "+r"(gopr));      // opaque: stays in a register
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
@@ -1730,6 +1732,17 @@ __global__ void int_peak_kernel(uint32_t *out, int iters, uint32_t seed) {
         b[i] = __viaddmax_s16x2(h, 0xfffafffau, b[i]);
         c[i] = __viaddmax_s16x2(h, 0xfffafffau, c[i]);
         a[i] = h;
+      } else if (WHICH == 9) {   // the same cell with the gap addend in a REGISTER, as the kernel has it (WHICH 8: an immediate)
+        uint32_t dd = a[i] + c[i];
+        uint32_t h = __vimax3_s16x2(dd, b[i], c[i]);
+        b[i] = __viaddmax_s16x2(h, gopr, b[i]);
+        c[i] = __viaddmax_s16x2(h, gopr, c[i]);
+        a[i] = h;
+      } else if (WHICH == 10) {  // add-max with three register sources
+        a[i] = __viaddmax_s16x2(a[i], gopr, c[i]); b[i] = __viaddmax_s16x2(b[i], gopr, a[i]);
+        c[i] = __viaddmax_s16x2(c[i], gopr, b[i]); a[i] = __viaddmax_s16x2(a[i], gopr, b[i]);
+      } else if (WHICH == 11) {  // two-input packed max
+        a[i] = __vmaxs2(a[i], b[i]); b[i] = __vmaxs2(b[i], c[i]); c[i] = __vmaxs2(c[i], a[i] ^ 1); a[i] = __vmaxs2(a[i], 0x00010001u);
       } else {                 // packed cell with plain 32-bit adds (biased-operand variant): 5 ops
         uint32_t dd = a[i] + c[i];
         uint32_t h = __vimax3_s16x2(dd, b[i], c[i]);
@@ -1745,7 +1758,7 @@ __global__ void int_peak_kernel(uint32_t *out, int iters, uint32_t seed) {
   for (int i = 0; i < CH; ++i) r ^= a[i] ^ b[i] ^ c[i];
   if (r == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = r;   // keeps the chains live
 }
-constexpr int INT_PEAK_OPS[9] = {4, 4, 4, 4, 5, 5, 4, 5, 4};   // lane-ops per chain per iteration
+constexpr int INT_PEAK_OPS[12] = {4, 4, 4, 4, 5, 5, 4, 5, 4, 4, 4, 4};   // lane-ops per chain per iteration
 constexpr int INT_PEAK_CHAINS = 8;
 
 }  // namespace abv
