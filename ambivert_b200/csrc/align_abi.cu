@@ -11,6 +11,8 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <chrono>
+#include <memory>
 #include <vector>
 
 #include "../../include/ambivert_align.h"
@@ -52,6 +54,7 @@ struct Options {
   int global_v1 = 0;            // 1 = use the first-generation packed kernel for global mode too
   int no_levels = 0;            // 1 = streaming global kernel resets every pair explicitly (no level staircase, mm16g_levels)
   int tb16 = 1;                 // 0 = one-to-one jobs always take the 32-bit kernel
+  int pairs_chunk = 200000;     // one-to-one jobs of at least 2x this many pairs run as a pipeline of chunks (0 = never)
 };
 
 struct Ctx {
@@ -60,6 +63,9 @@ struct Ctx {
   int device = 0;
   int sms = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;      // second lane of the chunk pipeline of the one-to-one jobs
+  cudaStream_t stream3 = nullptr;      // its downloads
+  unsigned long long *pin64 = nullptr; // 64 pinned words: counters read back per chunk (a copy into pageable memory would block the host until the chunk has finished)
   cudaEvent_t ev[6] = {};
   Options opt;
 };
@@ -82,6 +88,9 @@ int ctx_init() {
     return fail(ABV_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", g.device, prop.major, prop.minor);
   g.sms = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g.stream3, cudaStreamNonBlocking));
+  CU(cudaHostAlloc((void **)&g.pin64, 64 * sizeof(unsigned long long), cudaHostAllocDefault));
   for (auto &ev : g.ev) CU(cudaEventCreate(&ev));
   g.inited = true;
   return ABV_OK;
@@ -196,33 +205,42 @@ struct UploadKeep {
 // Sequences -> device: raw bytes + offsets, then to_raw on the device (helpers.h:26-32).  With `keep` nothing here waits
 // for the stream (pinned caller buffers then copy while the host goes on planning); without it the call returns synchronised.
 int upload_encoded(const char *buf, const long long *off, int n, const Scoring &sc, cudaStream_t st,
-                   DevMem &d_codes, DevMem &d_off, DevMem &d_map, double &h2d_bytes, DevMem *keep_raw = nullptr, UploadKeep *keep = nullptr) {
+                   DevMem &d_codes, DevMem &d_off, DevMem &d_map, double &h2d_bytes, DevMem *keep_raw = nullptr, UploadKeep *keep = nullptr,
+                   int phase = 0) {
+  // phase 0: everything; 1: the small pageable pieces only (offsets, map); 2: the sequence bytes + encode only.  A pageable
+  // copy holds the host until the copy engine has served it, so a pipelined caller sends all small pieces of a chunk before
+  // the first large (pinned, truly asynchronous) one.
   UploadKeep local;
   UploadKeep &K = keep ? *keep : local;
   const long long total = n ? off[n] - off[0] : 0;
-  std::vector<long long> &rel = K.rel[K.used++ & 3];
-  rel.resize((size_t)n + 1);
-  for (int i = 0; i <= n; ++i) rel[i] = n ? off[i] - off[0] : 0;
-  CU(d_off.alloc(sizeof(long long) * (n + 1)));
-  CU(cudaMemcpyAsync(d_off.p, rel.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
-  CU(d_codes.alloc((size_t)total + 16));
-  DevMem raw;
-  unsigned char ident[256];
-  const unsigned char *m = sc.map256;
-  if (!m) { for (int i = 0; i < 256; ++i) ident[i] = (unsigned char)i; m = ident; }
-  for (int i = 0; i < 256; ++i) K.clamped[i] = (unsigned char)std::min<int>(m[i], sc.alpha - 1);
-  if (!d_map.p) CU(d_map.alloc(256));
-  CU(cudaMemcpyAsync(d_map.p, K.clamped, 256, cudaMemcpyHostToDevice, st));
-  if (total > 0) {
-    CU(raw.alloc((size_t)total));
-    CU(cudaMemcpyAsync(raw.p, buf + off[0], (size_t)total, cudaMemcpyHostToDevice, st));
-    int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-    encode_kernel<<<blocks, 256, 0, st>>>(raw.as<uint8_t>(), d_codes.as<uint8_t>(), total, d_map.as<uint8_t>());
-    CU(cudaGetLastError());
-    if (keep_raw) { keep_raw->release(); keep_raw->p = raw.p; keep_raw->bytes = raw.bytes; raw.p = nullptr; raw.bytes = 0; }
+  if (phase != 2) {
+    std::vector<long long> &rel = K.rel[K.used++ & 3];
+    rel.resize((size_t)n + 1);
+    for (int i = 0; i <= n; ++i) rel[i] = n ? off[i] - off[0] : 0;
+    CU(d_off.alloc(sizeof(long long) * (n + 1)));
+    CU(cudaMemcpyAsync(d_off.p, rel.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
+    unsigned char ident[256];
+    const unsigned char *m = sc.map256;
+    if (!m) { for (int i = 0; i < 256; ++i) ident[i] = (unsigned char)i; m = ident; }
+    for (int i = 0; i < 256; ++i) K.clamped[i] = (unsigned char)std::min<int>(m[i], sc.alpha - 1);
+    if (!d_map.p) CU(d_map.alloc(256));
+    CU(cudaMemcpyAsync(d_map.p, K.clamped, 256, cudaMemcpyHostToDevice, st));
+    h2d_bytes += sizeof(long long) * (n + 1) + 256;
+  }
+  if (phase != 1) {
+    CU(d_codes.alloc((size_t)total + 16));
+    DevMem raw;
+    if (total > 0) {
+      CU(raw.alloc((size_t)total));
+      CU(cudaMemcpyAsync(raw.p, buf + off[0], (size_t)total, cudaMemcpyHostToDevice, st));
+      int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+      encode_kernel<<<blocks, 256, 0, st>>>(raw.as<uint8_t>(), d_codes.as<uint8_t>(), total, d_map.as<uint8_t>());
+      CU(cudaGetLastError());
+      if (keep_raw) { keep_raw->release(); keep_raw->p = raw.p; keep_raw->bytes = raw.bytes; raw.p = nullptr; raw.bytes = 0; }
+    }
+    h2d_bytes += (double)total;
   }
   if (!keep) CU(cudaStreamSynchronize(st));     // the staging vectors are locals
-  h2d_bytes += (double)total + sizeof(long long) * (n + 1) + 256;
   return ABV_OK;                                // `raw` returns to the allocation cache; its reuse is ordered on the same stream
 }
 
@@ -783,6 +801,7 @@ int abv_set_option(const char *key, int value) {
   if (!strcmp(key, "tb16")) { g.opt.tb16 = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "global_v1")) { g.opt.global_v1 = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "no_levels")) { g.opt.no_levels = value ? 1 : 0; return ABV_OK; }
+  if (!strcmp(key, "pairs_chunk")) { g.opt.pairs_chunk = std::max(0, value); return ABV_OK; }
   if (!strcmp(key, "mm16_blocks_per_sm")) { g.opt.mm16_blocks_per_sm = std::max(0, std::min(value, 8)); return ABV_OK; }
   return fail(ABV_ERR_ARGS, "unknown option %s", key);
 }
@@ -901,6 +920,15 @@ struct PairsRun {
   unsigned long long total = 0;
   int max_la = 0, max_lb = 0;
   double h2d = 0, cells = 0;
+  // a chunk of a pipelined job: its own stream, events and host-side plan (they live until the whole job has finished)
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  Tb16Plan *own_plan = nullptr;
+  unsigned long long *pin_total = nullptr;   // pinned landing place of `total`
+  ~PairsRun() {
+    for (auto &e : ev) if (e) cudaEventDestroy(e);
+    delete own_plan;
+  }
 };
 
 static int pairs_validate(int mode, const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
@@ -914,23 +942,42 @@ static int pairs_validate(int mode, const char *a, const long long *a_off, const
   return ABV_OK;
 }
 
-// upload + encode + fill + traceback for n > 0 validated pairs; g.ev[0..2] bracket upload and kernel
+static double trace_now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static bool trace_on() { static const bool on = getenv("ABV_TRACE") != nullptr; return on; }
+#define ABV_TRACE(...) do { if (trace_on()) { fprintf(stderr, "[abv %.3f] ", trace_now()); fprintf(stderr, __VA_ARGS__); fputc('\n', stderr); } } while (0)
+
+// upload + encode + fill + traceback for n > 0 validated pairs; g.ev[0..2] bracket upload and kernel.
+// A chunk of a pipelined job (R.st set) runs on its own stream with its own events and plan and returns WITHOUT waiting:
+// the caller synchronises R.st before it reads R.total.
 static int pairs_run(PairsRun &R, int mode, const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
                      const Scoring &sc, long long pool_cap, bool keep_raw) {
   int rc;
-  cudaStream_t st = g.stream;
-  CU(cudaEventRecord(g.ev[0], st));
-  if (!R.a_codes.p) {   // first attempt: the inputs are not on the device yet
-    if ((rc = upload_encoded(a, a_off, n, sc, st, R.a_codes, R.a_off, R.map, R.h2d, keep_raw ? &R.a_raw : nullptr, &R.keep))) return rc;
-    if ((rc = upload_encoded(b, b_off, n, sc, st, R.b_codes, R.b_off, R.map, R.h2d, keep_raw ? &R.b_raw : nullptr, &R.keep))) return rc;
+  const bool chunk = R.st != nullptr;
+  cudaStream_t st = chunk ? R.st : g.stream;
+  cudaEvent_t *ev = chunk ? R.ev : g.ev;
+  CU(cudaEventRecord(ev[0], st));
+  // One piece: the sequences go first and copy while the host plans.  A chunk of a pipeline sends its small pageable pieces
+  // first (offsets here, the plan below) and the sequence bytes last, see upload_encoded.
+  auto upload = [&](int phase) -> int {
+    int r2;
+    if ((r2 = upload_encoded(a, a_off, n, sc, st, R.a_codes, R.a_off, R.map, R.h2d, keep_raw ? &R.a_raw : nullptr, &R.keep, phase))) return r2;
+    if ((r2 = upload_encoded(b, b_off, n, sc, st, R.b_codes, R.b_off, R.map, R.h2d, keep_raw ? &R.b_raw : nullptr, &R.keep, phase))) return r2;
+    return ABV_OK;
+  };
+  const bool first = !R.a_codes.p && !R.a_off.p;      // first attempt: the inputs are not on the device yet
+  if (first) {
+    if ((rc = upload(chunk ? 1 : 0))) return rc;
     CU(R.matrix.alloc(sizeof(int) * sc.alpha * sc.alpha));
     CU(cudaMemcpyAsync(R.matrix.p, sc.matrix, sizeof(int) * sc.alpha * sc.alpha, cudaMemcpyHostToDevice, st));
     R.cells = 0;
     for (int i = 0; i < n; ++i) R.cells += (double)(a_off[i + 1] - a_off[i]) * (double)(b_off[i + 1] - b_off[i]);
   }
   // plan: pairs the packed traceback kernel takes (bucketed, partnered) and the rest for the 32-bit kernel
-  static thread_local Tb16Plan plan;      // keeps its vectors' capacity from call to call
+  static thread_local Tb16Plan tl_plan;      // keeps its vectors' capacity from call to call
+  Tb16Plan &plan = chunk ? *R.own_plan : tl_plan;
+  ABV_TRACE("pairs_run n=%d: uploads issued", n);
   tb16_plan(plan, mode, a_off, b_off, n, sc);
+  ABV_TRACE("pairs_run n=%d: planned", n);
   const int tmp_cap = R.max_la + R.max_lb + 2;
   const long long dwords = plan.n_rest ? dir_words(plan.rest_max_la, plan.rest_max_lb) : 0;
   const size_t per_warp = (size_t)dwords * 4 + (size_t)tmp_cap * sizeof(FragOut) + (size_t)R.max_lb * 8;
@@ -952,18 +999,20 @@ static int pairs_run(PairsRun &R, int mode, const char *a, const long long *a_of
   CU(R.frags.alloc(sizeof(FragOut) * (size_t)std::max<long long>(R.pool, 1)));
   CU(R.counters.alloc(8 * 16));
   CU(cudaMemsetAsync(R.counters.p, 0, 8 * 16, st));
+  cudaStream_t sp = st;
   CU(R.lists.alloc(sizeof(int) * std::max<size_t>(plan.list.size(), 1)));
-  CU(cudaMemcpyAsync(R.lists.p, plan.list.data(), sizeof(int) * plan.list.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(R.lists.p, plan.list.data(), sizeof(int) * plan.list.size(), cudaMemcpyHostToDevice, sp));
   if (!plan.buckets.empty()) {
     const int a1 = sc.alpha + 1;
     plan.mext.assign((size_t)a1 * a1, plan.pad_score);
     for (int i = 0; i < sc.alpha; ++i)
       for (int j = 0; j < sc.alpha; ++j) plan.mext[(size_t)i * a1 + j] = sc.matrix[i * sc.alpha + j];
     CU(R.matrix_ext.alloc(sizeof(int) * plan.mext.size()));
-    CU(cudaMemcpyAsync(R.matrix_ext.p, plan.mext.data(), sizeof(int) * plan.mext.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(R.matrix_ext.p, plan.mext.data(), sizeof(int) * plan.mext.size(), cudaMemcpyHostToDevice, sp));
   }
+  if (chunk && first && (rc = upload(2))) return rc;     // the sequence bytes, behind every small piece of this chunk
   // no wait here: plan is thread-local and this function synchronises the stream before it returns
-  CU(cudaEventRecord(g.ev[1], st));
+  CU(cudaEventRecord(ev[1], st));
 
   unsigned long long *counters = R.counters.as<unsigned long long>();   // [0] wf32 pairs, [1] fragment total, [2..] tb16 items per bucket
   int bi = 0;
@@ -1003,9 +1052,29 @@ static int pairs_run(PairsRun &R, int mode, const char *a, const long long *a_of
     p.pair_counter = counters;
     if ((rc = wf32_dispatch<true>(mode, grid, st, p, plan.rest_max_lb))) return rc;
   }
-  CU(cudaEventRecord(g.ev[2], st));
-  CU(cudaMemcpyAsync(&R.total, p.frag_total, sizeof R.total, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(cudaEventRecord(ev[2], st));
+  ABV_TRACE("pairs_run n=%d: kernels issued", n);
+  CU(cudaMemcpyAsync(chunk ? R.pin_total : &R.total, p.frag_total, sizeof R.total, cudaMemcpyDeviceToHost, st));
+  if (!chunk) CU(cudaStreamSynchronize(st));
+  return ABV_OK;
+}
+
+// ---- pipeline of chunks for large one-to-one jobs -------------------------------------------------------------------
+// The stage is upload (PCIe) -> fill + traceback (SMs) -> download (PCIe).  Run in one piece the three phases follow one
+// another (1M read pairs: 14 + 23 + 5 ms); cut into chunks on two alternating streams, the upload of chunk c+1 and the
+// download of chunk c-1 overlap the kernels of chunk c.  Every chunk is a complete job of its own (plan, scratch,
+// fragment pool); the caller stitches the outputs together.  Blocks go back to the allocation cache only after every
+// stream has been synchronised (the chunks' PairsRun objects outlive the pipeline).
+static int pairs_chunks(int n) {
+  const int per = g.opt.pairs_chunk;
+  if (per <= 0 || n < 2 * per) return 1;
+  return (int)std::min<long long>(16, ((long long)n + per - 1) / per);
+}
+static int pairs_chunk_begin(PairsRun &R, int c) {
+  R.st = (c & 1) ? g.stream2 : g.stream;
+  for (auto &e : R.ev) CU(cudaEventCreate(&e));
+  R.own_plan = new Tb16Plan();
+  R.pin_total = g.pin64 + c;
   return ABV_OK;
 }
 
@@ -1026,6 +1095,65 @@ int abv_align_pairs(int mode, const char *a, const long long *a_off, const char 
   if ((rc = ctx_init())) return rc;
   for (double &v : t_timing) v = 0;
   cudaStream_t st = g.stream;
+  if (const int C = pairs_chunks(n); C > 1) {
+    // pipeline of chunks: enqueue two ahead, then per chunk wait, download, enqueue the next one
+    std::vector<std::unique_ptr<PairsRun>> Rs;
+    for (int c = 0; c < C; ++c) Rs.emplace_back(new PairsRun());
+    auto lo_of = [&](int c) { return (int)((long long)n * c / C); };
+    auto enqueue = [&](int c) -> int {
+      PairsRun &Rc = *Rs[c];
+      Rc.max_la = R.max_la; Rc.max_lb = R.max_lb;
+      int r2;
+      if ((r2 = pairs_chunk_begin(Rc, c))) return r2;
+      const int lo = lo_of(c), hi = lo_of(c + 1);
+      return pairs_run(Rc, mode, a, a_off + lo, b, b_off + lo, hi - lo, sc, frag_cap, true);
+    };
+    auto drain = [&]() { cudaStreamSynchronize(g.stream); cudaStreamSynchronize(g.stream2); cudaStreamSynchronize(g.stream3); };
+    for (int c = 0; c < std::min(2, C); ++c)
+      if ((rc = enqueue(c))) { drain(); return rc; }
+    long long base = 0;
+    bool overflow = false;
+    double d2h = 0, h2d = 0, cells = 0, ms_up = 0, ms_k = 0, ms_down = 0;
+    ABV_TRACE("align_pairs: %d chunks, first two enqueued", C);
+    for (int c = 0; c < C; ++c) {
+      PairsRun &Rc = *Rs[c];
+      const int lo = lo_of(c), nc = lo_of(c + 1) - lo;
+      ABV_TRACE("chunk %d: wait", c);
+      if (cudaStreamSynchronize(Rc.st) != cudaSuccess) { drain(); return fail(ABV_ERR_CUDA, "chunk %d failed: %s", c, cudaGetErrorString(cudaGetLastError())); }
+      ABV_TRACE("chunk %d: done on the device", c);
+      if (c + 2 < C && (rc = enqueue(c + 2))) { drain(); return rc; }      // keeps the other stream busy while this chunk downloads
+      ABV_TRACE("chunk %d: next enqueued", c);
+      Rc.total = *Rc.pin_total;
+      const long long total = (long long)Rc.total;
+      if (total > Rc.pool || base + total > frag_cap) overflow = true;
+      if (!overflow) {
+        const auto t0 = std::chrono::steady_clock::now();
+        // the chunk has finished (synchronised above): its results leave on the download stream, beside the other chunks' kernels
+        CU(cudaMemcpyAsync(scores + lo, Rc.scores.p, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, g.stream3));
+        CU(cudaMemcpyAsync(frag_start + lo, Rc.start.p, sizeof(long long) * (size_t)nc, cudaMemcpyDeviceToHost, g.stream3));
+        CU(cudaMemcpyAsync(frag_count + lo, Rc.count.p, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, g.stream3));
+        if (total > 0) CU(cudaMemcpyAsync(frags + base, Rc.frags.p, sizeof(FragOut) * (size_t)total, cudaMemcpyDeviceToHost, g.stream3));
+        CU(cudaStreamSynchronize(g.stream3));
+        if (base)
+          for (int i = 0; i < nc; ++i) frag_start[lo + i] += base;         // the chunk's pool starts at `base` of the caller's
+        ABV_TRACE("chunk %d: downloaded", c);
+        ms_down += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        d2h += 16.0 * nc + 8 + 16.0 * total;
+      }
+      base += total;
+      h2d += Rc.h2d; cells += Rc.cells;
+      float t0 = 0, t1 = 0;
+      cudaEventElapsedTime(&t0, Rc.ev[0], Rc.ev[1]);
+      cudaEventElapsedTime(&t1, Rc.ev[1], Rc.ev[2]);
+      ms_up += t0; ms_k += t1;
+    }
+    drain();
+    if (frag_total) *frag_total = base;
+    t_timing[0] = ms_up; t_timing[1] = ms_k; t_timing[2] = ms_down; t_timing[3] = cells; t_timing[4] = 3 * C;
+    t_timing[5] = h2d; t_timing[6] = d2h; t_timing[7] = ms_k;
+    if (overflow) return fail(ABV_ERR_FRAG_CAP, "fragment pool of %lld entries is too small, %lld needed", frag_cap, base);
+    return ABV_OK;
+  }
   if ((rc = pairs_run(R, mode, a, a_off, b, b_off, n, sc, frag_cap, false))) return rc;
   CU(cudaMemcpyAsync(scores, R.scores.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(frag_start, R.start.p, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -1053,6 +1181,115 @@ int abv_align_pairs(int mode, const char *a, const long long *a_off, const char 
 // -------------------------------------------------------------------------------------------------
 // The two host-side string builders that follow the aligner in the pipeline, on the device:
 //   gapped rows  (ambivert.py:95-111 / :136-152)  and  merged read (ambivert.py:324-327)
+// The pipelined form of assemble_impl for large jobs (see pairs_chunks): per chunk alignment + traceback, sizing, scan, assembly
+// on the chunk's stream; downloads on the download stream.  Returns ABV_RETRY_WHOLE when a chunk's fragment pool or the
+// caller's output buffer is too small: the caller then runs the job in one piece, which sizes the pool exactly and reports errors.
+constexpr int ABV_RETRY_WHOLE = -1000;
+struct AsmChunk {
+  PairsRun R;
+  DevMem lens, offs, dstatus, dsa, dsb, dout1, dout2, scan_tmp;
+  long long bytes = 0;
+  cudaEvent_t done = nullptr;
+  ~AsmChunk() { if (done) cudaEventDestroy(done); }
+};
+static int assemble_chunked(int C, int what, int mode, const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
+                            const Scoring &sc, int max_la, int max_lb, int minimum_overlap, int *scores, int *status, int *start_a,
+                            int *start_b, long long *out_off, char *out1, char *out2, long long out_cap, long long *out_total) {
+  int rc;
+  std::vector<std::unique_ptr<AsmChunk>> Cs;
+  for (int c = 0; c < C; ++c) Cs.emplace_back(new AsmChunk());
+  auto lo_of = [&](int c) { return (int)((long long)n * c / C); };
+  auto drain = [&]() { cudaStreamSynchronize(g.stream); cudaStreamSynchronize(g.stream2); cudaStreamSynchronize(g.stream3); };
+  auto params = [&](AsmChunk &K, int nc) {
+    AssembleParams q{};
+    q.what = what; q.n = nc; q.min_overlap = minimum_overlap;
+    q.a = K.R.a_raw.as<uint8_t>(); q.a_off = K.R.a_off.as<long long>();
+    q.b = K.R.b_raw.as<uint8_t>(); q.b_off = K.R.b_off.as<long long>();
+    q.frags = K.R.frags.as<FragOut>(); q.frag_start = K.R.start.as<long long>(); q.frag_count = K.R.count.as<int>();
+    q.lens = K.lens.as<long long>(); q.offs = K.offs.as<long long>(); q.status = K.dstatus.as<int>();
+    q.start_a = K.dsa.as<int>(); q.start_b = K.dsb.as<int>();
+    return q;
+  };
+  // phase A: everything that does not need a size from the device
+  auto phase_a = [&](int c) -> int {
+    AsmChunk &K = *Cs[c];
+    const int lo = lo_of(c), nc = lo_of(c + 1) - lo;
+    K.R.max_la = max_la; K.R.max_lb = max_lb;
+    int r2;
+    if ((r2 = pairs_chunk_begin(K.R, c))) return r2;
+    CU(cudaEventCreate(&K.done));
+    if ((r2 = pairs_run(K.R, mode, a, a_off + lo, b, b_off + lo, nc, sc, std::max<long long>(1024, 8ll * nc), true))) return r2;
+    cudaStream_t st = K.R.st;
+    CU(K.lens.alloc(sizeof(long long) * ((size_t)nc + 1)));
+    CU(K.offs.alloc(sizeof(long long) * ((size_t)nc + 1)));
+    CU(K.dstatus.alloc(sizeof(int) * (size_t)nc));
+    CU(K.dsa.alloc(sizeof(int) * (size_t)nc));
+    CU(K.dsb.alloc(sizeof(int) * (size_t)nc));
+    AssembleParams q = params(K, nc);
+    assemble_len_kernel<<<(nc + 255) / 256, 256, 0, st>>>(q);
+    CU(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, K.lens.as<long long>(), K.offs.as<long long>(), nc + 1, st));
+    CU(K.scan_tmp.alloc(tmp_bytes));
+    CU(cub::DeviceScan::ExclusiveSum(K.scan_tmp.p, tmp_bytes, K.lens.as<long long>(), K.offs.as<long long>(), nc + 1, st));
+    CU(cudaMemcpyAsync(g.pin64 + 16 + c, K.offs.as<long long>() + nc, sizeof K.bytes, cudaMemcpyDeviceToHost, st));
+    return ABV_OK;
+  };
+  for (int c = 0; c < std::min(2, C); ++c)
+    if ((rc = phase_a(c))) { drain(); return rc; }
+  long long byte_base = 0;
+  double d2h = 0, h2d = 0, cells = 0, ms_up = 0, ms_k = 0, ms_down = 0;
+  for (int c = 0; c < C; ++c) {
+    AsmChunk &K = *Cs[c];
+    const int lo = lo_of(c), nc = lo_of(c + 1) - lo;
+    cudaStream_t st = K.R.st;
+    if (cudaStreamSynchronize(st) != cudaSuccess) { drain(); return fail(ABV_ERR_CUDA, "chunk %d failed: %s", c, cudaGetErrorString(cudaGetLastError())); }
+    K.R.total = *K.R.pin_total;
+    K.bytes = (long long)g.pin64[16 + c];
+    if ((long long)K.R.total > K.R.pool || byte_base + K.bytes > out_cap) { drain(); return ABV_RETRY_WHOLE; }
+    // phase B: the strings of this chunk, then the next chunk's phase A behind them on the same stream
+    if (K.bytes > 0) {
+      CU(K.dout1.alloc((size_t)K.bytes));
+      if (what == ASSEMBLE_GAPPED) CU(K.dout2.alloc((size_t)K.bytes));
+      AssembleParams q = params(K, nc);
+      q.out1 = K.dout1.as<uint8_t>(); q.out2 = K.dout2.as<uint8_t>();
+      const int wpb = 8;
+      assemble_kernel<<<(nc + wpb - 1) / wpb, wpb * 32, 0, st>>>(q);
+      CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(K.done, st));
+    if (c + 2 < C && (rc = phase_a(c + 2))) { drain(); return rc; }
+    const auto t0 = std::chrono::steady_clock::now();
+    CU(cudaStreamWaitEvent(g.stream3, K.done, 0));
+    CU(cudaMemcpyAsync(scores + lo, K.R.scores.p, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, g.stream3));
+    CU(cudaMemcpyAsync(out_off + lo, K.offs.p, sizeof(long long) * (size_t)nc, cudaMemcpyDeviceToHost, g.stream3));
+    if (start_a) CU(cudaMemcpyAsync(start_a + lo, K.dsa.p, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, g.stream3));
+    if (start_b) CU(cudaMemcpyAsync(start_b + lo, K.dsb.p, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, g.stream3));
+    if (K.bytes > 0) {
+      if (out1) CU(cudaMemcpyAsync(out1 + byte_base, K.dout1.p, (size_t)K.bytes, cudaMemcpyDeviceToHost, g.stream3));
+      if (what == ASSEMBLE_GAPPED && out2) CU(cudaMemcpyAsync(out2 + byte_base, K.dout2.p, (size_t)K.bytes, cudaMemcpyDeviceToHost, g.stream3));
+    }
+    CU(cudaMemcpyAsync(status + lo, K.dstatus.p, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, g.stream3));   // after assembly: it may flag -2
+    CU(cudaStreamSynchronize(g.stream3));
+    if (byte_base)
+      for (int i = 0; i < nc; ++i) out_off[lo + i] += byte_base;
+    ms_down += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    d2h += 24.0 * nc + (what == ASSEMBLE_GAPPED ? 2.0 : 1.0) * K.bytes;
+    byte_base += K.bytes;
+    h2d += K.R.h2d; cells += K.R.cells;
+    float u = 0, k = 0;
+    cudaEventElapsedTime(&u, K.R.ev[0], K.R.ev[1]);
+    cudaEventElapsedTime(&k, K.R.ev[1], K.R.ev[2]);
+    ms_up += u; ms_k += k;
+  }
+  drain();
+  out_off[n] = byte_base;
+  if (out_total) *out_total = byte_base;
+  t_timing[0] = ms_up; t_timing[1] = ms_k; t_timing[2] = ms_down; t_timing[3] = cells; t_timing[4] = 6 * C;
+  t_timing[5] = h2d; t_timing[6] = d2h; t_timing[7] = ms_k;
+  return ABV_OK;
+}
+
 static int assemble_impl(int what, int mode, const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
                          int alpha_len, const unsigned char *map256, const int *score_matrix, int gap_open, int gap_extend,
                          int minimum_overlap, int *scores, int *status, int *start_a, int *start_b,
@@ -1068,6 +1305,12 @@ static int assemble_impl(int what, int mode, const char *a, const long long *a_o
   if ((rc = ctx_init())) return rc;
   for (double &v : t_timing) v = 0;
   cudaStream_t st = g.stream;
+  if (const int C = pairs_chunks(n); C > 1) {
+    rc = assemble_chunked(C, what, mode, a, a_off, b, b_off, n, sc, R.max_la, R.max_lb, minimum_overlap, scores, status, start_a, start_b,
+                          out_off, out1, out2, out_cap, out_total);
+    if (rc != ABV_RETRY_WHOLE) return rc;
+    for (double &v : t_timing) v = 0;
+  }
   long long cap = std::max<long long>(1024, 8ll * n);
   for (int attempt = 0; attempt < 2; ++attempt) {          // the fragment pool lives on the device only
     if ((rc = pairs_run(R, mode, a, a_off, b, b_off, n, sc, cap, true))) return rc;

@@ -78,3 +78,59 @@ def test_bad_base_pair_is_reported():
     # identical ambiguity codes and N are fine: same base -> itself, anything vs N -> N
     sc, status, off, merged = B.merge_pairs([fwd], [fwd.replace("R", "N")], 10)
     assert status[0] == 1 and merged.tobytes().decode() == fwd.replace("R", "N")
+
+
+def test_chunk_pipeline_equals_one_piece():
+    """large one-to-one jobs run as a pipeline of chunks on alternating streams (uploads and downloads beside the kernels);
+    forced here on small batches: scores, fragments, gapped rows and merged reads must equal the one-piece run, including
+    pairs the packed traceback kernel cannot take (long sequences) and a fragment pool that is too small"""
+    import random
+
+    import numpy as np
+
+    from ambivert_b200 import batch as B
+    from util import mutate, rand_dna
+    rng = random.Random(99)
+    fwd, rev = [], []
+    for _ in range(700):
+        f = rand_dna(rng, rng.randint(20, 200))
+        r = mutate(rng, f[rng.randint(0, len(f) - 10):] + rand_dna(rng, rng.randint(5, 80)), rng.randint(0, 3))
+        fwd.append(f.encode()); rev.append(r.encode())
+    for _ in range(6):                                   # too long for the packed traceback kernel
+        f = rand_dna(rng, rng.randint(400, 700))
+        fwd.append(f.encode()); rev.append(mutate(rng, f, 4).encode())
+    order = list(range(len(fwd)))
+    rng.shuffle(order)
+    fwd = [fwd[i] for i in order]; rev = [rev[i] for i in order]
+
+    def frag_lists(res):
+        sc, st, cn, fr = res
+        return [(int(sc[k]), [tuple(int(x) for x in fr[int(st[k]) + j]) for j in range(int(cn[k]))]) for k in range(len(sc))]
+
+    def run_all():
+        out = {}
+        for mode in (B.LOCAL, B.GLOBAL):
+            out["align", mode] = frag_lists(B.align_pairs(fwd, rev, mode))
+            g = B.gapped_pairs(fwd, rev, mode)
+            out["gapped", mode] = [x.tolist() if hasattr(x, "tolist") else x for x in g]
+        out["merge"] = [x.tolist() for x in B.merge_pairs(fwd, rev, 10)]
+        return out
+
+    B.set_option("pairs_chunk", 0)
+    try:
+        want = run_all()
+        for per in (37, 150, 353):
+            B.set_option("pairs_chunk", per)
+            got = run_all()
+            for key in want:
+                assert got[key] == want[key], (per, key)
+        # a fragment pool that is too small: the same error and the same required size as the one-piece run
+        B.set_option("pairs_chunk", 0)
+        with pytest.raises(B.AlignError) as e0:
+            B.align_pairs(fwd, rev, B.LOCAL, frag_cap=50)
+        B.set_option("pairs_chunk", 100)
+        with pytest.raises(B.AlignError) as e1:
+            B.align_pairs(fwd, rev, B.LOCAL, frag_cap=50)
+        assert str(e0.value) == str(e1.value)
+    finally:
+        B.set_option("pairs_chunk", 200000)
