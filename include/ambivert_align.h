@@ -117,7 +117,15 @@ int abv_set_device(int ordinal);          /* device used by subsequent calls of 
 int abv_get_device(void);
 const char *abv_last_error(void);         /* message of the last failing call of this thread */
 const char *abv_version(void);
-int abv_set_option(const char *key, int value);   /* "path": ABV_PATH_*, "warps_per_sm", ... */
+/* tuning / test options (defaults are what the measurements use):
+ *   "path"               ABV_PATH_*            kernel selection of the many-to-many scorer
+ *   "split"              0 = automatic         slices of the target pairs per query (short tail on multi-GPU shards)
+ *   "tb16"               1                     0: one-to-one jobs always take the 32-bit kernel
+ *   "global_v1"          0                     1: first-generation packed kernel for global mode
+ *   "no_levels"          0                     1: streaming global kernel resets every pair explicitly (no level staircase)
+ *   "pairs_chunk"        200000                one-to-one jobs of >= 2x this many pairs run as a pipeline of chunks; 0: never
+ *   "wf32_blocks_per_sm", "mm16_blocks_per_sm", "cache_mb" (device allocation cache) */
+int abv_set_option(const char *key, int value);
 
 /*
  * Many-to-many best hit: what ambivert.py:461-485 / :487-511 compute with one ctypes call per
