@@ -974,7 +974,10 @@ __global__ void best_key_finalize_kernel(const unsigned long long *__restrict__ 
   best_idx[qi] = hit ? bi : -1;
 }
 
-constexpr int MM16_WARPS = 8;
+#ifndef ABV_MM16_WARPS
+#define ABV_MM16_WARPS 8
+#endif
+constexpr int MM16_WARPS = ABV_MM16_WARPS;
 
 template <int K>
 struct Mm16Cfg {
