@@ -598,3 +598,9 @@ extern "C" int emu_tb16(int mode, int K, const unsigned char *qa0, int la0, cons
   if (mode == GLOBAL) return emu_tb16_k<GLOBAL>(K, qa0, la0, tb0, lb0, qa1, la1, tb1, lb1, alpha, M, go, ge, pad_score, score, nfrag, f0, f1, cap);
   return -1;
 }
+
+// the level plan of the streaming global kernel (dp_core.cuh), for the property test
+extern "C" void emu_levels(int P, int max_rows, int go, int ge, int maxabs, int maxpos, int *out3) {
+  const Mm16gLevels L = mm16g_levels(P, max_rows, go, ge, maxabs, maxpos);
+  out3[0] = L.n; out3[1] = L.lvl0; out3[2] = L.step;
+}

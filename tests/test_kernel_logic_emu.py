@@ -267,3 +267,33 @@ def test_tb16_logic_vs_oracle(emu, oracle_port):
         got = emu_tb16(emu, mode, K, p0, p1, alpha, M, go, ge)
         for h, (sa, sb) in enumerate((p0, p1)):
             assert got[h] == chk.align_raw(mode, sa, sb, alpha, M, go, ge), (it, mode, K, h, sa, sb, go, ge)
+
+
+def test_level_plan_invariants(emu):
+    """mm16g_levels: every level of the staircase keeps a pair's values inside the biased 16-bit range, and a step is
+    large enough for the injected constant to dominate everything the previous pair left behind"""
+    rng = random.Random(5)
+    out = (C.c_int * 3)()
+    seen_many = 0
+    for _ in range(4000):
+        K = rng.choice([2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16])
+        P = 32 * K
+        rows = rng.choice([32, 48, 96, 272, 528, 1040])
+        ge = -rng.randint(0, 4)
+        go = -rng.randint(0, 12)
+        maxpos = rng.randint(0, 6)
+        maxabs = max(1, maxpos, rng.randint(0, 8), -go, -ge)
+        emu.emu_levels(C.c_int(P), C.c_int(rows), C.c_int(go), C.c_int(ge), C.c_int(maxabs), C.c_int(maxpos), out)
+        n, lvl0, step = out[0], out[1], out[2]
+        W = (P + rows + 12) * (maxabs + abs(ge))
+        assert n >= 1
+        if n == 1:
+            assert lvl0 == 0 and step == 0          # every pair reset explicitly, values centred as before
+            continue
+        seen_many += 1
+        assert W <= 16000 and go <= ge
+        U = (min(P, rows + 1) + 3) * (maxpos + 2 * abs(ge))     # d diagonal steps add at most d * (max S + 2|g|) in drift form
+        top = lvl0 + (n - 1) * step
+        assert lvl0 - W >= -16000 and top + U <= 16000
+        assert step >= U + abs(go - ge) + abs(go + ge)
+    assert seen_many > 1000
