@@ -1065,10 +1065,28 @@ static int pairs_run(PairsRun &R, int mode, const char *a, const long long *a_of
 // download of chunk c-1 overlap the kernels of chunk c.  Every chunk is a complete job of its own (plan, scratch,
 // fragment pool); the caller stitches the outputs together.  Blocks go back to the allocation cache only after every
 // stream has been synchronised (the chunks' PairsRun objects outlive the pipeline).
-static int pairs_chunks(int n) {
-  const int per = g.opt.pairs_chunk;
-  if (per <= 0 || n < 2 * per) return 1;
-  return (int)std::min<long long>(16, ((long long)n + per - 1) / per);
+// Chunk boundaries: nothing overlaps the first chunk's upload and the last chunk's download, so the pipeline starts with a
+// quarter-size chunk, grows by 1.6x per chunk (an upload takes ~0.6 of the kernel time of the same pairs, so the next chunk has
+// arrived when the current one finishes) up to the nominal size, and ends with a quarter-size chunk.  At most 16 chunks.
+static std::vector<int> pairs_chunk_bounds(int n) {
+  const long long per = g.opt.pairs_chunk;
+  std::vector<int> b{0};
+  if (per <= 0 || n < 2 * per) { b.push_back(n); return b; }
+  long long s = std::max<long long>(per / 4, 1), pos = 0;
+  while (pos < n) {
+    long long take = std::min<long long>(s, n - pos);
+    if (n - pos - take < per / 8) take = n - pos;          // no crumb at the end
+    pos += take;
+    b.push_back((int)pos);
+    s = std::min<long long>(per, s * 8 / 5 + 1);
+  }
+  const int last = b[b.size() - 1] - b[b.size() - 2];
+  if (last > per / 2) b.insert(b.end() - 1, n - (int)std::max<long long>(per / 4, 1));
+  if (b.size() - 1 > 16) {                                   // pinned counter slots: 16 chunks
+    b.assign(1, 0);
+    for (int c = 1; c <= 16; ++c) b.push_back((int)((long long)n * c / 16));
+  }
+  return b;
 }
 static int pairs_chunk_begin(PairsRun &R, int c) {
   R.st = (c & 1) ? g.stream2 : g.stream;
@@ -1095,11 +1113,12 @@ int abv_align_pairs(int mode, const char *a, const long long *a_off, const char 
   if ((rc = ctx_init())) return rc;
   for (double &v : t_timing) v = 0;
   cudaStream_t st = g.stream;
-  if (const int C = pairs_chunks(n); C > 1) {
+  if (const std::vector<int> bounds = pairs_chunk_bounds(n); bounds.size() > 2) {
     // pipeline of chunks: enqueue two ahead, then per chunk wait, download, enqueue the next one
+    const int C = (int)bounds.size() - 1;
     std::vector<std::unique_ptr<PairsRun>> Rs;
     for (int c = 0; c < C; ++c) Rs.emplace_back(new PairsRun());
-    auto lo_of = [&](int c) { return (int)((long long)n * c / C); };
+    auto lo_of = [&](int c) { return bounds[c]; };
     auto enqueue = [&](int c) -> int {
       PairsRun &Rc = *Rs[c];
       Rc.max_la = R.max_la; Rc.max_lb = R.max_lb;
@@ -1181,7 +1200,7 @@ int abv_align_pairs(int mode, const char *a, const long long *a_off, const char 
 // -------------------------------------------------------------------------------------------------
 // The two host-side string builders that follow the aligner in the pipeline, on the device:
 //   gapped rows  (ambivert.py:95-111 / :136-152)  and  merged read (ambivert.py:324-327)
-// The pipelined form of assemble_impl for large jobs (see pairs_chunks): per chunk alignment + traceback, sizing, scan, assembly
+// The pipelined form of assemble_impl for large jobs (see pairs_chunk_bounds): per chunk alignment + traceback, sizing, scan, assembly
 // on the chunk's stream; downloads on the download stream.  Returns ABV_RETRY_WHOLE when a chunk's fragment pool or the
 // caller's output buffer is too small: the caller then runs the job in one piece, which sizes the pool exactly and reports errors.
 constexpr int ABV_RETRY_WHOLE = -1000;
@@ -1192,13 +1211,14 @@ struct AsmChunk {
   cudaEvent_t done = nullptr;
   ~AsmChunk() { if (done) cudaEventDestroy(done); }
 };
-static int assemble_chunked(int C, int what, int mode, const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
+static int assemble_chunked(const std::vector<int> &bounds, int what, int mode, const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
                             const Scoring &sc, int max_la, int max_lb, int minimum_overlap, int *scores, int *status, int *start_a,
                             int *start_b, long long *out_off, char *out1, char *out2, long long out_cap, long long *out_total) {
   int rc;
+  const int C = (int)bounds.size() - 1;
   std::vector<std::unique_ptr<AsmChunk>> Cs;
   for (int c = 0; c < C; ++c) Cs.emplace_back(new AsmChunk());
-  auto lo_of = [&](int c) { return (int)((long long)n * c / C); };
+  auto lo_of = [&](int c) { return bounds[c]; };
   auto drain = [&]() { cudaStreamSynchronize(g.stream); cudaStreamSynchronize(g.stream2); cudaStreamSynchronize(g.stream3); };
   auto params = [&](AsmChunk &K, int nc) {
     AssembleParams q{};
@@ -1305,8 +1325,8 @@ static int assemble_impl(int what, int mode, const char *a, const long long *a_o
   if ((rc = ctx_init())) return rc;
   for (double &v : t_timing) v = 0;
   cudaStream_t st = g.stream;
-  if (const int C = pairs_chunks(n); C > 1) {
-    rc = assemble_chunked(C, what, mode, a, a_off, b, b_off, n, sc, R.max_la, R.max_lb, minimum_overlap, scores, status, start_a, start_b,
+  if (const std::vector<int> bounds = pairs_chunk_bounds(n); bounds.size() > 2) {
+    rc = assemble_chunked(bounds, what, mode, a, a_off, b, b_off, n, sc, R.max_la, R.max_lb, minimum_overlap, scores, status, start_a, start_b,
                           out_off, out1, out2, out_cap, out_total);
     if (rc != ABV_RETRY_WHOLE) return rc;
     for (double &v : t_timing) v = 0;
