@@ -35,7 +35,11 @@ constexpr int kHotUnroll = ABV_UNROLL;   // steps of the steady-state loop unrol
 #ifndef ABV_SWITCH_UNROLL
 #define ABV_SWITCH_UNROLL 2
 #endif
-constexpr int kSwitchUnroll = ABV_SWITCH_UNROLL;   // steps of the pair-switching segments unrolled together (code size: instruction cache)
+constexpr int kSwitchUnroll = ABV_SWITCH_UNROLL;
+#ifndef ABV_INJ_UNROLL
+#define ABV_INJ_UNROLL 4   // measured: 1: 8.065, 2: 8.040, 4: 8.084, 8: 8.088 TCUPS
+#endif
+constexpr int kInjUnroll = ABV_INJ_UNROLL;         // the same for the (lighter) switching segments of injected pairs   // steps of the pair-switching segments unrolled together (code size: instruction cache)
 #ifndef ABV_MINB8
 #define ABV_MINB8 3   // measured on B200: 3 CTAs (24 warps, <= 85 registers) beat 4 (32 warps, 64 registers) by 4 %; 2 and 5 are slower
 #endif
@@ -1634,7 +1638,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
             if (cs1 >= s && cs1 < stop) stop = cs1 + 1;
             if (cs2 >= s && cs2 < stop) stop = cs2 + 1;
             if (switching && inj) {
-#pragma unroll kSwitchUnroll
+#pragma unroll kInjUnroll
               for (; s < stop; ++s) {
                 if (lane == s) tb_off = bufoff - lane;
                 body(s);
