@@ -36,6 +36,10 @@ constexpr int kHotUnroll = ABV_UNROLL;   // steps of the steady-state loop unrol
 #define ABV_SWITCH_UNROLL 2
 #endif
 constexpr int kSwitchUnroll = ABV_SWITCH_UNROLL;
+#ifndef ABV_GL_SW_UNROLL
+#define ABV_GL_SW_UNROLL 1
+#endif
+constexpr int kGlSwitchUnroll = ABV_GL_SW_UNROLL;   // glocal (deferred last rows): steps of a switching segment unrolled together
 #ifndef ABV_INJ_UNROLL
 #define ABV_INJ_UNROLL 4   // measured: 1: 8.065, 2: 8.040, 4: 8.084, 8: 8.088 TCUPS
 #endif
@@ -1519,7 +1523,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
             if (switching) {
               // lane s switches to this pair at step s and computes its row 0 through the common row (dp_core.cuh,
               // MM16G_NO_EGAP); the lanes still on the previous pair park its last rows
-#pragma unroll 1
+#pragma unroll kGlSwitchUnroll
               for (; s < stop; ++s) {
                 uint32_t h_sh, e_sh, gope = gop2;
                 exchange(h_sh, e_sh);
