@@ -469,8 +469,8 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   const int a1 = sc.alpha + 1;
   bool packed_ok = g.opt.path != ABV_PATH_WF32 && n_t > 0 && a1 * a1 <= 64 &&
                    (mode == ABV_GLOBAL || mode == ABV_LOCAL || mode == ABV_GLOCAL);
-  // >= 32: the streaming kernel sweeps at least 32 rows per pair; > max_lt: one pad row after every pair (its separator row, mm16g_levels)
-  const int tp_stride = std::max(32, (max_lt + 1 + 15) & ~15);
+  // the streaming kernel sweeps at least 32 rows per pair, plus one pad row after every pair (its separator row, mm16g_levels)
+  const int tp_stride = (std::max(max_lt, MM16G_MIN_ROWS) + 1 + 15) & ~15;
   std::vector<std::vector<int>> lists(MM16_NK);
   std::vector<int> wf32_list;
   for (int i = 0; i < n_q; ++i) {

@@ -266,7 +266,7 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
   }
   int max_lt = 1;
   for (int i = 0; i < n_pairs; ++i) max_lt = std::max(max_lt, std::max(l1s[i], l2s[i]));
-  const int stride = std::max(32, (max_lt + 1 + 15) & ~15);
+  const int stride = (std::max(max_lt, MM16G_MIN_ROWS) + 1 + 15) & ~15;     // as align_abi.cu job_prepare: room for the separator row
   std::vector<unsigned char> sm(64 + 3 * stride, 0);
   const int zero = 0, tbuf0 = 64;
   auto fill = [&](int buf, int pi) {
@@ -287,7 +287,8 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
   bool explicit_reset = true, inject = false;    // how lanes enter the current pair; lane 0 on a separator row
   const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;
   uint32_t Hp[32][K], F[32][K], S[32][KP], hleft[32], h_out[32], e_out[32];
-  int tb_off[32];
+  int tb_off[32], buf_lo[32], buf_hi[32];
+  for (int t = 0; t < 32; ++t) { buf_lo[t] = zero; buf_hi[t] = zero + 64; }
   int slots[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
   for (int t = 0; t < 32; ++t) {
     for (int k = 0; k < K; ++k) { Hp[t][k] = b16::biased(0, 0); F[t][k] = b16::biased(0, 0); }
@@ -326,6 +327,7 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
     if (sw >= 0) {
       const int t = sw;
       tb_off[t] = bufoff - t;
+      buf_lo[t] = bufoff >= tbuf0 ? bufoff : zero; buf_hi[t] = bufoff >= tbuf0 ? bufoff + stride : zero + 64;
       if (!GL && explicit_reset) {
         for (int k = 0; k < K; ++k) { Hp[t][k] = Hc; F[t][k] = Ec; }
         hleft[t] = t ? Hc : H00;
@@ -336,7 +338,9 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
     h_sh[0] = Hc; e_sh[0] = Ec;
     if (inject) { const uint32_t up = b16::addend(lv.step, lv.step); h_sh[0] = H00 + up; e_sh[0] = Hc + up; }
     for (int t = 0; t < 32; ++t) {
-      const int code = sm.at(tb_off[t] + s);
+      const int at = tb_off[t] + s;
+      if (at < buf_lo[t] || at >= buf_hi[t]) throw 2;      // a row read outside the buffer of the pair the lane is on
+      const int code = sm.at(at);
       if (code >= ncodes) throw 1;
       load_S<KP>(&lut[(size_t)code * P], t, S[t]);
       uint32_t gope = gop2;

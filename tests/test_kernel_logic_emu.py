@@ -165,6 +165,8 @@ def test_streaming_logic_vs_oracle(emu, oracle_port, mode):
         q = bytes(rng.choice([0, 1, 2, 3, 0, 1, 2, 3, 4]) for _ in range(lq))
         n_pairs = rng.choice([1, 2, 3, 4, 7, 12])
         lens = sorted([max(lmin, rng.choice([1, 2, 5, 31, 32, 33, rng.randint(lmin, 300), rng.randint(150, 300)])) for _ in range(2 * n_pairs)], reverse=True)
+        if mode == O.GLOBAL and rng.random() < 0.15:
+            lens = sorted([rng.randint(1, 31) for _ in lens], reverse=True)   # only short targets: 32-step pairs, separator row at index 32
         if rng.random() < 0.3:
             lens[1] = lens[0]                                # equal lengths: both halves end on the same row
         if rng.random() < 0.5:
