@@ -240,6 +240,9 @@ def cluster_measurement(n_pairs):
     (f, fo), (r, ro) = synth.read_pairs_packed(n_pairs, seed=0xF2)
     dup = np.random.default_rng(3).integers(0, n_pairs // 4, n_pairs)          # ~4 copies per unique pair, shuffled
     f2, r2 = f.reshape(n_pairs, -1)[dup].reshape(-1), r.reshape(n_pairs, -1)[dup].reshape(-1)
+    import torch
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()   # host buffers are pinned, as for the headline e2e
+    f2, r2 = pin(f2), pin(r2)
     B.cluster_pairs((f2[:150000], fo[:1001]), (r2[:150000], ro[:1001]))
     best = None
     for _ in range(3):
