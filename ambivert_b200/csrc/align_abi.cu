@@ -1082,6 +1082,7 @@ static std::vector<int> pairs_chunk_bounds(int n) {
   }
   const int last = b[b.size() - 1] - b[b.size() - 2];
   if (last > per / 2) b.insert(b.end() - 1, n - (int)std::max<long long>(per / 4, 1));
+  b.erase(std::unique(b.begin(), b.end()), b.end());          // no empty chunk (tiny chunk sizes)
   if (b.size() - 1 > 16) {                                   // pinned counter slots: 16 chunks
     b.assign(1, 0);
     for (int c = 1; c <= 16; ++c) b.push_back((int)((long long)n * c / 16));
@@ -1624,6 +1625,13 @@ int abv_get_timing(double *out, int n) {
   n = std::min(n, 8);
   for (int i = 0; i < n; ++i) out[i] = t_timing[i];
   return n;
+}
+
+int abv_pairs_chunk_bounds(int n, int *bounds, int cap) {
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  const std::vector<int> b = pairs_chunk_bounds(std::max(n, 0));
+  for (int i = 0; i < (int)b.size() && i < cap && bounds; ++i) bounds[i] = b[i];
+  return (int)b.size();
 }
 
 int abv_int_peak(int which, int iters, double *lane_ops_per_s, double *sm_clock_mhz) {

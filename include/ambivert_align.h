@@ -294,6 +294,9 @@ int abv_get_timing(double *out, int n);
  *         8: the streaming kernel's cell: 1 add + VIMNMX3.S16x2 + 2 VIADDMNMX.S16x2 (4 lane-ops per cell pair)
  */
 int abv_int_peak(int which, int iters, double *lane_ops_per_s, double *sm_clock_mhz);
+/* diagnostics (host logic only, no device needed): the chunk boundaries the one-to-one jobs would use for n pairs
+ * ("pairs_chunk" option); writes min(count, cap) entries, returns the count (chunks + 1; 2 = one piece) */
+int abv_pairs_chunk_bounds(int n, int *bounds, int cap);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

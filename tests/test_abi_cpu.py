@@ -98,3 +98,34 @@ def test_argument_validation_needs_no_gpu():
     with pytest.raises(B.AlignError) as e:
         B.best_hits([b""], [b"ACGT"])
     assert e.value.code == B.ERR_ARGS
+
+
+def test_chunk_bounds_of_the_pair_pipeline():
+    """host logic of the chunk pipeline of the one-to-one jobs (align_abi.cu, pairs_chunk_bounds): the chunks tile [0, n) in
+    order, there are at most 16, small jobs stay in one piece, and the first and last chunks are the small ones"""
+    import random
+
+    import ambivert_b200.align as A
+    lib = A.align_c
+    lib.abv_pairs_chunk_bounds.restype = C.c_int
+    lib.abv_set_option.argtypes = [C.c_char_p, C.c_int]
+    buf = (C.c_int * 64)()
+    rng = random.Random(3)
+    try:
+        for per in (0, 1, 37, 1000, 200000):
+            assert lib.abv_set_option(b"pairs_chunk", per) == 0
+            for n in [0, 1, 2, per, max(2 * per - 1, 0), 2 * per, 2 * per + 1, 5 * per, 1000000, 40 * max(per, 1)] + [rng.randint(0, 3000000) for _ in range(50)]:
+                k = lib.abv_pairs_chunk_bounds(n, buf, 64)
+                b = list(buf[:k])
+                assert 2 <= k <= 17 and b[0] == 0 and b[-1] == n, (per, n, b)
+                assert all(x <= y for x, y in zip(b, b[1:])), (per, n, b)
+                if per == 0 or n < 2 * per:
+                    assert k == 2                                   # one piece
+                else:
+                    sizes = [y - x for x, y in zip(b, b[1:])]
+                    assert k > 2 and min(sizes) > 0, (per, n, b)
+                    if k - 1 < 16:
+                        assert sizes[0] <= max(sizes) and sizes[-1] <= max(sizes)
+                        assert max(sizes) <= max(per, 1) + max(per // 8, 1), (per, n, sizes)
+    finally:
+        lib.abv_set_option(b"pairs_chunk", 200000)
