@@ -397,6 +397,7 @@ struct abv_job {
   DevMem q_codes, q_off, t_codes, t_off, map, matrix, matrix_ext, tp_codes, tp_meta, lists, counters;
   DevMem best_score, best_idx, all_scores, chunk_scores, border, best_key;
   int tp_stride = 0, n_pairs = 0, a1 = 0, max_lt = 0, max_lq = 0, maxabs = 1, maxpos = 0;
+  int n_pairs_stream = 0;          // leading target pairs (longest first) the streaming kernel takes; the rest goes to mm16_kernel
   struct Bucket { int K, n, offset; double cells; cudaEvent_t e0, e1; bool streaming; };
   std::vector<Bucket> buckets;     // packed-kernel launches (one per K class), lists at `offset`
   ~abv_job() { for (auto &b : buckets) { if (b.e0) cudaEventDestroy(b.e0); if (b.e1) cudaEventDestroy(b.e1); } }
@@ -427,9 +428,8 @@ int mm_validate(int mode, const char *q, const long long *q_off, int n_q, const 
 
 // drift-normalised values carry an extra |ge| per column and row (dp_core.cuh, mm16d_row); glocal
 // keeps half the range free for its minus-infinity sentinel
-bool packed_exact_streaming(int mode, int P, int max_lt, int maxabs, int ge, int min_lt) {
+bool packed_exact_streaming(int mode, int P, int max_lt, int maxabs, int ge) {
   if (mode != ABV_GLOBAL && mode != ABV_GLOCAL) return false;
-  if (mode == ABV_GLOCAL && min_lt < MM16G_MIN_ROWS) return false;   // deferred last rows: a pair's capture precedes the next pair's last rows (kernels.cuh)
   return (long long)(P + max_lt + 12) * (maxabs + std::abs(ge)) <= (mode == ABV_GLOCAL ? p16::P16_LIMIT : b16::LIMIT);
 }
 
@@ -471,6 +471,26 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
                    (mode == ABV_GLOBAL || mode == ABV_LOCAL || mode == ABV_GLOCAL);
   // the streaming kernel sweeps at least 32 rows per pair, plus one pad row after every pair (its separator row, mm16g_levels)
   const int tp_stride = (std::max(max_lt, MM16G_MIN_ROWS) + 1 + 15) & ~15;
+  // glocal streams only target pairs whose members have >= 32 rows (deferred last rows, kernels.cuh): the targets are paired
+  // longest first, so those are the leading pairs; the few short ones at the end take the first-generation kernel with the
+  // next even strip width, and both kernels fold into the same per-query best key
+  const int n_pairs_all = (n_t + 1) / 2;
+  int n_pairs_stream = n_pairs_all;
+  if (mode == ABV_GLOCAL) {
+    int n_long = 0;
+    for (int j = 0; j < n_t; ++j) n_long += (t_off[j + 1] - t_off[j]) >= MM16G_MIN_ROWS;
+    n_pairs_stream = n_long / 2 + (((n_long & 1) && n_long == n_t) ? 1 : 0);
+  }
+  J.n_pairs_stream = n_pairs_stream;
+  auto stream_ok = [&](int K) {
+    if (g.opt.global_v1 || n_pairs_stream == 0) return false;
+    if (!packed_exact_streaming(mode, 32 * K, tp_stride, maxabs, sc.ge)) return false;
+    if (n_pairs_stream < n_pairs_all) {
+      const int K2 = K + (K & 1);
+      if (!packed_exact(mode, 32 * K2, tp_stride, maxabs) || mm16_smem_layout(K2, a1, tp_stride).total > 100 * 1024) return false;
+    }
+    return true;
+  };
   std::vector<std::vector<int>> lists(MM16_NK);
   std::vector<int> wf32_list;
   for (int i = 0; i < n_q; ++i) {
@@ -479,7 +499,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
     if (packed_ok) {
       for (int k = 0; k < MM16_NK; ++k) {
         const int K = MM16_KS[k];
-        if (K % 2 && !(!g.opt.global_v1 && packed_exact_streaming(mode, 32 * K, tp_stride, maxabs, sc.ge, min_lt))) continue;
+        if (K % 2 && !stream_ok(K)) continue;
         if (32 * K >= lq) { slot = k; break; }
       }
       if (slot >= 0) {
@@ -499,7 +519,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
       double qlen = 0;
       for (int i : lists[k]) qlen += (double)(q_off[i + 1] - q_off[i]);
       abv_job::Bucket b{MM16_KS[k], (int)lists[k].size(), (int)flat.size(), qlen * (double)(t_off[n_t] - t_off[0]), nullptr, nullptr,
-                        !g.opt.global_v1 && packed_exact_streaming(mode, 32 * MM16_KS[k], tp_stride, maxabs, sc.ge, min_lt)};
+                        stream_ok(MM16_KS[k])};
       CU(cudaEventCreate(&b.e0));
       CU(cudaEventCreate(&b.e1));
       J.buckets.push_back(b);
@@ -512,7 +532,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   CU(cudaMemcpyAsync(J.lists.p, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));
   J.h2d_bytes += sizeof(int) * flat.size();
-  J.n_counters = (int)J.buckets.size() + 64;
+  J.n_counters = 2 * (int)J.buckets.size() + 64;
   CU(J.counters.alloc(sizeof(unsigned long long) * J.n_counters));
 
   // ---- target pairs for the packed kernel: sort by length, pair neighbours ----------------------
@@ -567,6 +587,8 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   CU(cudaStreamSynchronize(st));
   // launches per run: counter memset is not a kernel
   J.launches_per_run = (int)J.buckets.size();
+  if (J.n_pairs_stream < J.n_pairs)
+    for (const auto &b : J.buckets) J.launches_per_run += b.streaming ? 1 : 0;      // the short target pairs: a second launch
   if (J.n_wf32 > 0 && n_t > 0) {
     const long long max_chunk_scores = 32ll << 20;
     long long rows = std::max<long long>(1, std::min<long long>(J.n_wf32, max_chunk_scores / n_t));
@@ -613,7 +635,14 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
       p.lv_n = lv.n; p.lv0 = lv.lvl0; p.lv_step = lv.step;
     }
     CU(cudaEventRecord(b.e0, st));
-    if ((rc = mm16_launch(J.mode, b.K, b.streaming, st, p, launched))) return rc;
+    if (b.streaming && J.n_pairs_stream < J.n_pairs) {
+      Mm16Params r = p;                                  // the short target pairs at the end of the list
+      r.tp_codes += (size_t)J.n_pairs_stream * J.tp_stride; r.tp_meta += J.n_pairs_stream; r.n_pairs = J.n_pairs - J.n_pairs_stream;
+      r.q_counter = reinterpret_cast<unsigned int *>(J.counters.as<unsigned long long>() + ci++);
+      p.n_pairs = J.n_pairs_stream;
+      if ((rc = mm16_launch(J.mode, b.K, true, st, p, launched))) return rc;
+      if ((rc = mm16_launch(J.mode, b.K + (b.K & 1), false, st, r, launched))) return rc;
+    } else if ((rc = mm16_launch(J.mode, b.K, b.streaming, st, p, launched))) return rc;
     CU(cudaEventRecord(b.e1, st));
   }
   if (!J.buckets.empty()) {   // seed rule + unpack, over the queries the packed kernels served

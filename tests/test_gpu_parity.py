@@ -493,6 +493,38 @@ def test_streaming_kernels_many_pairs_vs_wf32(B):
                 assert (bs == np.where(hit, best, 0)).all() and (bi == np.where(hit, first, -1)).all(), (it, mode)
 
 
+def test_glocal_short_targets_beside_the_streaming_kernel(B):
+    """glocal: the streaming kernel takes the target pairs of >= 32 rows, the first-generation kernel the short ones at
+    the end of the length-sorted list; both fold into one best key per query (first maximum in ORIGINAL target order)"""
+    rng = random.Random(808)
+    for n_long, n_short in ((40, 7), (41, 6), (41, 1), (1, 9), (0, 5), (33, 0)):
+        targets = [rand_dna(rng, rng.randint(32, 260)) for _ in range(n_long)] + [rand_dna(rng, rng.randint(2, 31)) for _ in range(n_short)]
+        targets += targets[:3]                               # duplicates: equal scores, the lower original index must win
+        rng.shuffle(targets)
+        queries = [rand_dna(rng, L) for L in (10, 40, 70, 100, 150, 200, 230, 280)]
+        queries += [mutate(rng, (t * 8)[:rng.randint(20, 250)], 2) for t in targets[:12]]
+        q = [s.encode() for s in queries]
+        t = [s.encode() for s in targets]
+        B.set_option("path", B.PATH_WF32)
+        try:
+            want = B.score_matrix(q, t, O.GLOCAL)
+            want_hits = B.best_hits(q, t, O.GLOCAL, 0)
+        finally:
+            B.set_option("path", B.PATH_AUTO)
+        got = B.score_matrix(q, t, O.GLOCAL)
+        assert (got == want).all(), (n_long, n_short, np.argwhere(got != want)[:3])
+        with B.BestHitsJob(q, t, O.GLOCAL, 0) as job:
+            job.launch()
+            bs, bi = job.fetch()
+            ks = {r["K"] for r in job.profile()}
+            launches = job.kernel_launches()
+        assert (bs == want_hits[0]).all() and (bi == want_hits[1]).all(), (n_long, n_short)
+        if n_long >= 2:
+            assert ks & {3, 5, 7, 9}, ks                     # odd strip widths exist only in the streaming kernel
+        if n_long >= 2 and n_short:
+            assert launches >= 2 * len(ks) + 1               # per strip width: streaming launch + short-target launch; + finalize
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_legacy_single_calls_fuzz(A, oracle_port, mode):
     """the lean one-launch path behind the reference's own symbols: the column blocks of the one pair are
