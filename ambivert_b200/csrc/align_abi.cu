@@ -187,6 +187,23 @@ int check_seqs(const char *buf, const long long *off, int n, const char *what, i
   return ABV_OK;
 }
 
+// Symbols outside the alphabet: the reference indexes score_matrix[a*alpha_len + b] with whatever the map or the caller
+// supplies (helpers.h:26-32, global_align.c:148), i.e. reads past the matrix.  The batched calls reject such input.  A map
+// whose entries are all < alpha_len (DNA_MAP, PROT_MAP) needs no look at the data; otherwise (make_map(s, None): unknown ==
+// alpha_len, or raw codes) the bytes are scanned.
+int check_symbols(const char *buf, const long long *off, int n, const Scoring &sc, const char *what) {
+  if (n <= 0) return ABV_OK;
+  bool bad[256];
+  bool any = false;
+  for (int i = 0; i < 256; ++i) { bad[i] = (sc.map256 ? sc.map256[i] : i) >= sc.alpha; any = any || bad[i]; }
+  if (!any || (sc.map256 && sc.alpha > 255)) return ABV_OK;
+  const unsigned char *p = (const unsigned char *)buf + off[0], *e = (const unsigned char *)buf + off[n];
+  unsigned hit = 0;
+  for (; p < e; ++p) hit |= bad[*p];
+  if (hit) return fail(ABV_ERR_ARGS, "%s: a symbol maps outside the alphabet (code >= alpha_len %d; the reference reads past its score matrix there)", what, sc.alpha);
+  return ABV_OK;
+}
+
 int check_mode_lengths(int mode, int min_la, int min_lb) {
   if (mode < 0 || mode > 3) return fail(ABV_ERR_ARGS, "unknown mode %d", mode);
   if (mode == ABV_GLOCAL && min_lb < 2) return fail(ABV_ERR_UNDEFINED, "glocal with a target of length 1 is undefined in the reference (glocal_align.c:138,172)");
@@ -402,6 +419,7 @@ struct abv_job {
   std::vector<Bucket> buckets;     // packed-kernel launches (one per K class), lists at `offset`
   ~abv_job() { for (auto &b : buckets) { if (b.e0) cudaEventDestroy(b.e0); if (b.e1) cudaEventDestroy(b.e1); } }
   int n_wf32 = 0, wf32_offset = 0; // queries served by the 32-bit kernel, list at `wf32_offset`
+  int wf32_blocks = 0;             // its grid, fixed when `border` was sized (the option may change before the launch)
   int n_counters = 0;
   int launches_per_run = 0;
   cudaStream_t last_stream = nullptr;
@@ -423,6 +441,8 @@ int mm_validate(int mode, const char *q, const long long *q_off, int n_q, const 
   if ((rc = check_seqs(q, q_off, n_q, "query", max_lq, min_lq))) return rc;
   if ((rc = check_seqs(t, t_off, n_t, "target", max_lt, min_lt))) return rc;
   if (n_q > 0 && n_t > 0 && (rc = check_mode_lengths(mode, min_lq, min_lt))) return rc;
+  if ((rc = check_symbols(q, q_off, n_q, sc, "query"))) return rc;
+  if ((rc = check_symbols(t, t_off, n_t, sc, "target"))) return rc;
   return ABV_OK;
 }
 
@@ -581,8 +601,8 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
     const long long max_chunk_scores = 32ll << 20;
     long long rows = std::max<long long>(1, std::min<long long>(J.n_wf32, max_chunk_scores / n_t));
     if (!all_scores) CU(J.chunk_scores.alloc(sizeof(int) * (size_t)(rows * n_t)));
-    const int grid = wf32_grid(rows * n_t, 0);
-    CU(J.border.alloc(sizeof(int) * 2 * (size_t)max_lt * grid * WF32_WARPS));
+    J.wf32_blocks = wf32_grid(rows * n_t, 0);
+    CU(J.border.alloc(sizeof(int) * 2 * (size_t)max_lt * J.wf32_blocks * WF32_WARPS));
   }
   CU(cudaStreamSynchronize(st));
   // launches per run: counter memset is not a kernel
@@ -655,7 +675,7 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
   if (J.n_wf32 > 0) {
     const long long max_chunk_scores = 32ll << 20;
     const long long rows_per = std::max<long long>(1, std::min<long long>(J.n_wf32, max_chunk_scores / J.n_t));
-    const int grid = wf32_grid(rows_per * J.n_t, 0);
+    const int grid = J.wf32_blocks;        // the grid `border` was sized for in job_prepare
     int chunk = 0;
     for (long long base = 0; base < J.n_wf32; base += rows_per, ++chunk) {
       const long long rows = std::min<long long>(rows_per, J.n_wf32 - base);
@@ -880,7 +900,11 @@ int abv_job_profile(abv_job *job, double *out, int max_rows) {
 }
 int abv_job_kernel_launches(const abv_job *job) { return job ? job->launches_per_run : 0; }
 void abv_job_free(abv_job *job) {
+  if (!job) return;
   std::lock_guard<std::recursive_mutex> lk(g.mu);
+  // abv_best_hits_launch is asynchronous and may have run on a caller's stream: the job's blocks go back to the
+  // allocation cache (and from there to the next job's uploads on the library's stream) only once those kernels are done
+  if (job->last_stream && cudaStreamSynchronize(job->last_stream) != cudaSuccess) cudaGetLastError();
   delete job;
 }
 
@@ -968,6 +992,8 @@ static int pairs_validate(int mode, const char *a, const long long *a_off, const
   if ((rc = check_seqs(b, b_off, n, "sequence b", max_lb, min_lb))) return rc;
   if (mode < 0 || mode > 3) return fail(ABV_ERR_ARGS, "unknown mode %d", mode);
   if (n > 0 && (rc = check_mode_lengths(mode, min_la, min_lb))) return rc;
+  if ((rc = check_symbols(a, a_off, n, sc, "sequence a"))) return rc;
+  if ((rc = check_symbols(b, b_off, n, sc, "sequence b"))) return rc;
   return ABV_OK;
 }
 
@@ -1155,13 +1181,15 @@ int abv_align_pairs(int mode, const char *a, const long long *a_off, const char 
       int r2;
       if ((r2 = pairs_chunk_begin(Rc, c))) return r2;
       const int lo = lo_of(c), hi = lo_of(c + 1);
-      return pairs_run(Rc, mode, a, a_off + lo, b, b_off + lo, hi - lo, sc, frag_cap, true);
+      // a chunk's pool: twice its share of the caller's pool (fragments per pair vary little over >= 50k pairs), not the whole of it
+      const long long share = std::min<long long>(frag_cap, 2 * (frag_cap / n + 1) * (long long)(hi - lo) + 4096);
+      return pairs_run(Rc, mode, a, a_off + lo, b, b_off + lo, hi - lo, sc, share, true);
     };
     auto drain = [&]() { cudaStreamSynchronize(g.stream); cudaStreamSynchronize(g.stream2); cudaStreamSynchronize(g.stream3); };
     for (int c = 0; c < std::min(2, C); ++c)
       if ((rc = enqueue(c))) { drain(); return rc; }
     long long base = 0;
-    bool overflow = false;
+    bool overflow = false, chunk_overflow = false;
     double d2h = 0, h2d = 0, cells = 0, ms_up = 0, ms_k = 0, ms_down = 0;
     ABV_TRACE("align_pairs: %d chunks, first two enqueued", C);
     for (int c = 0; c < C; ++c) {
@@ -1174,21 +1202,25 @@ int abv_align_pairs(int mode, const char *a, const long long *a_off, const char 
       ABV_TRACE("chunk %d: next enqueued", c);
       Rc.total = *Rc.pin_total;
       const long long total = (long long)Rc.total;
+      if (total > Rc.pool) chunk_overflow = true;
       if (total > Rc.pool || base + total > frag_cap) overflow = true;
-      if (!overflow) {
+      {
         const auto t0 = std::chrono::steady_clock::now();
-        // the chunk has finished (synchronised above): its results leave on the download stream, beside the other chunks' kernels
+        // the chunk has finished (synchronised above): its results leave on the download stream, beside the other chunks' kernels.
+        // Scores, starts and counts always (they are valid on ABV_ERR_FRAG_CAP, include/ambivert_align.h); the fragments while they fit.
         CU(cudaMemcpyAsync(scores + lo, Rc.scores.p, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, g.stream3));
         CU(cudaMemcpyAsync(frag_start + lo, Rc.start.p, sizeof(long long) * (size_t)nc, cudaMemcpyDeviceToHost, g.stream3));
         CU(cudaMemcpyAsync(frag_count + lo, Rc.count.p, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, g.stream3));
-        if (total > 0) CU(cudaMemcpyAsync(frags + base, Rc.frags.p, sizeof(FragOut) * (size_t)total, cudaMemcpyDeviceToHost, g.stream3));
+        if (!overflow && total > 0) CU(cudaMemcpyAsync(frags + base, Rc.frags.p, sizeof(FragOut) * (size_t)total, cudaMemcpyDeviceToHost, g.stream3));
         CU(cudaStreamSynchronize(g.stream3));
         if (base)
           for (int i = 0; i < nc; ++i) frag_start[lo + i] += base;         // the chunk's pool starts at `base` of the caller's
         ABV_TRACE("chunk %d: downloaded", c);
         ms_down += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        d2h += 16.0 * nc + 8 + 16.0 * total;
+        d2h += 16.0 * nc + 8 + (overflow ? 0.0 : 16.0 * total);
       }
+      // the chunk is complete on the device and on the host: its scratch goes back to the allocation cache for the chunks to come
+      Rc.dir.release(); Rc.tmp.release(); Rc.border.release(); Rc.frags.release(); Rc.a_raw.release(); Rc.b_raw.release();
       base += total;
       h2d += Rc.h2d; cells += Rc.cells;
       float t0 = 0, t1 = 0;
@@ -1200,8 +1232,11 @@ int abv_align_pairs(int mode, const char *a, const long long *a_off, const char 
     if (frag_total) *frag_total = base;
     t_timing[0] = ms_up; t_timing[1] = ms_k; t_timing[2] = ms_down; t_timing[3] = cells; t_timing[4] = 3 * C;
     t_timing[5] = h2d; t_timing[6] = d2h; t_timing[7] = ms_k;
-    if (overflow) return fail(ABV_ERR_FRAG_CAP, "fragment pool of %lld entries is too small, %lld needed", frag_cap, base);
-    return ABV_OK;
+    if (base > frag_cap) return fail(ABV_ERR_FRAG_CAP, "fragment pool of %lld entries is too small, %lld needed", frag_cap, base);
+    if (!chunk_overflow) return ABV_OK;
+    // the caller's pool is large enough but one chunk's share was not (very uneven fragment counts): run the job in one piece
+    Rs.clear();
+    for (double &v : t_timing) v = 0;
   }
   if ((rc = pairs_run(R, mode, a, a_off, b, b_off, n, sc, frag_cap, false))) return rc;
   CU(cudaMemcpyAsync(scores, R.scores.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));

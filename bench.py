@@ -28,8 +28,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-PACKED_CELL_OPS = 5          # 2 packed adds + 1 max3 + 2 add-max per cell pair
+# lane-ops per packed cell pair of the two kernel generations and the abv_int_peak mix that measures each
+CELL_OPS_STREAMING = 4       # mm16g_kernel: 1 add + VIMNMX3.S16x2 + 2 VIADDMNMX.S16x2          -> abv_int_peak(8)
+CELL_OPS_FIRST_GEN = 5       # mm16_kernel:  2 VIADD.16x2 + VIMNMX3.S16x2 + 2 VIADDMNMX.S16x2   -> abv_int_peak(4)
 MODE_NAMES = {"global": 2, "glocal": 3, "local": 1}
+WORKLOADS = {"config4": (100000, 2000), "config5": (1000000, 10000)}
 
 
 def parse_args():
@@ -39,8 +42,12 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--mode", default="global", choices=list(MODE_NAMES))
-    ap.add_argument("--queries", type=int, default=100000)
-    ap.add_argument("--targets", type=int, default=2000)
+    ap.add_argument("--workload", default="config4", choices=list(WORKLOADS),
+                    help="config4 = BASELINE.json configs[3] (100k amplicons x 2k manifest targets, the headline); "
+                         "config5 = configs[4] (1M x 250 bp amplicons x 10k FASTA targets; meant for --gpus 8)")
+    ap.add_argument("--queries", type=int, default=0, help="override the workload's amplicon count (the label then says so)")
+    ap.add_argument("--targets", type=int, default=0, help="override the workload's target count")
+    ap.add_argument("--glocal-steps", type=int, default=5, help="timed steps of the glocal block (>= 5 unless --no-glocal)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work of one cpu_baseline sample / reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-glocal", action="store_true", help="skip the secondary glocal-mode measurement of the same job")
@@ -50,12 +57,23 @@ def parse_args():
 
 
 def workload(args):
+    """synthetic inputs of SURVEY.md 8(d): config 4 = manifest-style targets of 200-260 bp with soft-masked primers x
+    mutated-copy amplicons; config 5 = 250 bp FASTA targets (seed 0xD5) x amplicons generated the same way"""
     from ambivert_b200 import synth
-    targets = synth.panel_targets(args.targets)
-    queries, source = synth.panel_queries(targets, args.queries)
+    n_q0, n_t0 = WORKLOADS[args.workload]
+    n_q, n_t = args.queries or n_q0, args.targets or n_t0
+    if args.workload == "config5":
+        targets = synth.fasta_targets(n_t)
+        queries, source = synth.panel_queries(targets, n_q, seed=0xD5 + 1)
+        what, cfg = "FASTA targets of 250 bp", "BASELINE.json configs[4]"
+    else:
+        targets = synth.panel_targets(n_t)
+        queries, source = synth.panel_queries(targets, n_q)
+        what, cfg = "manifest targets", "BASELINE.json configs[3]"
+    if (n_q, n_t) != (n_q0, n_t0):
+        cfg = "generator of %s at a NON-STANDARD size (%d x %d is the config)" % (cfg, n_q0, n_t0)
     targets = [t.upper() for t in targets]          # the call site upper-cases the target (ambivert.py:169)
-    name = "hashtable build: %d unique amplicons x %d manifest targets, %s alignment (BASELINE.json configs[3])" % (
-        len(queries), len(targets), args.mode)
+    name = "hashtable build: %d unique amplicons x %d %s, %s alignment (%s)" % (len(queries), len(targets), what, args.mode, cfg)
     return queries, targets, name
 
 
@@ -167,6 +185,43 @@ def reference_arm(args, rank):
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "projected_full_job_s": float(sum(map(len, queries))) * float(sum(map(len, targets))) / (gcups * 1e9)}
     emit(line)
+
+
+def as_shipped_measurement(queries, targets, gpu_score, gpu_idx, n_sample=64):
+    """the reference AS SHIPPED -- its unmodified Python package with its own C extension
+    (oracle/_ref/pkg_cpu, vendored by `make -C oracle ref`), AmpliconData.match_to_reference(threads=ncores): one ctypes call
+    per (amplicon, target) from a multiprocessing.dummy.Pool per amplicon (ambivert.py:461-485).  Run in a subprocess on the
+    package's bundled data and on n_sample amplicons x all targets of this workload; the chosen targets of the sample are
+    compared with the GPU's (min_score 0.1 applied as the reference does, ambivert.py:528)."""
+    import oracle as O
+    import tempfile
+    if not O.as_shipped_available():
+        return {"unavailable": "oracle/_ref/pkg_cpu was not vendored (no /root/reference when build() ran)"}
+    script = os.path.join(ROOT, "oracle", "as_shipped.py")
+    threads = os.cpu_count() or 1
+
+    def run(extra):
+        out = subprocess.run([sys.executable, "-W", "ignore", script, "--threads", str(threads)] + extra, stdout=subprocess.PIPE,
+                             stderr=subprocess.DEVNULL, text=True, timeout=600)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    try:
+        bundled = run(["--bundled"])
+        pick = np.unique(np.linspace(0, len(queries) - 1, min(n_sample, len(queries))).astype(np.int64))
+        with tempfile.TemporaryDirectory() as d:
+            with open(os.path.join(d, "q.txt"), "w") as f:
+                f.write("\n".join(queries[i].decode("ascii") for i in pick))
+            with open(os.path.join(d, "t.txt"), "w") as f:
+                f.write("\n".join(t.decode("ascii") for t in targets))
+            sample = run(["--queries", os.path.join(d, "q.txt"), "--targets", os.path.join(d, "t.txt")])
+    except (subprocess.SubprocessError, ValueError, IndexError, OSError) as e:
+        return {"unavailable": "as-shipped run failed: %r" % (e,)}
+    want = [int(gpu_idx[i]) if gpu_score[i] > 0.1 else -1 for i in pick]
+    return {"value": sample["gcups"], "unit": "GCUPS", "cores": threads, "kind": "reference",
+            "api": sample["api"], "extension": sample["extension"],
+            "sample": "%d amplicons evenly drawn from the workload x all %d targets (%.2e cells, %.1f s)" % (len(pick), len(targets), sample["cells"], sample["seconds"]),
+            "chosen_targets_match_gpu": sample["chosen"] == want,
+            "bundled_test_data": {"value": bundled["gcups"], "unit": "GCUPS", "seconds": bundled["seconds"], "cells": bundled["cells"],
+                                  "what": "%s: %d merged amplicons x %d manifest targets (BASELINE.json configs[0] data)" % (bundled["what"], bundled["amplicons"], bundled["targets"])}}
 
 
 def ncu_traffic(mode, K):
@@ -297,6 +352,25 @@ def variants_measurement(n):
             "records_match_port_on_sample": bool(same)}
 
 
+def parity_sample(bounds, n_want):
+    """query indices drawn from ALL shards: per shard its first and last query and evenly spaced ones between"""
+    world = len(bounds) - 1
+    per = max(2, -(-int(n_want) // world))
+    idx = set()
+    for r in range(world):
+        lo, hi = int(bounds[r]), int(bounds[r + 1])
+        if hi > lo:
+            idx.update(np.unique(np.linspace(lo, hi - 1, min(per, hi - lo)).astype(np.int64)).tolist())
+    return np.asarray(sorted(idx), np.int64)
+
+
+def result_digest(score, idx):
+    """sha256 over the gathered (best_score, best_idx) int32 arrays in query order: equal digests at N = 1/2/4/8 mean the
+    hash table does not depend on the sharding"""
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(score, np.int32).tobytes() + np.ascontiguousarray(idx, np.int32).tobytes()).hexdigest()
+
+
 def cuda_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -315,14 +389,15 @@ def cuda_arm(args, rank, world, local_rank):
     mode = MODE_NAMES[args.mode]
     queries, targets, name = workload(args)
     total_cells = float(sum(map(len, queries))) * float(sum(map(len, targets)))
+    bounds = shard_bounds_by_work([len(q) for q in queries], world)
 
     # measured denominator of the roofline: the instruction mix of one packed DP cell pair, register-only.
-    # global/glocal: the streaming kernel's mix (1 x 32-bit add + VIMNMX3.S16x2 + 2 x VIADDMNMX.S16x2 = 4 lane-ops per
-    # cell pair); local: the first-generation kernel's mix (2 x VIADD.16x2 + max3 + 2 add-max = 5 lane-ops)
-    peak_which = 8 if args.mode in ("global", "glocal") else 4
-    peak_ops = max(B.int_peak(peak_which, 20000)[0] for _ in range(6))      # best of 6: the first runs see ramping clocks
-    cell_ops = 4 if peak_which == 8 else PACKED_CELL_OPS
-    peak_gcups = peak_ops / cell_ops * 2 / 1e9
+    # global/glocal: the streaming kernel's mix; local: the first-generation kernel's mix
+    def measured_peak(streaming):
+        which, ops = (8, CELL_OPS_STREAMING) if streaming else (4, CELL_OPS_FIRST_GEN)
+        lane_ops = max(B.int_peak(which, 20000)[0] for _ in range(6))      # best of 6: the first runs see ramping clocks
+        return {"which": which, "cell_ops": ops, "lane_ops": lane_ops, "gcups": lane_ops / ops * 2 / 1e9}
+    peak = measured_peak(args.mode in ("global", "glocal"))
 
     def barrier():
         if world > 1:
@@ -337,22 +412,24 @@ def cuda_arm(args, rank, world, local_rank):
 
     stream = torch.cuda.Stream(device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    result = None
-    with torch.cuda.stream(stream):
-        # ---------------- device-resident arm: `value` -------------------------------------------
-        sh = ShardedBestHits(queries, targets, rank, world, mode=mode)
-        for _ in range(args.warmup):
+
+    def resident(mode_name, steps, warmup, sample_clocks):
+        """device-resident job of this rank's shard: `warmup` untimed + `steps` timed steps (L2 flushed before each, one
+        gather per step at N > 1), CUDA events on the launch stream, max over ranks"""
+        sh = ShardedBestHits(queries, targets, rank, world, mode=MODE_NAMES[mode_name])
+        result = None
+        for _ in range(warmup):
             flush.zero_()
             sh.step(dist if world > 1 else None)
         torch.cuda.synchronize(); barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        if sampler:
             sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         prof = {}
         torch.cuda.synchronize(); barrier()
         ev0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             flush.zero_()
             result = sh.step(dist if world > 1 else None)
             stream.synchronize()                                        # per-launch CUDA-event times of this step
@@ -361,15 +438,36 @@ def cuda_arm(args, rank, world, local_rank):
                 p["ms"] += row["ms"]; p["n"] += 1
         ev1.record()
         torch.cuda.synchronize(); barrier()
-        clocks = sampler.stop() if rank == 0 else None
-        elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1))
-        launches = sh.job.kernel_launches() * args.steps
+        out = {"clocks": sampler.stop() if sampler else None, "elapsed_ms": max_over_ranks(ev0.elapsed_time(ev1)),
+               "launches": sh.job.kernel_launches() * steps, "prof": prof, "steps": steps, "warmup": warmup}
         if rank == 0:
-            gpu_score, gpu_idx = result[0].cpu().numpy(), result[1].cpu().numpy()
+            out["score"], out["idx"] = result[0].cpu().numpy(), result[1].cpu().numpy()
         sh.close()
+        return out
+
+    def roofline_of(run, mode_name, pk, io_bytes):
+        """the dominant packed-kernel launch of this rank against the measured rate of its own instruction mix"""
+        if not run["prof"]:
+            return None
+        K, p = max(run["prof"].items(), key=lambda kv: kv[1]["ms"])
+        avg_ms = p["ms"] / p["n"]
+        achieved = p["cells"] / (avg_ms * 1e-3) / 1e9
+        streaming = mode_name in ("global", "glocal")
+        return {"bound": "int_alu", "kernel": ("mm16g_kernel<%s,K=%d>" if streaming else "mm16_kernel<%s,K=%d>") % (mode_name, K),
+                "achieved": achieved, "peak": pk["gcups"], "unit": "GCUPS", "frac": achieved / pk["gcups"],
+                "peak_source": "measured in this run by abv_int_peak(%d): register-only chains of the kernel's cell mix (%d lane-ops per cell pair: %s + VIMNMX3.S16x2 + 2 VIADDMNMX.S16x2), %.3e lane-ops/s" % (
+                    pk["which"], pk["cell_ops"], "1 add" if pk["cell_ops"] == 4 else "2 adds", pk["lane_ops"]),
+                "avg_launch_ms": avg_ms, "cells_per_launch": p["cells"],
+                "share_of_step": p["ms"] / max(1e-9, sum(x["ms"] for x in run["prof"].values())),
+                "launches_timed": p["n"], "rank": 0,
+                "traffic": ncu_traffic(mode_name, K) if (world == 1 and args.workload == "config4" and not (args.queries or args.targets)) else None,
+                "hbm": hbm_info(p["cells"], p["queries"], len(targets), total_cells / world, io_bytes, avg_ms)}
+
+    with torch.cuda.stream(stream):
+        # ---------------- device-resident arm: `value` -------------------------------------------
+        main = resident(args.mode, args.steps, args.warmup, True)
 
         # ---------------- end-to-end arm: host buffers in, host results out ------------------------
-        bounds = shard_bounds_by_work([len(q) for q in queries], world)
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         qbuf, qoff = B.pack(queries[lo:hi])
         tbuf, toff = B.pack(targets)
@@ -398,38 +496,16 @@ def cuda_arm(args, rank, world, local_rank):
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
 
-        # ---------------- the same job in the mode BASELINE.json's config names (glocal), device-resident --------
+        # ---------------- the same job in the mode BASELINE.json's config names (glocal), at every N ----------------
         glocal = None
-        if world == 1 and args.mode == "global" and not args.no_glocal:
-            sh2 = ShardedBestHits(queries, targets, 0, 1, mode=MODE_NAMES["glocal"])
-            flush.zero_(); sh2.step(None); torch.cuda.synchronize()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            for _ in range(2):
-                flush.zero_()
-                sh2.step(None)
-            g1.record()
-            torch.cuda.synchronize()
-            gms = g0.elapsed_time(g1) / 2
-            glocal = {"mode": "glocal", "value": total_cells / (gms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": gms, "steps": 2, "warmup": 1,
-                      "note": "same workload, glocal_align semantics (glocal_align.c:73-202); the pipeline itself scores with global_align (ambivert.py:157-199)"}
-            sh2.close()
+        if args.mode == "global" and not args.no_glocal:
+            glocal = resident("glocal", max(1, args.glocal_steps), 2, False)
 
     if rank == 0:
-        assert (host[0].numpy() == gpu_score).all() and (host[1].numpy() == gpu_idx).all()
+        gpu_score, gpu_idx = main["score"], main["idx"]
+        assert (host[0].numpy() == gpu_score).all() and (host[1].numpy() == gpu_idx).all(), "end-to-end results differ from the resident job's"
+        elapsed_ms = main["elapsed_ms"]
         value = total_cells * args.steps / (elapsed_ms * 1e-3) / 1e9
-        dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else None
-        roofline = None
-        if dom:
-            K, p = dom
-            avg_ms = p["ms"] / p["n"]
-            achieved = p["cells"] / (avg_ms * 1e-3) / 1e9
-            roofline = {"bound": "int_alu", "kernel": ("mm16g_kernel<%s,K=%d>" % (args.mode, K)) if args.mode in ("global", "glocal") else "mm16_kernel<%s,K=%d>" % (args.mode, K), "achieved": achieved,
-                        "peak": peak_gcups, "unit": "GCUPS", "frac": achieved / peak_gcups,
-                        "peak_source": "measured in this run by abv_int_peak(%d): register-only chains of the kernel's cell mix (%d lane-ops per cell pair: %s + VIMNMX3.S16x2 + 2 VIADDMNMX.S16x2), %.3e lane-ops/s" % (peak_which, cell_ops, "1 add" if cell_ops == 4 else "2 adds", peak_ops),
-                        "avg_launch_ms": avg_ms, "cells_per_launch": p["cells"], "share_of_step": p["ms"] / max(1e-9, sum(x["ms"] for x in prof.values())),
-                        "traffic": ncu_traffic(args.mode, K),
-                        "hbm": hbm_info(p["cells"], p["queries"], len(targets), total_cells, h2d + d2h, avg_ms)}
         line = {"metric": "hashtable-build alignment throughput", "value": value, "unit": "GCUPS", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "s16x2 (int32-exact)", "data": "synthetic",
@@ -439,19 +515,39 @@ def cuda_arm(args, rank, world, local_rank):
                 "gcups_per_gpu": value / world,
                 "e2e": {"value": total_cells * args.steps / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "s_per_step": e2e_s / args.steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+                "gpu_launches": main["launches"], "clocks": main["clocks"],
+                "roofline": roofline_of(main, args.mode, peak, h2d + d2h),
+                "result_sha256": result_digest(gpu_score, gpu_idx)}
         if glocal:
-            line["glocal"] = glocal
+            gms = glocal["elapsed_ms"] / glocal["steps"]
+            line["glocal"] = {"mode": "glocal", "value": total_cells / (gms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": gms,
+                              "steps": glocal["steps"], "warmup": glocal["warmup"], "n_gpus": world, "gpu_launches": glocal["launches"],
+                              "roofline": roofline_of(glocal, "glocal", peak, h2d + d2h),
+                              "result_sha256": result_digest(glocal["score"], glocal["idx"]),
+                              "note": "same workload and sharding, glocal_align semantics (glocal_align.c:73-202), one gather per step; the pipeline itself scores with global_align (ambivert.py:157-199)"}
         if world == 1 and args.merge_pairs > 0:
             line["merge"] = merge_measurement(args.merge_pairs)
             line["cluster"] = cluster_measurement(args.merge_pairs)
             line["variants"] = variants_measurement(100000)
-        if world == 1 and not args.no_cpu_baseline:
+        if not args.no_cpu_baseline:
+            # the reference's CPU path on a sample drawn from ALL shards, beside the GPU's results for the same queries:
+            # N = 1: the bounded (~--cpu-seconds) sample that also gives the CPU rate; N > 1: >= 64 queries, parity only
             arm = cpu_arm(queries, targets, mode, args.cpu_seconds)
-            sec, cells, bs, bi = arm["run"](queries[:arm["n"]])
+            pick = parity_sample(bounds, arm["n"] if world == 1 else max(64, 8 * world))
+            sec, cells, bs, bi = arm["run"]([queries[i] for i in pick])
             line["cpu_baseline"] = {"value": cells / sec / 1e9, "unit": "GCUPS", "cores": arm["threads"], "kind": arm["kind"],
-                                    "sample": "first %d of %d queries x all %d targets (%.2e cells, %.1f s); %s" % (arm["n"], len(queries), len(targets), cells, sec, arm["build"]),
-                                    "matches_gpu": bool((bs == gpu_score[:arm["n"]]).all() and (bi == gpu_idx[:arm["n"]]).all())}
+                                    "sample": "%d of %d queries, evenly drawn from all %d shard(s) incl. each shard's first and last query, x all %d targets (%.2e cells, %.1f s); %s" % (
+                                        len(pick), len(queries), world, len(targets), cells, sec, arm["build"]),
+                                    "matches_gpu": bool((bs == gpu_score[pick]).all() and (bi == gpu_idx[pick]).all())}
+            if world == 1:
+                line["cpu_baseline"]["as_shipped"] = as_shipped_measurement(queries, targets, gpu_score, gpu_idx)
+            if glocal:
+                garm = cpu_arm(queries, targets, MODE_NAMES["glocal"], 4.0)
+                gpick = parity_sample(bounds, max(64, 8 * world))
+                gsec, gcells, gbs, gbi = garm["run"]([queries[i] for i in gpick])
+                line["glocal"]["cpu_baseline"] = {"value": gcells / gsec / 1e9, "unit": "GCUPS", "cores": garm["threads"], "kind": garm["kind"],
+                                                  "sample": "%d queries drawn from all %d shard(s) x all %d targets, glocal_align_raw" % (len(gpick), world, len(targets)),
+                                                  "matches_gpu": bool((gbs == glocal["score"][gpick]).all() and (gbi == glocal["idx"][gpick]).all())}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -138,6 +138,10 @@ int abv_set_option(const char *key, int value);
  * Sequences are concatenated: sequence i is bytes [off[i], off[i+1]) of the buffer.
  * map256 != NULL: buffers hold characters, encoded on the device through map256 (to_raw);
  * map256 == NULL: buffers already hold symbol indices (< alpha_len).
+ * A symbol outside the alphabet (a byte whose map entry, or a raw code, is >= alpha_len) makes every batched call
+ * return ABV_ERR_ARGS: the reference reads past its score matrix there (helpers.h:26-32, global_align.c:148).  The
+ * legacy single-pair symbols of part 1 keep the reference's signature (no status) and score such a symbol as the last
+ * symbol of the alphabet.
  */
 int abv_best_hits(int mode,
                   const char *q, const long long *q_off, int n_q,

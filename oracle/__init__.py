@@ -20,6 +20,8 @@ PORT_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libalign_ref.so")
 REF_O3_SO = os.path.join(HERE, "_ref", "libalign_ref_O3.so")
 REF_SRC = "/root/reference/lib/align"
+REF_PKG_CPU = os.path.join(HERE, "_ref", "pkg_cpu")      # the unmodified reference package + its own C extension
+REF_PKG_GPU = os.path.join(HERE, "_ref", "pkg_gpu")      # the unmodified reference package, extension slot empty
 
 OVERLAP, LOCAL, GLOBAL, GLOCAL = 0, 1, 2, 3
 MODE_NAMES = {OVERLAP: "overlap", LOCAL: "local", GLOBAL: "global", GLOCAL: "glocal"}
@@ -243,6 +245,25 @@ class Ref:
     def fns(self, mode):
         """(aligner, free) function addresses for Port.timed_* (the harness lives in liboracle.so)."""
         return (C.cast(getattr(self.lib, self.RAW[mode]), C.c_void_p), C.cast(self.lib.alignment_free, C.c_void_p))
+
+
+def install_dropin(so_path):
+    """Put a shared object into the empty extension slot of the vendored reference package (pkg_gpu) under a
+    name its loader accepts (align_ctypes.py:30-32: the first file whose name contains 'align_c.').
+    -> directory to put on PYTHONPATH, or None when the package was not vendored (no /root/reference at build time)"""
+    import shutil
+    slot = os.path.join(REF_PKG_GPU, "ambivert", "align")
+    if not os.path.isdir(slot):
+        return None
+    for f in os.listdir(slot):
+        if "align_c." in f:
+            os.remove(os.path.join(slot, f))
+    shutil.copy2(so_path, os.path.join(slot, "align_c." + os.path.basename(so_path).split("align_c.", 1)[-1]))
+    return REF_PKG_GPU
+
+
+def as_shipped_available():
+    return os.path.exists(os.path.join(REF_PKG_CPU, "ambivert", "align", "align_c.ref.so"))
 
 
 _port = None

@@ -98,6 +98,22 @@ def test_argument_validation_needs_no_gpu():
     with pytest.raises(B.AlignError) as e:
         B.best_hits([b""], [b"ACGT"])
     assert e.value.code == B.ERR_ARGS
+    # symbols outside the alphabet (the reference reads past its score matrix): raw codes >= alpha_len, or a byte whose
+    # map entry is >= alpha_len (make_map(s, None): unknown == alpha_len) -- rejected, not silently clamped
+    import numpy as np
+    with pytest.raises(B.AlignError) as e:
+        B.best_hits([bytes([0, 1, 5])], [bytes([0, 1, 2])], map256=None)
+    assert e.value.code == B.ERR_ARGS and "outside the alphabet" in str(e.value)
+    import ambivert_b200.align as A
+    n, m = A.make_map("ACGT", None, True)
+    with pytest.raises(B.AlignError) as e:
+        B.align_pairs([b"ACGT"], [b"ACNT"], B.GLOBAL, alpha_len=n, map256=bytes(m), matrix=np.ones(16, np.int32))
+    assert e.value.code == B.ERR_ARGS
+    with pytest.raises(B.AlignError) as e:              # the same map is fine while no unknown byte occurs: fails later, for want of a GPU
+        B.align_pairs([b"ACGT"], [b"ACGT"], B.GLOBAL, alpha_len=n, map256=bytes(m), matrix=np.ones(16, np.int32))
+    import torch
+    if not torch.cuda.is_available():
+        assert e.value.code == B.ERR_NO_DEVICE
 
 
 def test_chunk_bounds_of_the_pair_pipeline():
