@@ -24,6 +24,7 @@ SEED_LOCAL = 0           # ambivert.py:504
 _vp = C.c_void_p
 _lib.abv_device_count.restype = C.c_int
 _lib.abv_set_device.argtypes = [C.c_int]
+_lib.abv_set_thread_device.argtypes = [C.c_int]
 _lib.abv_get_device.restype = C.c_int
 _lib.abv_last_error.restype = C.c_char_p
 _lib.abv_version.restype = C.c_char_p
@@ -31,6 +32,9 @@ _lib.abv_set_option.argtypes = [C.c_char_p, C.c_int]
 _MM = [C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int]
 _lib.abv_best_hits.argtypes = _MM + [C.c_int, _vp, _vp]
 _lib.abv_score_matrix.argtypes = _MM + [_vp]
+_lib.abv_best_hits_multi.argtypes = _MM + [C.c_int, _vp, C.c_int, _vp, _vp]
+_lib.abv_shard_bounds.argtypes = [_vp, C.c_int, C.c_int, _vp]
+_lib.abv_shard_bounds.restype = None
 _lib.abv_best_hits_prepare.argtypes = _MM + [C.c_int]
 _lib.abv_best_hits_prepare.restype = _vp
 _lib.abv_best_hits_launch.argtypes = [_vp, _vp, _vp, _vp]
@@ -39,6 +43,7 @@ _lib.abv_job_cells.argtypes = [_vp]
 _lib.abv_job_cells.restype = C.c_double
 _lib.abv_job_kernel_launches.argtypes = [_vp]
 _lib.abv_job_profile.argtypes = [_vp, _vp, C.c_int]
+_lib.abv_job_profile_history.argtypes = [_vp, C.c_int, _vp, C.c_int]
 _lib.abv_job_free.argtypes = [_vp]
 _lib.abv_job_free.restype = None
 _lib.abv_align_pairs.argtypes = [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int,
@@ -74,6 +79,11 @@ def device_count():
 
 def set_device(ordinal):
     _check(_lib.abv_set_device(int(ordinal)))
+
+
+def set_thread_device(ordinal):
+    """device of the calling thread's subsequent calls (-1: the process default); every device has its own context"""
+    _check(_lib.abv_set_thread_device(int(ordinal)))
 
 
 def version():
@@ -120,6 +130,18 @@ def pack(seqs):
     return buf, off
 
 
+def pack_text(seqs):
+    """list of str -> (uint8 buffer, int64 offsets[n+1]) without one bytes object per sequence: one join, one
+    encode.  Non-ASCII text raises UnicodeEncodeError, as bytes(seq, 'ascii') does at the reference's call sites
+    (ambivert.py:84, :125, :168)."""
+    n = len(seqs)
+    off = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        np.cumsum(np.fromiter(map(len, seqs), dtype=np.int64, count=n), out=off[1:])
+    buf = np.frombuffer("".join(seqs).encode("ascii"), dtype=np.uint8)
+    return buf, off
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(_vp)
 
@@ -156,6 +178,30 @@ def best_hits(queries, targets, mode=GLOBAL, seed=SEED_GLOBAL, alpha_len=DNA_MAP
     bi = np.empty(n_q, np.int32)
     _check(_lib.abv_best_hits(mode, _ptr(q), _ptr(qo), n_q, _ptr(t), _ptr(to), n_t, alpha_len,
                               _ptr(mp), _ptr(m), gap_open, gap_extend, seed, _ptr(bs), _ptr(bi)))
+    return bs, bi
+
+
+def shard_bounds(q_off, n_shards):
+    """the contiguous query shards abv_best_hits_multi uses, balanced by summed length: int32[n_shards + 1]"""
+    qo = np.ascontiguousarray(q_off, dtype=np.int64)
+    out = np.zeros(int(n_shards) + 1, np.int32)
+    _lib.abv_shard_bounds(_ptr(qo), len(qo) - 1, int(n_shards), _ptr(out))
+    return out
+
+
+def best_hits_multi(queries, targets, gpus, mode=GLOBAL, seed=SEED_GLOBAL, alpha_len=DNA_MAP[0], map256=DNA_MAP[1],
+                    matrix=DNA_SCORE, gap_open=GAP_OPEN, gap_extend=GAP_EXTEND):
+    """best_hits on several GPUs of the box from this one process (abv_best_hits_multi): `gpus` = a count (devices
+    0..gpus-1) or a list of device ordinals (an ordinal may repeat).  Same result as best_hits."""
+    q, qo = pack(queries)
+    t, to = pack(targets)
+    mp, m = _scoring(alpha_len, map256, matrix)
+    n_q, n_t = len(qo) - 1, len(to) - 1
+    dev = np.arange(int(gpus), dtype=np.int32) if isinstance(gpus, (int, np.integer)) else np.ascontiguousarray(list(gpus), dtype=np.int32)
+    bs = np.empty(n_q, np.int32)
+    bi = np.empty(n_q, np.int32)
+    _check(_lib.abv_best_hits_multi(mode, _ptr(q), _ptr(qo), n_q, _ptr(t), _ptr(to), n_t, alpha_len,
+                                    _ptr(mp), _ptr(m), gap_open, gap_extend, seed, _ptr(dev), len(dev), _ptr(bs), _ptr(bi)))
     return bs, bi
 
 
@@ -201,6 +247,12 @@ class BestHitsJob:
         out = np.zeros((16, 4), np.float64)
         n = _lib.abv_job_profile(self._h, out.ctypes.data_as(_vp), 16)
         return [dict(K=int(r[0]), queries=int(r[1]), cells=float(r[2]), ms=float(r[3])) for r in out[:n]]
+
+    def profile_history(self, last_launches):
+        """the same for the last `last_launches` (<= 32) calls of launch(), timed back to back: dicts with `launch` added"""
+        out = np.zeros((16 * 32, 5), np.float64)
+        n = _lib.abv_job_profile_history(self._h, int(last_launches), out.ctypes.data_as(_vp), out.shape[0])
+        return [dict(K=int(r[0]), queries=int(r[1]), cells=float(r[2]), ms=float(r[3]), launch=int(r[4])) for r in out[:n]]
 
     def fetch(self):
         bs = np.empty(self.n_q, np.int32)

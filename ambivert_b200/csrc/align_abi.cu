@@ -3,6 +3,7 @@
 // Everything computes on the GPU (kernels.cuh).  There is deliberately no CPU implementation of
 // any alignment in this library: if CUDA is unavailable the calls fail (NULL / ABV_ERR_NO_DEVICE).
 #include <algorithm>
+#include <array>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -11,6 +12,7 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <chrono>
 #include <memory>
 #include <vector>
@@ -45,61 +47,11 @@ int fail(int code, const char *fmt, ...) {
       return fail(ABV_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
   } while (0)
 
-// ---- process-wide context: one device per process (one process per GPU) ----------------------
-struct Options {
-  int path = ABV_PATH_AUTO;
-  int wf32_blocks_per_sm = 4;
-  int mm16_blocks_per_sm = 0;   // 0 = what the occupancy query returns
-  int split = 0;                // 0 = automatic; otherwise slices of the target pairs per query
-  int global_v1 = 0;            // 1 = use the first-generation packed kernel for global mode too
-  int no_levels = 0;            // 1 = streaming global kernel resets every pair explicitly (no level staircase, mm16g_levels)
-  int tb16 = 1;                 // 0 = one-to-one jobs always take the 32-bit kernel
-  int pairs_chunk = 200000;     // one-to-one jobs of at least 2x this many pairs run as a pipeline of chunks (0 = never)
-};
-
-struct Ctx {
-  std::recursive_mutex mu;
-  bool inited = false;
-  int device = 0;
-  int sms = 0;
-  cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;      // second lane of the chunk pipeline of the one-to-one jobs
-  cudaStream_t stream3 = nullptr;      // its downloads
-  unsigned long long *pin64 = nullptr; // 64 pinned words: counters read back per chunk (a copy into pageable memory would block the host until the chunk has finished)
-  cudaEvent_t ev[6] = {};
-  Options opt;
-};
-Ctx g;
-
-int ctx_init() {
-  if (g.inited) return ABV_OK;
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n <= 0) {
-    cudaGetLastError();
-    return fail(ABV_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback",
-                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-  }
-  if (g.device >= n) return fail(ABV_ERR_ARGS, "device %d out of range (%d devices)", g.device, n);
-  CU(cudaSetDevice(g.device));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, g.device));
-  if (prop.major < 10)
-    return fail(ABV_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", g.device, prop.major, prop.minor);
-  g.sms = prop.multiProcessorCount;
-  CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&g.stream3, cudaStreamNonBlocking));
-  CU(cudaHostAlloc((void **)&g.pin64, 64 * sizeof(unsigned long long), cudaHostAllocDefault));
-  for (auto &ev : g.ev) CU(cudaEventCreate(&ev));
-  g.inited = true;
-  return ABV_OK;
-}
-
-// Device allocations go through a small process-wide cache: cudaMalloc/cudaFree cost up to ~100 ms
+// Device allocations go through a small per-device cache: cudaMalloc/cudaFree cost up to ~100 ms
 // per job on a busy box (cudaFree synchronises the device), which showed up as end-to-end time.  Freed
 // blocks are kept (up to a byte budget) and handed out again to requests of a similar size.  All callers
-// hold g.mu, and every user of a block has synchronised its stream before the block is released.
+// hold the device context's mutex, and every user of a block has synchronised its stream before the block is
+// released (abv_job_free waits for the job's last launch stream).
 struct DevCache {
   struct Block { void *p; size_t bytes; };
   std::vector<Block> free_blocks;
@@ -138,22 +90,101 @@ struct DevCache {
     }
   }
 };
-DevCache g_cache;
+
+// ---- device contexts -----------------------------------------------------------------------------------------------
+// One context per CUDA device (streams, events, pinned words, allocation cache, a mutex).  A call works on the context of
+// the CALLING THREAD's device: the process default (abv_set_device; one process per GPU under torchrun) unless the thread
+// chose another one (abv_set_thread_device; the worker threads of abv_best_hits_multi do, one per device of the box).
+// Calls on different devices run concurrently; calls on the same device are serialised by its mutex.
+struct Options {
+  int path = ABV_PATH_AUTO;
+  int wf32_blocks_per_sm = 4;
+  int mm16_blocks_per_sm = 0;   // 0 = what the occupancy query returns
+  int split = 0;                // 0 = automatic; otherwise slices of the target pairs per query
+  int fine_tail = 1;            // 1 = the last work items of a packed launch are cut finer (short tail of the persistent grid)
+  int global_v1 = 0;            // 1 = use the first-generation packed kernel for global mode too
+  int no_gop_imm = 0;           // 1 = never take the streaming kernel's instantiation with the gap addend as an immediate
+  int no_levels = 0;            // 1 = streaming global kernel resets every pair explicitly (no level staircase, mm16g_levels)
+  int tb16 = 1;                 // 0 = one-to-one jobs always take the 32-bit kernel
+  int pairs_chunk = 200000;     // one-to-one jobs of at least 2x this many pairs run as a pipeline of chunks (0 = never)
+};
+Options g_opt;                  // process-wide
+
+constexpr int ABV_MAX_DEVICES = 64;
+struct Ctx {
+  std::recursive_mutex mu;
+  bool inited = false;
+  int device = 0;
+  int sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;      // second lane of the chunk pipeline of the one-to-one jobs
+  cudaStream_t stream3 = nullptr;      // its downloads
+  unsigned long long *pin64 = nullptr; // 64 pinned words: counters read back per chunk (a copy into pageable memory would block the host until the chunk has finished)
+  cudaEvent_t ev[6] = {};
+  DevCache cache;
+  bool md5_ready = false;              // constant memory is per device: the MD5 table has been uploaded here
+};
+Ctx g_ctx[ABV_MAX_DEVICES];
+int g_default_device = 0;
+thread_local int t_device = -1;        // -1: the process default
+inline Ctx &cur_ctx() { return g_ctx[t_device >= 0 ? t_device : g_default_device]; }
+#define g (cur_ctx())
+
+// runs the enclosed calls on another device's context (jobs remember the device they were prepared on)
+struct DeviceScope {
+  int saved;
+  explicit DeviceScope(int device) : saved(t_device) { t_device = device; }
+  ~DeviceScope() { t_device = saved; if (cur_ctx().inited) cudaSetDevice(cur_ctx().device); }
+};
+
+int ctx_init() {
+  Ctx &c = cur_ctx();
+  const int want = t_device >= 0 ? t_device : g_default_device;
+  if (c.inited) {
+    // the CUDA "current device" is per host thread: worker threads (multiprocessing.dummy, abv_best_hits_multi) arrive unset
+    if (cudaSetDevice(c.device) != cudaSuccess) return fail(ABV_ERR_CUDA, "cudaSetDevice(%d): %s", c.device, cudaGetErrorString(cudaGetLastError()));
+    return ABV_OK;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(ABV_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (want >= n) return fail(ABV_ERR_ARGS, "device %d out of range (%d devices)", want, n);
+  c.device = want;
+  CU(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, c.device));
+  if (prop.major < 10)
+    return fail(ABV_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", c.device, prop.major, prop.minor);
+  c.sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c.stream3, cudaStreamNonBlocking));
+  CU(cudaHostAlloc((void **)&c.pin64, 64 * sizeof(unsigned long long), cudaHostAllocDefault));
+  for (auto &ev : c.ev) CU(cudaEventCreate(&ev));
+  c.inited = true;
+  return ABV_OK;
+}
 
 // RAII device allocation
 struct DevMem {
   void *p = nullptr;
   size_t bytes = 0;
+  Ctx *owner = nullptr;         // the device context whose cache the block came from (and goes back to)
   DevMem() = default;
   DevMem(const DevMem &) = delete;
   DevMem &operator=(const DevMem &) = delete;
   ~DevMem() { release(); }
-  void release() { if (p) g_cache.put(p, bytes); p = nullptr; bytes = 0; }
+  void release() { if (p) owner->cache.put(p, bytes); p = nullptr; bytes = 0; }
   cudaError_t alloc(size_t n) {
     release();
     if (n == 0) n = 16;
     n = (n + 255) & ~(size_t)255;
-    return g_cache.get(n, &p, &bytes);
+    owner = &cur_ctx();
+    return owner->cache.get(n, &p, &bytes);
   }
   template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
@@ -253,7 +284,7 @@ int upload_encoded(const char *buf, const long long *off, int n, const Scoring &
       int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
       encode_kernel<<<blocks, 256, 0, st>>>(raw.as<uint8_t>(), d_codes.as<uint8_t>(), total, d_map.as<uint8_t>());
       CU(cudaGetLastError());
-      if (keep_raw) { keep_raw->release(); keep_raw->p = raw.p; keep_raw->bytes = raw.bytes; raw.p = nullptr; raw.bytes = 0; }
+      if (keep_raw) { keep_raw->release(); keep_raw->p = raw.p; keep_raw->bytes = raw.bytes; keep_raw->owner = raw.owner; raw.p = nullptr; raw.bytes = 0; }
     }
     h2d_bytes += (double)total;
   }
@@ -297,7 +328,7 @@ int wf32_dispatch(int mode, int grid, cudaStream_t st, const Wf32Params &p, int 
 
 int wf32_grid(long long n_pairs, size_t scratch_per_warp) {
   long long want = (n_pairs + WF32_WARPS - 1) / WF32_WARPS;
-  long long cap = (long long)g.sms * g.opt.wf32_blocks_per_sm;
+  long long cap = (long long)g.sms * g_opt.wf32_blocks_per_sm;
   const size_t budget = (size_t)3 << 30;   // bound the per-warp scratch to 3 GiB
   if (scratch_per_warp > 0) {
     long long by_mem = (long long)(budget / (scratch_per_warp * WF32_WARPS));
@@ -313,24 +344,63 @@ constexpr int MM16_NK = 11;
 // Work items per launch: a query is cut into `split` slices of the target pairs when there are too few
 // queries to keep the tail of the persistent grid short (each slice keeps >= 4 pairs per warp).
 int pick_split(int n_list, int n_pairs, int resident_ctas) {
-  if (g.opt.split > 0) return std::max(1, std::min(g.opt.split, std::max(1, n_pairs / MM16_WARPS)));
+  if (g_opt.split > 0) return std::max(1, std::min(g_opt.split, std::max(1, n_pairs / MM16_WARPS)));
   int split = 1;
   while (split < 16 && (long long)n_list * split < 24ll * resident_ctas && n_pairs / (split * 2) >= 4 * MM16_WARPS) split *= 2;
   return split;
 }
+// Work items of one packed launch, built on the host and kept on the device: item = (query, slice of the target pairs).
+// A query is cut into `split` slices when there are too few queries to keep the persistent grid busy (multi-GPU shards).  The
+// tail of a persistent grid is as long as its last work item, and the CTAs finish their last coarse item spread over one item's
+// duration: so about one coarse item per CTA of work is cut as fine as the pipeline allows (>= 4 target pairs per warp and
+// slice) and handed out LAST -- it fills that span and leaves a tail of one fine item (1/16 of a query instead of a whole one).
+struct WorkItems {
+  std::vector<int4> host;          // stays alive while the upload may be in flight (the job owns it)
+  DevMem dev;
+  int n = 0;
+  int key[5] = {-1, -1, -1, -1, -1};   // resident CTAs, n_pairs, n_list, split option, fine_tail option
+};
+int build_work_items(WorkItems &W, const int *h_list, int n_list, int n_pairs, int resident_ctas, cudaStream_t st) {
+  const int key[5] = {resident_ctas, n_pairs, n_list, g_opt.split, g_opt.fine_tail};
+  if (W.dev.p && !memcmp(key, W.key, sizeof key)) return ABV_OK;
+  const int split = pick_split(n_list, n_pairs, resident_ctas);
+  int fine = split, n_fine = 0;
+  if (g_opt.fine_tail) {
+    while (fine < 16 && n_pairs / (fine * 2) >= 4 * MM16_WARPS) fine *= 2;
+    if (fine > split) n_fine = (int)std::min<long long>(n_list, (resident_ctas + split - 1) / split);
+  }
+  W.host.clear();
+  W.host.reserve((size_t)(n_list - n_fine) * split + (size_t)n_fine * fine);
+  auto cut = [&](int li, int parts) {
+    for (int part = 0; part < parts; ++part) {
+      const int lo = (int)((long long)n_pairs * part / parts), hi = (int)((long long)n_pairs * (part + 1) / parts);
+      if (hi > lo) W.host.push_back(make_int4(h_list[li], lo, hi, 0));
+    }
+  };
+  for (int li = 0; li < n_list - n_fine; ++li) cut(li, split);
+  for (int li = n_list - n_fine; li < n_list; ++li) cut(li, fine);
+  W.n = (int)W.host.size();
+  CU(W.dev.alloc(sizeof(int4) * std::max<size_t>(W.host.size(), 1)));
+  CU(cudaMemcpyAsync(W.dev.p, W.host.data(), sizeof(int4) * W.host.size(), cudaMemcpyHostToDevice, st));
+  memcpy(W.key, key, sizeof key);
+  return ABV_OK;
+}
 
 template <int MODE, int K>
-int mm16_launch_one(int grid_cap, cudaStream_t st, const Mm16Params &p, int &launched) {
+int mm16_launch_one(int grid_cap, cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
   const Mm16Smem L = mm16_smem_layout(K, p.a1, p.tp_stride);
   auto kern = mm16_kernel<MODE, K>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MM16_WARPS * 32, L.total));
   if (per_sm < 1) return fail(ABV_ERR_CUDA, "mm16 kernel K=%d does not fit (smem %d)", K, L.total);
-  if (g.opt.mm16_blocks_per_sm > 0) per_sm = std::min(per_sm, g.opt.mm16_blocks_per_sm);
+  if (g_opt.mm16_blocks_per_sm > 0) per_sm = std::min(per_sm, g_opt.mm16_blocks_per_sm);
   Mm16Params q = p;
-  q.split = pick_split(p.n_list, p.n_pairs, g.sms * per_sm);
-  int grid = (int)std::min<long long>((long long)p.n_list * q.split, g.sms * per_sm);
+  int rc;
+  if ((rc = build_work_items(W, h_list, p.n_list, p.n_pairs, g.sms * per_sm, st))) return rc;
+  q.items = W.dev.as<int4>(); q.n_items = W.n;
+  if (W.n == 0) return ABV_OK;
+  int grid = (int)std::min<long long>(W.n, g.sms * per_sm);
   if (grid_cap > 0) grid = std::min(grid, grid_cap);
   kern<<<grid, MM16_WARPS * 32, L.total, st>>>(q);
   CU(cudaGetLastError());
@@ -338,65 +408,75 @@ int mm16_launch_one(int grid_cap, cudaStream_t st, const Mm16Params &p, int &lau
   return ABV_OK;
 }
 
-template <int MODE, int K>
-int mm16g_launch_one(cudaStream_t st, const Mm16Params &p, int &launched) {
+template <int MODE, int K, int GOPC>
+int mm16g_launch_gop(cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
   const Mm16gSmem L = mm16g_smem_layout(K, p.a1, p.tp_stride, mm16g_defer(MODE == GLOCAL, K));
-  auto kern = mm16g_kernel<MODE, K>;
+  auto kern = mm16g_kernel<MODE, K, GOPC>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MM16_WARPS * 32, L.total));
   if (per_sm < 1) return fail(ABV_ERR_CUDA, "mm16g kernel K=%d does not fit (smem %d)", K, L.total);
-  if (g.opt.mm16_blocks_per_sm > 0) per_sm = std::min(per_sm, g.opt.mm16_blocks_per_sm);
+  if (g_opt.mm16_blocks_per_sm > 0) per_sm = std::min(per_sm, g_opt.mm16_blocks_per_sm);
   Mm16Params q = p;
-  q.split = pick_split(p.n_list, p.n_pairs, g.sms * per_sm);
-  const int grid = (int)std::min<long long>((long long)p.n_list * q.split, g.sms * per_sm);
+  int rc;
+  if ((rc = build_work_items(W, h_list, p.n_list, p.n_pairs, g.sms * per_sm, st))) return rc;
+  q.items = W.dev.as<int4>(); q.n_items = W.n;
+  if (W.n == 0) return ABV_OK;
+  const int grid = (int)std::min<long long>(W.n, g.sms * per_sm);
   kern<<<grid, MM16_WARPS * 32, L.total, st>>>(q);
   CU(cudaGetLastError());
   ++launched;
   return ABV_OK;
 }
 
+template <int MODE, int K>
+int mm16g_launch_one(cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
+  // the pipeline's gap penalties (-7, -1) take the instantiation with the gap addend as an immediate
+  if (p.go - p.ge == MM16G_GOP_DNA && !g_opt.no_gop_imm) return mm16g_launch_gop<MODE, K, MM16G_GOP_DNA>(st, p, launched, W, h_list);
+  return mm16g_launch_gop<MODE, K, MM16G_GOP_RUNTIME>(st, p, launched, W, h_list);
+}
+
 template <int MODE>
-int mm16g_launch_mode(int K, cudaStream_t st, const Mm16Params &p, int &launched) {
+int mm16g_launch_mode(int K, cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
   switch (K) {
-    case 2: return mm16g_launch_one<MODE, 2>(st, p, launched);
-    case 3: return mm16g_launch_one<MODE, 3>(st, p, launched);
-    case 4: return mm16g_launch_one<MODE, 4>(st, p, launched);
-    case 5: return mm16g_launch_one<MODE, 5>(st, p, launched);
-    case 6: return mm16g_launch_one<MODE, 6>(st, p, launched);
-    case 7: return mm16g_launch_one<MODE, 7>(st, p, launched);
-    case 8: return mm16g_launch_one<MODE, 8>(st, p, launched);
-    case 9: return mm16g_launch_one<MODE, 9>(st, p, launched);
-    case 10: return mm16g_launch_one<MODE, 10>(st, p, launched);
-    case 12: return mm16g_launch_one<MODE, 12>(st, p, launched);
-    case 16: return mm16g_launch_one<MODE, 16>(st, p, launched);
+    case 2: return mm16g_launch_one<MODE, 2>(st, p, launched, W, h_list);
+    case 3: return mm16g_launch_one<MODE, 3>(st, p, launched, W, h_list);
+    case 4: return mm16g_launch_one<MODE, 4>(st, p, launched, W, h_list);
+    case 5: return mm16g_launch_one<MODE, 5>(st, p, launched, W, h_list);
+    case 6: return mm16g_launch_one<MODE, 6>(st, p, launched, W, h_list);
+    case 7: return mm16g_launch_one<MODE, 7>(st, p, launched, W, h_list);
+    case 8: return mm16g_launch_one<MODE, 8>(st, p, launched, W, h_list);
+    case 9: return mm16g_launch_one<MODE, 9>(st, p, launched, W, h_list);
+    case 10: return mm16g_launch_one<MODE, 10>(st, p, launched, W, h_list);
+    case 12: return mm16g_launch_one<MODE, 12>(st, p, launched, W, h_list);
+    case 16: return mm16g_launch_one<MODE, 16>(st, p, launched, W, h_list);
   }
   return fail(ABV_ERR_ARGS, "no packed kernel for K=%d", K);
 }
 
-int mm16g_launch(int mode, int K, cudaStream_t st, const Mm16Params &p, int &launched) {
-  return mode == ABV_GLOCAL ? mm16g_launch_mode<GLOCAL>(K, st, p, launched) : mm16g_launch_mode<GLOBAL>(K, st, p, launched);
+int mm16g_launch(int mode, int K, cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
+  return mode == ABV_GLOCAL ? mm16g_launch_mode<GLOCAL>(K, st, p, launched, W, h_list) : mm16g_launch_mode<GLOBAL>(K, st, p, launched, W, h_list);
 }
 
 template <int MODE>
-int mm16_launch_mode(int K, cudaStream_t st, const Mm16Params &p, int &launched) {
+int mm16_launch_mode(int K, cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
   switch (K) {
-    case 2: return mm16_launch_one<MODE, 2>(0, st, p, launched);
-    case 4: return mm16_launch_one<MODE, 4>(0, st, p, launched);
-    case 6: return mm16_launch_one<MODE, 6>(0, st, p, launched);
-    case 8: return mm16_launch_one<MODE, 8>(0, st, p, launched);
-    case 10: return mm16_launch_one<MODE, 10>(0, st, p, launched);
-    case 12: return mm16_launch_one<MODE, 12>(0, st, p, launched);
-    case 16: return mm16_launch_one<MODE, 16>(0, st, p, launched);
+    case 2: return mm16_launch_one<MODE, 2>(0, st, p, launched, W, h_list);
+    case 4: return mm16_launch_one<MODE, 4>(0, st, p, launched, W, h_list);
+    case 6: return mm16_launch_one<MODE, 6>(0, st, p, launched, W, h_list);
+    case 8: return mm16_launch_one<MODE, 8>(0, st, p, launched, W, h_list);
+    case 10: return mm16_launch_one<MODE, 10>(0, st, p, launched, W, h_list);
+    case 12: return mm16_launch_one<MODE, 12>(0, st, p, launched, W, h_list);
+    case 16: return mm16_launch_one<MODE, 16>(0, st, p, launched, W, h_list);
   }
   return fail(ABV_ERR_ARGS, "no packed kernel for K=%d", K);
 }
 
-int mm16_launch(int mode, int K, bool streaming, cudaStream_t st, const Mm16Params &p, int &launched) {
-  if ((mode == ABV_GLOBAL || mode == ABV_GLOCAL) && streaming) return mm16g_launch(mode, K, st, p, launched);
-  if (mode == ABV_GLOBAL) return mm16_launch_mode<GLOBAL>(K, st, p, launched);
-  if (mode == ABV_LOCAL) return mm16_launch_mode<LOCAL>(K, st, p, launched);
-  if (mode == ABV_GLOCAL) return mm16_launch_mode<GLOCAL>(K, st, p, launched);
+int mm16_launch(int mode, int K, bool streaming, cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
+  if ((mode == ABV_GLOBAL || mode == ABV_GLOCAL) && streaming) return mm16g_launch(mode, K, st, p, launched, W, h_list);
+  if (mode == ABV_GLOBAL) return mm16_launch_mode<GLOBAL>(K, st, p, launched, W, h_list);
+  if (mode == ABV_LOCAL) return mm16_launch_mode<LOCAL>(K, st, p, launched, W, h_list);
+  if (mode == ABV_GLOCAL) return mm16_launch_mode<GLOCAL>(K, st, p, launched, W, h_list);
   return fail(ABV_ERR_ARGS, "packed kernel does not implement mode %d", mode);
 }
 
@@ -405,6 +485,7 @@ int mm16_launch(int mode, int K, bool streaming, cudaStream_t st, const Mm16Para
 // =================================================================================================
 // the many-to-many job
 struct abv_job {
+  int device = 0;                  // the device context the job lives on
   int mode = 0, n_q = 0, n_t = 0, seed = 0;
   int alpha = 0, go = 0, ge = 0;
   double cells = 0;
@@ -415,9 +496,17 @@ struct abv_job {
   DevMem best_score, best_idx, all_scores, chunk_scores, border, best_key;
   int tp_stride = 0, n_pairs = 0, a1 = 0, max_lt = 0, max_lq = 0, maxabs = 1, maxpos = 0;
   int n_pairs_stream = 0;          // leading target pairs (longest first) the streaming kernel takes; the rest goes to mm16_kernel
-  struct Bucket { int K, n, offset; double cells; cudaEvent_t e0, e1; bool streaming; };
+  // per-launch timing: event pairs of the last PROFILE_RING launches of every bucket, so that a caller can time many
+  // launches back to back and read them afterwards (no host synchronisation per launch)
+  static constexpr int PROFILE_RING = 32;
+  struct Bucket {
+    int K, n, offset; double cells; std::vector<cudaEvent_t> ev; bool streaming;
+    std::shared_ptr<WorkItems> items, items_short;      // work-item tables of its launch(es), built at the first launch
+  };
+  std::vector<int> h_lists;        // host copy of `lists`
   std::vector<Bucket> buckets;     // packed-kernel launches (one per K class), lists at `offset`
-  ~abv_job() { for (auto &b : buckets) { if (b.e0) cudaEventDestroy(b.e0); if (b.e1) cudaEventDestroy(b.e1); } }
+  long long n_launches = 0;        // abv_best_hits_launch calls so far
+  ~abv_job() { for (auto &b : buckets) for (auto e : b.ev) if (e) cudaEventDestroy(e); }
   int n_wf32 = 0, wf32_offset = 0; // queries served by the 32-bit kernel, list at `wf32_offset`
   int wf32_blocks = 0;             // its grid, fixed when `border` was sized (the option may change before the launch)
   int n_counters = 0;
@@ -459,6 +548,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   if ((rc = mm_validate(mode, q, q_off, n_q, t, t_off, n_t, sc, max_lq, max_lt, min_lt))) return rc;
   if ((rc = ctx_init())) return rc;
   cudaStream_t st = g.stream;
+  J.device = g.device;
   J.mode = mode; J.n_q = n_q; J.n_t = n_t; J.seed = seed; J.alpha = sc.alpha; J.go = sc.go; J.ge = sc.ge;
   J.max_lq = max_lq; J.max_lt = max_lt; J.want_all_scores = all_scores;
   {
@@ -487,7 +577,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   for (int i = 0; i < sc.alpha * sc.alpha; ++i) maxpos = std::max(maxpos, sc.matrix[i]);
   J.maxabs = maxabs; J.maxpos = maxpos;
   const int a1 = sc.alpha + 1;
-  bool packed_ok = g.opt.path != ABV_PATH_WF32 && n_t > 0 && a1 * a1 <= 64 &&
+  bool packed_ok = g_opt.path != ABV_PATH_WF32 && n_t > 0 && a1 * a1 <= 64 &&
                    (mode == ABV_GLOBAL || mode == ABV_LOCAL || mode == ABV_GLOCAL);
   // the streaming kernel sweeps at least 32 rows per pair, plus one pad row after every pair (its separator row, mm16g_levels)
   const int tp_stride = (std::max(max_lt, MM16G_MIN_ROWS) + 1 + 15) & ~15;
@@ -503,7 +593,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   }
   J.n_pairs_stream = n_pairs_stream;
   auto stream_ok = [&](int K) {
-    if (g.opt.global_v1 || n_pairs_stream == 0) return false;
+    if (g_opt.global_v1 || n_pairs_stream == 0) return false;
     if (!packed_exact_streaming(mode, 32 * K, tp_stride, maxabs, sc.ge)) return false;
     if (n_pairs_stream < n_pairs_all) {
       const int K2 = K + (K & 1);
@@ -530,7 +620,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
     }
     if (slot >= 0) lists[slot].push_back(i); else wf32_list.push_back(i);
   }
-  if (g.opt.path == ABV_PATH_PACKED && !wf32_list.empty())
+  if (g_opt.path == ABV_PATH_PACKED && !wf32_list.empty())
     return fail(ABV_ERR_ARGS, "packed path forced but %zu queries are not eligible for it", wf32_list.size());
 
   std::vector<int> flat;
@@ -538,16 +628,17 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
     if (!lists[k].empty()) {
       double qlen = 0;
       for (int i : lists[k]) qlen += (double)(q_off[i + 1] - q_off[i]);
-      abv_job::Bucket b{MM16_KS[k], (int)lists[k].size(), (int)flat.size(), qlen * (double)(t_off[n_t] - t_off[0]), nullptr, nullptr,
-                        stream_ok(MM16_KS[k])};
-      CU(cudaEventCreate(&b.e0));
-      CU(cudaEventCreate(&b.e1));
+      abv_job::Bucket b{MM16_KS[k], (int)lists[k].size(), (int)flat.size(), qlen * (double)(t_off[n_t] - t_off[0]), {},
+                        stream_ok(MM16_KS[k]), std::make_shared<WorkItems>(), std::make_shared<WorkItems>()};
+      b.ev.assign(2 * abv_job::PROFILE_RING, nullptr);
+      for (auto &e : b.ev) CU(cudaEventCreate(&e));
       J.buckets.push_back(b);
       flat.insert(flat.end(), lists[k].begin(), lists[k].end());
     }
   J.wf32_offset = (int)flat.size();
   J.n_wf32 = (int)wf32_list.size();
   flat.insert(flat.end(), wf32_list.begin(), wf32_list.end());
+  J.h_lists = flat;
   CU(J.lists.alloc(sizeof(int) * std::max<size_t>(flat.size(), 1)));
   CU(cudaMemcpyAsync(J.lists.p, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));
@@ -648,22 +739,23 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
     p.best_score = d_best_score; p.best_idx = d_best_idx;
     p.all_scores = J.want_all_scores ? J.all_scores.as<int>() : nullptr; p.n_t = J.n_t;
     p.q_counter = reinterpret_cast<unsigned int *>(J.counters.as<unsigned long long>() + ci++);
-    p.best_key = J.best_key.as<unsigned long long>(); p.split = 1;
+    p.best_key = J.best_key.as<unsigned long long>();
     {
-      const Mm16gLevels lv = (b.streaming && J.mode == ABV_GLOBAL && !g.opt.no_levels)
+      const Mm16gLevels lv = (b.streaming && J.mode == ABV_GLOBAL && !g_opt.no_levels)
                                  ? mm16g_levels(32 * b.K, J.tp_stride, J.go, J.ge, J.maxabs, J.maxpos) : Mm16gLevels{1, 0, 0};
       p.lv_n = lv.n; p.lv0 = lv.lvl0; p.lv_step = lv.step;
     }
-    CU(cudaEventRecord(b.e0, st));
+    const int slot = (int)(J.n_launches % abv_job::PROFILE_RING);
+    CU(cudaEventRecord(b.ev[2 * slot], st));
     if (b.streaming && J.n_pairs_stream < J.n_pairs) {
       Mm16Params r = p;                                  // the short target pairs at the end of the list
       r.tp_codes += (size_t)J.n_pairs_stream * J.tp_stride; r.tp_meta += J.n_pairs_stream; r.n_pairs = J.n_pairs - J.n_pairs_stream;
       r.q_counter = reinterpret_cast<unsigned int *>(J.counters.as<unsigned long long>() + ci++);
       p.n_pairs = J.n_pairs_stream;
-      if ((rc = mm16_launch(J.mode, b.K, true, st, p, launched))) return rc;
-      if ((rc = mm16_launch(J.mode, b.K + (b.K & 1), false, st, r, launched))) return rc;
-    } else if ((rc = mm16_launch(J.mode, b.K, b.streaming, st, p, launched))) return rc;
-    CU(cudaEventRecord(b.e1, st));
+      if ((rc = mm16_launch(J.mode, b.K, true, st, p, launched, *b.items, J.h_lists.data() + b.offset))) return rc;
+      if ((rc = mm16_launch(J.mode, b.K + (b.K & 1), false, st, r, launched, *b.items_short, J.h_lists.data() + b.offset))) return rc;
+    } else if ((rc = mm16_launch(J.mode, b.K, b.streaming, st, p, launched, *b.items, J.h_lists.data() + b.offset))) return rc;
+    CU(cudaEventRecord(b.ev[2 * slot + 1], st));
   }
   if (!J.buckets.empty()) {   // seed rule + unpack, over the queries the packed kernels served
     const int n_packed = J.wf32_offset;
@@ -705,6 +797,7 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
     }
   }
   J.launches_per_run = launched;
+  ++J.n_launches;
   return ABV_OK;
 }
 
@@ -754,7 +847,7 @@ struct Tb16Plan {
   int pad_score = -1;
 };
 bool tb16_eligible(int mode, const Scoring &sc) {
-  if (!g.opt.tb16 || g.opt.path == ABV_PATH_WF32) return false;
+  if (!g_opt.tb16 || g_opt.path == ABV_PATH_WF32) return false;
   if (mode != ABV_LOCAL && mode != ABV_GLOBAL) return false;
   if (sc.alpha > TB16_MAX_ALPHA) return false;
   if (mode == ABV_LOCAL && sc.go >= 0) return false;      // the padding argument needs a strictly negative gap_open
@@ -829,29 +922,46 @@ int abv_device_count(void) {
 }
 
 int abv_set_device(int ordinal) {
+  if (ordinal < 0 || ordinal >= ABV_MAX_DEVICES) return fail(ABV_ERR_ARGS, "device ordinal %d out of range", ordinal);
+  g_default_device = ordinal;          // the process default (threads that never chose a device use it) ...
+  t_device = -1;                       // ... and this thread follows it
   std::lock_guard<std::recursive_mutex> lk(g.mu);
-  if (g.inited && g.device != ordinal) return fail(ABV_ERR_ARGS, "device already initialised as %d", g.device);
-  if (ordinal < 0) return fail(ABV_ERR_ARGS, "negative device ordinal");
-  g.device = ordinal;
   return ctx_init();
 }
 
-int abv_get_device(void) { return g.device; }
+int abv_set_thread_device(int ordinal) {
+  if (ordinal < -1 || ordinal >= ABV_MAX_DEVICES) return fail(ABV_ERR_ARGS, "device ordinal %d out of range", ordinal);
+  t_device = ordinal;                  // -1: back to the process default
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  return ctx_init();
+}
+
+int abv_get_device(void) { return t_device >= 0 ? t_device : g_default_device; }
 const char *abv_last_error(void) { return t_err.c_str(); }
 const char *abv_version(void) { return "ambivert-b200 0.1 (sm_100a)"; }
 
 int abv_set_option(const char *key, int value) {
   std::lock_guard<std::recursive_mutex> lk(g.mu);
   if (!key) return fail(ABV_ERR_ARGS, "NULL key");
-  if (!strcmp(key, "path")) { if (value < 0 || value > 2) return fail(ABV_ERR_ARGS, "bad path"); g.opt.path = value; return ABV_OK; }
-  if (!strcmp(key, "wf32_blocks_per_sm")) { g.opt.wf32_blocks_per_sm = std::max(1, std::min(value, 8)); return ABV_OK; }
-  if (!strcmp(key, "cache_mb")) { g_cache.budget = (size_t)std::max(0, value) << 20; g_cache.trim(g_cache.budget); return ABV_OK; }
-  if (!strcmp(key, "split")) { g.opt.split = std::max(0, std::min(value, 64)); return ABV_OK; }
-  if (!strcmp(key, "tb16")) { g.opt.tb16 = value ? 1 : 0; return ABV_OK; }
-  if (!strcmp(key, "global_v1")) { g.opt.global_v1 = value ? 1 : 0; return ABV_OK; }
-  if (!strcmp(key, "no_levels")) { g.opt.no_levels = value ? 1 : 0; return ABV_OK; }
-  if (!strcmp(key, "pairs_chunk")) { g.opt.pairs_chunk = std::max(0, value); return ABV_OK; }
-  if (!strcmp(key, "mm16_blocks_per_sm")) { g.opt.mm16_blocks_per_sm = std::max(0, std::min(value, 8)); return ABV_OK; }
+  if (!strcmp(key, "path")) { if (value < 0 || value > 2) return fail(ABV_ERR_ARGS, "bad path"); g_opt.path = value; return ABV_OK; }
+  if (!strcmp(key, "wf32_blocks_per_sm")) { g_opt.wf32_blocks_per_sm = std::max(1, std::min(value, 8)); return ABV_OK; }
+  if (!strcmp(key, "cache_mb")) {
+    for (Ctx &c : g_ctx) {                      // per device
+      std::lock_guard<std::recursive_mutex> lc(c.mu);
+      c.cache.budget = (size_t)std::max(0, value) << 20;
+      if (c.inited && cudaSetDevice(c.device) == cudaSuccess) c.cache.trim(c.cache.budget);
+    }
+    if (g.inited) cudaSetDevice(g.device);
+    return ABV_OK;
+  }
+  if (!strcmp(key, "split")) { g_opt.split = std::max(0, std::min(value, 64)); return ABV_OK; }
+  if (!strcmp(key, "fine_tail")) { g_opt.fine_tail = value ? 1 : 0; return ABV_OK; }
+  if (!strcmp(key, "tb16")) { g_opt.tb16 = value ? 1 : 0; return ABV_OK; }
+  if (!strcmp(key, "global_v1")) { g_opt.global_v1 = value ? 1 : 0; return ABV_OK; }
+  if (!strcmp(key, "no_gop_imm")) { g_opt.no_gop_imm = value ? 1 : 0; return ABV_OK; }
+  if (!strcmp(key, "no_levels")) { g_opt.no_levels = value ? 1 : 0; return ABV_OK; }
+  if (!strcmp(key, "pairs_chunk")) { g_opt.pairs_chunk = std::max(0, value); return ABV_OK; }
+  if (!strcmp(key, "mm16_blocks_per_sm")) { g_opt.mm16_blocks_per_sm = std::max(0, std::min(value, 8)); return ABV_OK; }
   return fail(ABV_ERR_ARGS, "unknown option %s", key);
 }
 
@@ -868,13 +978,17 @@ abv_job *abv_best_hits_prepare(int mode, const char *q, const long long *q_off, 
 
 int abv_best_hits_launch(abv_job *job, void *stream, int *d_best_score, int *d_best_idx) {
   if (!job) return fail(ABV_ERR_ARGS, "NULL job");
+  DeviceScope on(job->device);
   std::lock_guard<std::recursive_mutex> lk(g.mu);
   return job_launch(*job, (cudaStream_t)stream, d_best_score, d_best_idx);
 }
 
 int abv_best_hits_fetch(abv_job *job, int *best_score, int *best_idx) {
   if (!job) return fail(ABV_ERR_ARGS, "NULL job");
+  DeviceScope on(job->device);
   std::lock_guard<std::recursive_mutex> lk(g.mu);
+  int rc;
+  if ((rc = ctx_init())) return rc;
   cudaStream_t st = job->last_stream ? job->last_stream : g.stream;
   if (job->n_q == 0) return ABV_OK;
   if (best_score) CU(cudaMemcpyAsync(best_score, job->best_score.p, sizeof(int) * job->n_q, cudaMemcpyDeviceToHost, st));
@@ -887,21 +1001,46 @@ double abv_job_cells(const abv_job *job) { return job ? job->cells : 0; }
 
 int abv_job_profile(abv_job *job, double *out, int max_rows) {
   if (!job || !out) return 0;
+  DeviceScope on(job->device);
   std::lock_guard<std::recursive_mutex> lk(g.mu);
+  if (ctx_init() != ABV_OK) return 0;
   int n = 0;
+  if (job->n_launches == 0) return 0;
+  const int slot = (int)((job->n_launches - 1) % abv_job::PROFILE_RING);
   for (const auto &b : job->buckets) {
     if (n >= max_rows) break;
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, b.e0, b.e1) != cudaSuccess) { cudaGetLastError(); ms = -1; }
+    if (cudaEventElapsedTime(&ms, b.ev[2 * slot], b.ev[2 * slot + 1]) != cudaSuccess) { cudaGetLastError(); ms = -1; }
     out[4 * n] = b.K; out[4 * n + 1] = b.n; out[4 * n + 2] = b.cells; out[4 * n + 3] = ms;
     ++n;
+  }
+  return n;
+}
+int abv_job_profile_history(abv_job *job, int last_launches, double *out, int max_rows) {
+  if (!job || !out || last_launches <= 0) return 0;
+  DeviceScope on(job->device);
+  std::lock_guard<std::recursive_mutex> lk(g.mu);
+  if (ctx_init() != ABV_OK) return 0;
+  const long long have = std::min<long long>(std::min<long long>(job->n_launches, abv_job::PROFILE_RING), last_launches);
+  int n = 0;
+  for (long long l = job->n_launches - have; l < job->n_launches; ++l) {
+    const int slot = (int)(l % abv_job::PROFILE_RING);
+    for (const auto &b : job->buckets) {
+      if (n >= max_rows) return n;
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, b.ev[2 * slot], b.ev[2 * slot + 1]) != cudaSuccess) { cudaGetLastError(); ms = -1; }
+      out[5 * n] = b.K; out[5 * n + 1] = b.n; out[5 * n + 2] = b.cells; out[5 * n + 3] = ms; out[5 * n + 4] = (double)l;
+      ++n;
+    }
   }
   return n;
 }
 int abv_job_kernel_launches(const abv_job *job) { return job ? job->launches_per_run : 0; }
 void abv_job_free(abv_job *job) {
   if (!job) return;
+  DeviceScope on(job->device);
   std::lock_guard<std::recursive_mutex> lk(g.mu);
+  ctx_init();
   // abv_best_hits_launch is asynchronous and may have run on a caller's stream: the job's blocks go back to the
   // allocation cache (and from there to the next job's uploads on the library's stream) only once those kernels are done
   if (job->last_stream && cudaStreamSynchronize(job->last_stream) != cudaSuccess) cudaGetLastError();
@@ -961,6 +1100,73 @@ int abv_score_matrix(int mode, const char *q, const long long *q_off, int n_q,
   if (n_q > 0 && n_t > 0 && !scores) return fail(ABV_ERR_ARGS, "NULL output");
   return best_hits_impl(mode, q, q_off, n_q, t, t_off, n_t, alpha_len, map256, score_matrix, gap_open, gap_extend,
                         INT_MIN, nullptr, nullptr, scores);
+}
+
+// -------------------------------------------------------------------------------------------------
+// The hashtable build on several GPUs of one box from ONE process (the successor of the reference's --threads,
+// ambivert.py:474-476, :1092-1095): the queries are cut into contiguous shards balanced by their summed length (cells are
+// proportional to it), every device gets the whole target set, one host thread per device runs the single-device job on
+// its shard, and each shard's 8 bytes per query go straight from its device into the caller's arrays.  The arg-max is
+// per query, so the result does not depend on the sharding.
+void abv_shard_bounds(const long long *q_off, int n_q, int n_shards, int *bounds) {
+  bounds[0] = 0;
+  const long long base = n_q > 0 ? q_off[0] : 0, total = n_q > 0 ? q_off[n_q] - base : 0;
+  for (int r = 1; r < n_shards; ++r) {
+    // first query index whose cumulative length reaches r/n of the total (numpy.searchsorted(csum, total*r/n, 'left'))
+    const double want = (double)total * r / n_shards;
+    int lo = 0, hi = n_q;
+    while (lo < hi) {
+      const int mid = (lo + hi) / 2;
+      if ((double)(q_off[mid + 1] - base) < want) lo = mid + 1; else hi = mid;
+    }
+    bounds[r] = std::max(bounds[r - 1], std::min(lo, n_q));
+  }
+  bounds[n_shards] = n_q;
+}
+
+int abv_best_hits_multi(int mode, const char *q, const long long *q_off, int n_q,
+                        const char *t, const long long *t_off, int n_t,
+                        int alpha_len, const unsigned char *map256, const int *score_matrix,
+                        int gap_open, int gap_extend, int seed_score,
+                        const int *devices, int n_devices, int *best_score, int *best_idx) {
+  if (n_devices < 1 || n_devices > ABV_MAX_DEVICES) return fail(ABV_ERR_ARGS, "n_devices %d out of range", n_devices);
+  if (n_q > 0 && (!best_score || !best_idx)) return fail(ABV_ERR_ARGS, "NULL output");
+  int rc;
+  Scoring sc{alpha_len, gap_open, gap_extend, map256, score_matrix};
+  { int a, b, c; if ((rc = mm_validate(mode, q, q_off, n_q, t, t_off, n_t, sc, a, b, c))) return rc; }
+  std::vector<int> dev(n_devices), bounds(n_devices + 1);
+  for (int i = 0; i < n_devices; ++i) {
+    dev[i] = devices ? devices[i] : i;
+    if (dev[i] < 0 || dev[i] >= ABV_MAX_DEVICES) return fail(ABV_ERR_ARGS, "device ordinal %d out of range", dev[i]);
+  }
+  if (n_q == 0) return ABV_OK;
+  abv_shard_bounds(q_off, n_q, n_devices, bounds.data());
+  std::vector<int> rcs(n_devices, ABV_OK);
+  std::vector<std::string> errs(n_devices);
+  std::vector<std::array<double, 8>> tms(n_devices);
+  auto work = [&](int i) {
+    t_device = dev[i];
+    const int lo = bounds[i], hi = bounds[i + 1];
+    rcs[i] = best_hits_impl(mode, q, q_off + lo, hi - lo, t, t_off, n_t, alpha_len, map256, score_matrix, gap_open, gap_extend,
+                            seed_score, best_score + lo, best_idx + lo, nullptr);
+    if (rcs[i] != ABV_OK) errs[i] = t_err;
+    for (int k = 0; k < 8; ++k) tms[i][k] = t_timing[k];
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < n_devices; ++i) th.emplace_back(work, i);
+  const int saved = t_device;
+  work(0);                                   // the calling thread takes the first shard
+  t_device = saved;
+  for (auto &x : th) x.join();
+  if (cur_ctx().inited) cudaSetDevice(cur_ctx().device);
+  for (double &v : t_timing) v = 0;
+  for (int i = 0; i < n_devices; ++i) {
+    for (int k : {0, 1, 2, 7}) t_timing[k] = std::max(t_timing[k], tms[i][k]);      // the slowest device
+    for (int k : {3, 4, 5, 6}) t_timing[k] += tms[i][k];                            // cells, launches, bytes: all devices
+  }
+  for (int i = 0; i < n_devices; ++i)
+    if (rcs[i] != ABV_OK) return fail(rcs[i], "device %d: %s", dev[i], errs[i].c_str());
+  return ABV_OK;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1124,7 +1330,7 @@ static int pairs_run(PairsRun &R, int mode, const char *a, const long long *a_of
 // quarter-size chunk, grows by 1.6x per chunk (an upload takes ~0.6 of the kernel time of the same pairs, so the next chunk has
 // arrived when the current one finishes) up to the nominal size, and ends with a quarter-size chunk.  At most 16 chunks.
 static std::vector<int> pairs_chunk_bounds(int n) {
-  const long long per = g.opt.pairs_chunk;
+  const long long per = g_opt.pairs_chunk;
   std::vector<int> b{0};
   if (per <= 0 || n < 2 * per) { b.push_back(n); return b; }
   long long s = std::max<long long>(per / 4, 1), pos = 0;
@@ -1499,12 +1705,11 @@ int abv_cluster_pairs(const char *fwd, const long long *fwd_off, const char *rev
   if ((rc = ctx_init())) return rc;
   for (double &v : t_timing) v = 0;
   cudaStream_t st = g.stream;
-  static bool k_ready = false;
-  if (!k_ready) {      // K[i] = floor(2^32 * |sin(i + 1)|)  (RFC 1321, section 3.4)
+  if (!g.md5_ready) {  // K[i] = floor(2^32 * |sin(i + 1)|)  (RFC 1321, section 3.4)
     uint32_t k[64];
     for (int i = 0; i < 64; ++i) k[i] = (uint32_t)(long long)floor(fabs(sin((double)(i + 1))) * 4294967296.0);
     CU(cudaMemcpyToSymbol(c_md5_k, k, sizeof k));
-    k_ready = true;
+    g.md5_ready = true;
   }
   CU(cudaEventRecord(g.ev[0], st));
   DevMem df, dfo, dr, dro, lo, hi, lo2, hi2, idx, idx2, flag, seg, tmp, run_start, run_first, run_first_s, run_id, order_run, rank_of_run,
@@ -1783,6 +1988,7 @@ Alignment *alignment_new(AlignFrag *align_frag, int score) {
 // per-call resources (stream, pinned staging, device scratch) are pooled: worker threads come and go (the
 // reference builds a new Pool per amplicon), the contexts stay.
 struct OneCtx {
+  int device = 0;                                   // streams and allocations belong to one device
   cudaStream_t st = nullptr;
   unsigned char *h = nullptr; size_t h_cap = 0;     // pinned: [input blob][result blob]
   unsigned char *d = nullptr; size_t d_cap = 0;     // device: input blob + scratch + result blob
@@ -1791,11 +1997,14 @@ std::mutex g_one_mu;
 std::vector<OneCtx *> g_one_free;
 
 static OneCtx *one_acquire() {
+  const int device = g.device;
   {
     std::lock_guard<std::mutex> lk(g_one_mu);
-    if (!g_one_free.empty()) { OneCtx *c = g_one_free.back(); g_one_free.pop_back(); return c; }
+    for (size_t i = g_one_free.size(); i-- > 0;)
+      if (g_one_free[i]->device == device) { OneCtx *c = g_one_free[i]; g_one_free.erase(g_one_free.begin() + i); return c; }
   }
   OneCtx *c = new OneCtx();
+  c->device = device;
   if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete c; return nullptr; }
   return c;
 }
@@ -1826,8 +2035,7 @@ static void one_launch(cudaStream_t st, const Wf32OneParams &p) {
   const size_t smem = (size_t)((p.la + 31) / 32) * 2 * p.lb * 4 + p.la + p.lb;
   if (smem <= 150 * 1024) {
     auto kern = wf32_one_kernel<MODE, true>;
-    static thread_local bool raised = false;
-    if (smem > 40 * 1024 && !raised) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024); raised = true; }
+    if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);   // rare (long pairs); the attribute is per device
     kern<<<1, WF32_ONE_WARPS * 32, smem, st>>>(p);
   } else {
     wf32_one_kernel<MODE, false><<<1, WF32_ONE_WARPS * 32, 0, st>>>(p);

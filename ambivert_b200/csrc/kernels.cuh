@@ -960,7 +960,8 @@ struct Mm16Params {
   int *all_scores; int n_t;                   // optional full score matrix [query*n_t + target]
   unsigned int *q_counter;
   unsigned long long *best_key;               // per query: packed (score, target) of the best hit so far, see best_key_pack
-  int split;                                  // work item = (query, one of `split` slices of the target pairs)
+  const int4 *items; int n_items;             // work items of this launch, built by the host: {query, first target pair, end target pair, -};
+                                              // a persistent CTA takes the next one with an atomic counter
   int lv_n, lv0, lv_step;                     // streaming global kernel: level plan (dp_core.cuh, mm16g_levels); lv_n <= 1: every pair is reset explicitly
 };
 
@@ -1076,10 +1077,9 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16_
     if (threadIdx.x == 0) misc[0] = (int)atomicAdd(p.q_counter, 1u);
     __syncthreads();
     const int item = misc[0];
-    if (item >= p.n_list * p.split) break;
-    const int li = item / p.split, part = item - li * p.split;
-    const int pair_lo = (int)((long long)p.n_pairs * part / p.split), pair_hi = (int)((long long)p.n_pairs * (part + 1) / p.split);
-    const int qi = p.q_list[li];
+    if (item >= p.n_items) break;
+    const int4 work = p.items[item];
+    const int qi = work.x, pair_lo = work.y, pair_hi = work.z;
     const uint8_t *qs = p.q + p.q_off[qi];
     const int lq = (int)(p.q_off[qi + 1] - p.q_off[qi]);
     for (int c = threadIdx.x; c < P; c += blockDim.x) qcodes[c] = c < lq ? qs[c] : (uint8_t)(a1 - 1);
@@ -1259,7 +1259,13 @@ __host__ __device__ inline Mm16gSmem mm16g_smem_layout(int K, int a1, int tp_str
   return L;
 }
 
-template <int MODE, int K>
+// GOPC: gap_open - gap_extend as a COMPILE-TIME constant (<= 0), or MM16G_GOP_RUNTIME.  The specialised instantiation (the
+// pipeline's scoring, -7 - -1 = -6: every call site of the reference, ambivert.py:86-89, :127-130, :170-173) carries the
+// addend of the two add-max instructions of a cell as an immediate, so they read two registers instead of three (fewer
+// register-bank conflicts on the half-rate pipe that bounds the kernel) and one register is freed.
+constexpr int MM16G_GOP_RUNTIME = 1;
+constexpr int MM16G_GOP_DNA = -6;
+template <int MODE, int K, int GOPC>
 __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g_kernel(Mm16Params p) {
   static_assert(MODE == GLOBAL || MODE == GLOCAL, "the streaming kernel implements global and glocal");
   constexpr bool GL = (MODE == GLOCAL);
@@ -1281,7 +1287,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
   int *slots = reinterpret_cast<int *>(smem + L.slots) + warp * 4;       // glocal: [pair parity][half] running last-row maxima
   const int a1 = p.a1, ncodes = a1 * a1;
   const int go = p.go, ge = p.ge;
-  const uint32_t gop2 = p16::pack(go - ge, go - ge);
+  const uint32_t gop2 = GOPC <= 0 ? p16::pack(GOPC, GOPC) : p16::pack(go - ge, go - ge);
   const uint32_t gopw = b16::addend(go - ge, go - ge), gew = b16::addend(ge, ge);
   const uint32_t NEGb = b16::biased(p16::NEG16, p16::NEG16);
   // values handed to column 0 by the virtual column -1 (drift-normalised, see mm16d_row):
@@ -1306,10 +1312,9 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
     if (threadIdx.x == 0) misc[0] = (int)atomicAdd(p.q_counter, 1u);
     __syncthreads();
     const int item = misc[0];
-    if (item >= p.n_list * p.split) break;
-    const int li = item / p.split, part = item - li * p.split;
-    const int pair_lo = (int)((long long)p.n_pairs * part / p.split), pair_hi = (int)((long long)p.n_pairs * (part + 1) / p.split);
-    const int qi = p.q_list[li];
+    if (item >= p.n_items) break;
+    const int4 work = p.items[item];
+    const int qi = work.x, pair_lo = work.y, pair_hi = work.z;
     const uint8_t *qs = p.q + p.q_off[qi];
     const int lq = (int)(p.q_off[qi + 1] - p.q_off[qi]);
     for (int c = threadIdx.x; c < P; c += blockDim.x) qcodes[c] = c < lq ? qs[c] : (uint8_t)(a1 - 1);

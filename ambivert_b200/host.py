@@ -18,6 +18,7 @@ import logging
 import pickle
 import warnings
 from collections import defaultdict
+from itertools import compress
 
 import numpy as np
 
@@ -157,33 +158,44 @@ def merge_overlaps(self, threshold=0, minimum_overlap=10):
     logging.info("\nSuccessfully merged {0} reads. {1} reads could not be merged".format(len(self.merged), len(self.unmergable)))
 
 
-def match_to_reference(self, min_score=0.1, trim_primers=0, global_align=True, show_progress=False, threads=1):
+def match_to_reference(self, min_score=0.1, trim_primers=0, global_align=True, show_progress=False, threads=1, gpus=1):
     """ambivert.py:365-541: the exact-match hash table.  Every merged amplicon that is not already
     in the table is scored against every reference target (global alignment in both settings of
     `global_align` -- the reference's calculate_local_score calls global_align too, ambivert.py:190; the
     settings differ by the arg-max seed, 0 vs -1000000) and keeps the first best-scoring target if its
-    score exceeds min_score.  `threads` is accepted for signature compatibility; the GPU does the work."""
-    keys = [k for k in self.merged if k not in self.reference]
+    score exceeds min_score.  `threads` is accepted for signature compatibility; the GPUs do the work:
+    `gpus` (the successor of --threads, ambivert.py:474-476, :1092-1095) = how many GPUs of the box, or a list of device
+    ordinals -- the amplicons are sharded over them inside the library (abv_best_hits_multi), one process."""
+    reference = self.reference
+    keys = [k for k in self.merged if k not in reference]
     ref_keys = list(self.reference_sequences)
     if not keys:
         return
-    seqs = [self.merged[k][trim_primers:-trim_primers] if trim_primers else self.merged[k] for k in keys]
+    merged = self.merged
+    seqs = [merged[k][trim_primers:-trim_primers] for k in keys] if trim_primers else [merged[k] for k in keys]
     targets = [self.reference_sequences[x].upper() for x in ref_keys]
     seed = B.SEED_GLOBAL if global_align else B.SEED_LOCAL
     logging.info("Matching read bins to references - {0} amplicons x {1} targets on the GPU".format(len(keys), len(ref_keys)))
+    many = not isinstance(gpus, int) or gpus > 1
     try:
-        best_score, best_idx = B.best_hits(_ascii(seqs), _ascii(targets), B.GLOBAL, seed)
+        q, t = B.pack_text(seqs), B.pack_text(targets)          # one join + one encode per set, not one bytes object per amplicon
+        if many:
+            best_score, best_idx = B.best_hits_multi(q, t, gpus, B.GLOBAL, seed)
+        else:
+            best_score, best_idx = B.best_hits(q, t, B.GLOBAL, seed)
     except B.AlignError as e:
         if e.code in (B.ERR_ARGS, B.ERR_UNDEFINED):
-            raise ValueError("NULL pointer access") from e
+            raise ValueError("NULL pointer access") from e     # what ctypes raises on the reference's NULL result
         raise
-    for key, score, idx in zip(keys, best_score.tolist(), best_idx.tolist()):
-        best_hit = ref_keys[idx] if idx >= 0 else ""
-        if best_hit and score > min_score:
-            self.reference[key] = best_hit
-        else:
-            logging.warning("\nWARNING NO MATCH FOR {0}\n Use ambivert --fastqamplicon {1} to retrieve reads from this amplicon".format(
-                self.merged[key], key))
+    # best_hit and best_score > min_score (ambivert.py:528), for all amplicons at once; insertion order = order of `merged`
+    truthy = np.fromiter((bool(r) for r in ref_keys), dtype=bool, count=len(ref_keys))
+    hit = (best_idx >= 0) & (best_score > min_score)
+    hit[hit] &= truthy[best_idx[hit]]
+    which = best_idx[hit].tolist()
+    reference.update(zip(compress(keys, hit.tolist()), (ref_keys[i] for i in which)))
+    for key in compress(keys, (~hit).tolist()):
+        logging.warning("\nWARNING NO MATCH FOR {0}\n Use ambivert --fastqamplicon {1} to retrieve reads from this amplicon".format(
+            merged[key], key))
 
 
 def align_to_reference(self, global_align=True):

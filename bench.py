@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--no-glocal", action="store_true", help="skip the secondary glocal-mode measurement of the same job")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="library tuning option (abv_set_option), e.g. no_levels=1")
     ap.add_argument("--merge-pairs", type=int, default=1000000, help="read pairs of the secondary overlap-merge measurement (0 = skip)")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the pipeline block (merge -> match -> align through host.AmpliconData)")
+    ap.add_argument("--pipeline-gpus", type=int, default=0, help="GPUs the pipeline block's match_to_reference(gpus=) uses from this ONE process (0 = all visible at N=1)")
     return ap.parse_args()
 
 
@@ -287,6 +289,52 @@ def merge_measurement(n_pairs):
             "kernel": "tb16_kernel<local,K=5> (two pairs per warp, 16-bit halves, traceback)", "timing": "best of 3 calls of abv_align_pairs (CUDA events inside the library for the kernel)"}
 
 
+def pipeline_measurement(n_unique, n_targets, gpus):
+    """what the user calls: the on-path pipeline stages through the host mirror of the reference's AmpliconData
+    (ambivert_b200/host.py; ambivert.py:244-262, :301-331, :365-541, :543-574) at config-4 size -- n_unique unique F/R read
+    pairs x n_targets manifest targets -- from Python objects in to Python objects out.  Per stage: wall time, the device
+    part of it (H2D + kernels + D2H, CUDA events inside the library) and the rest (Python + host-side planning)."""
+    from ambivert_b200 import batch as B, synth
+    from ambivert_b200.host import AmpliconData
+    refs, pairs = synth.panel_pipeline_inputs(n_targets=n_targets, n_unique=n_unique, seed=0xC4A)
+    recs = [(("f%d" % i, f, "I" * len(f)), ("r%d" % i, r, "I" * len(r))) for i, (f, r, _c) in enumerate(pairs)]
+
+    def run():
+        amp = AmpliconData()
+        for k, sq in refs:
+            amp.reference_sequences[k] = sq
+        stages = {}
+
+        def stage(name, fn):
+            t0 = time.perf_counter()
+            fn()
+            wall = time.perf_counter() - t0
+            tm = B.timing()
+            dev = (tm["h2d_ms"] + tm["kernel_ms"] + tm["d2h_ms"]) * 1e-3
+            stages[name] = {"wall_s": wall, "device_s": dev, "kernel_ms": tm["kernel_ms"], "python_and_host_s": max(0.0, wall - dev),
+                            "python_share": max(0.0, wall - dev) / wall if wall > 0 else 0.0, "cells": tm["cells"]}
+        stage("cluster (add_read_pairs)", lambda: amp.add_read_pairs(recs))
+        stage("merge_overlaps", lambda: amp.merge_overlaps(threshold=0, minimum_overlap=20))
+        stage("match_to_reference", lambda: amp.match_to_reference(gpus=gpus))
+        stage("align_to_reference", lambda: amp.align_to_reference())
+        return amp, stages
+    run()                                                   # warm-up: device contexts, allocation caches, kernel attributes
+    amp, stages = run()
+    m, a = stages["match_to_reference"], stages["align_to_reference"]
+    out = {"workload": "merge -> match -> align through host.AmpliconData: %d unique 150 bp F/R read pairs x %d manifest targets (config-4 size), %s" % (
+               len(pairs), len(refs), "gpus=%r" % (gpus,)),
+           "api": "ambivert_b200.host.AmpliconData.add_read_pairs / merge_overlaps / match_to_reference(gpus=) / align_to_reference",
+           "stages": stages, "total_wall_s": sum(x["wall_s"] for x in stages.values()),
+           "merged": len(amp.merged), "unmergable": len(amp.unmergable), "matched": len(amp.reference), "aligned": len(amp.aligned),
+           "potential_variants": len(amp.potential_variants),
+           "match_gcups_wall": m["cells"] / m["wall_s"] / 1e9 if m["wall_s"] > 0 else None,
+           # job 3 (ambivert.py:543-574): one global alignment WITH traceback per matched amplicon, packed kernel tb16_kernel<global,K>
+           "job3_final_alignment": {"pairs": len(amp.aligned), "cells": a["cells"], "kernel_ms": a["kernel_ms"],
+                                    "gcups_kernel": a["cells"] / a["kernel_ms"] / 1e6 if a["kernel_ms"] > 0 else None,
+                                    "kernel": "tb16_kernel<global,K=8> (+ assemble kernels for the gapped rows)"}}
+    return out
+
+
 def cluster_measurement(n_pairs):
     """secondary: the step before the path -- md5 keys + grouping of read pairs on the device
     (AmpliconData.add_reads, ambivert.py:244-262), beside hashlib in a Python loop on a sample"""
@@ -429,15 +477,14 @@ def cuda_arm(args, rank, world, local_rank):
         prof = {}
         torch.cuda.synchronize(); barrier()
         ev0.record()
-        for _ in range(steps):
+        for _ in range(steps):                                          # back to back: no host synchronisation inside the timed region
             flush.zero_()
             result = sh.step(dist if world > 1 else None)
-            stream.synchronize()                                        # per-launch CUDA-event times of this step
-            for row in sh.job.profile():
-                p = prof.setdefault(row["K"], {"ms": 0.0, "cells": row["cells"], "queries": row["queries"], "n": 0})
-                p["ms"] += row["ms"]; p["n"] += 1
         ev1.record()
         torch.cuda.synchronize(); barrier()
+        for row in sh.job.profile_history(steps):                       # per-launch CUDA-event times of the timed steps (the last 32 at most)
+            p = prof.setdefault(row["K"], {"ms": 0.0, "cells": row["cells"], "queries": row["queries"], "n": 0})
+            p["ms"] += row["ms"]; p["n"] += 1
         out = {"clocks": sampler.stop() if sampler else None, "elapsed_ms": max_over_ranks(ev0.elapsed_time(ev1)),
                "launches": sh.job.kernel_launches() * steps, "prof": prof, "steps": steps, "warmup": warmup}
         if rank == 0:
@@ -529,6 +576,9 @@ def cuda_arm(args, rank, world, local_rank):
             line["merge"] = merge_measurement(args.merge_pairs)
             line["cluster"] = cluster_measurement(args.merge_pairs)
             line["variants"] = variants_measurement(100000)
+        if world == 1 and not args.no_pipeline:
+            n_q0, n_t0 = WORKLOADS["config4"]
+            line["pipeline"] = pipeline_measurement(args.queries or n_q0, args.targets or n_t0, args.pipeline_gpus or B.device_count())
         if not args.no_cpu_baseline:
             # the reference's CPU path on a sample drawn from ALL shards, beside the GPU's results for the same queries:
             # N = 1: the bounded (~--cpu-seconds) sample that also gives the CPU rate; N > 1: >= 64 queries, parity only

@@ -113,13 +113,18 @@ typedef struct abv_job abv_job;   /* opaque: a many-to-many job whose inputs are
 
 /* device management / diagnostics */
 int abv_device_count(void);               /* number of usable CUDA devices (0 if none) */
-int abv_set_device(int ordinal);          /* device used by subsequent calls of this process */
-int abv_get_device(void);
+int abv_set_device(int ordinal);          /* the process's default device (one process per GPU under torchrun) */
+int abv_set_thread_device(int ordinal);   /* device of the CALLING THREAD's subsequent calls; -1 = the process default.  Every
+                                             device has its own context (streams, allocation cache, lock): host threads working
+                                             on different devices run concurrently */
+int abv_get_device(void);                 /* the calling thread's device */
 const char *abv_last_error(void);         /* message of the last failing call of this thread */
 const char *abv_version(void);
 /* tuning / test options (defaults are what the measurements use):
  *   "path"               ABV_PATH_*            kernel selection of the many-to-many scorer
  *   "split"              0 = automatic         slices of the target pairs per query (short tail on multi-GPU shards)
+ *   "fine_tail"          1                     the last work items of a packed launch are cut into finer slices (the tail of the
+ *                                              persistent grid is one short item long); 0: uniform slices
  *   "tb16"               1                     0: one-to-one jobs always take the 32-bit kernel
  *   "global_v1"          0                     1: first-generation packed kernel for global mode
  *   "no_levels"          0                     1: streaming global kernel resets every pair explicitly (no level staircase)
@@ -149,6 +154,23 @@ int abv_best_hits(int mode,
                   int alpha_len, const unsigned char *map256, const int *score_matrix,
                   int gap_open, int gap_extend, int seed_score,
                   int *best_score, int *best_idx);
+
+/*
+ * The same job on n_devices GPUs of one box from ONE process -- the successor of the reference's --threads
+ * (ambivert.py:474-476, :1092-1095).  The queries are cut into n_devices contiguous shards balanced by
+ * summed length (abv_shard_bounds), every device gets all targets, one host thread per device scores its shard, and each
+ * shard's (best_score, best_idx) go from its device straight into the caller's arrays.  devices = NULL: ordinals
+ * 0 .. n_devices-1; an ordinal may repeat (shards then queue on that device).  Results are identical to abv_best_hits.
+ * (Under torchrun, one process per GPU, the shards are gathered by one NCCL collective instead: ambivert_b200/dist.py.)
+ */
+int abv_best_hits_multi(int mode,
+                        const char *q, const long long *q_off, int n_q,
+                        const char *t, const long long *t_off, int n_t,
+                        int alpha_len, const unsigned char *map256, const int *score_matrix,
+                        int gap_open, int gap_extend, int seed_score,
+                        const int *devices, int n_devices, int *best_score, int *best_idx);
+/* shard r of n_shards owns queries [bounds[r], bounds[r+1]); bounds has n_shards + 1 entries (host logic, no device needed) */
+void abv_shard_bounds(const long long *q_off, int n_q, int n_shards, int *bounds);
 
 /* Full n_q x n_t score matrix (row-major, scores[i*n_t + j]); same arguments. */
 int abv_score_matrix(int mode,
@@ -181,6 +203,11 @@ int abv_job_kernel_launches(const abv_job *job);   /* kernels one abv_best_hits_
  * 4 doubles {K = packed columns per lane, queries, cells, milliseconds by CUDA events on the
  * launch stream}.  Returns the number of rows written (<= max_rows). */
 int abv_job_profile(abv_job *job, double *out, int max_rows);
+/* The same for the last `last_launches` calls of abv_best_hits_launch (the library keeps the event pairs of the last 32), so
+ * that many launches can be timed back to back without a host synchronisation between them: rows of 5 doubles
+ * {K, queries, cells, milliseconds, launch number (0 = the job's first launch)}, oldest launch first.  Call after the last
+ * launch completed.  Returns the number of rows written (<= max_rows). */
+int abv_job_profile_history(abv_job *job, int last_launches, double *out, int max_rows);
 void abv_job_free(abv_job *job);
 
 /*
