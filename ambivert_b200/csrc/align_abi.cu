@@ -439,17 +439,19 @@ int mm16g_launch_one(cudaStream_t st, const Mm16Params &p, int &launched, WorkIt
 template <int MODE>
 int mm16g_launch_mode(int K, cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
   switch (K) {
+#ifndef ABV_TUNE_FAST   // tuning builds (tools/sweep_builds.sh) carry the strip widths of the 200..260 bp panel only
     case 2: return mm16g_launch_one<MODE, 2>(st, p, launched, W, h_list);
     case 3: return mm16g_launch_one<MODE, 3>(st, p, launched, W, h_list);
     case 4: return mm16g_launch_one<MODE, 4>(st, p, launched, W, h_list);
     case 5: return mm16g_launch_one<MODE, 5>(st, p, launched, W, h_list);
     case 6: return mm16g_launch_one<MODE, 6>(st, p, launched, W, h_list);
-    case 7: return mm16g_launch_one<MODE, 7>(st, p, launched, W, h_list);
-    case 8: return mm16g_launch_one<MODE, 8>(st, p, launched, W, h_list);
-    case 9: return mm16g_launch_one<MODE, 9>(st, p, launched, W, h_list);
     case 10: return mm16g_launch_one<MODE, 10>(st, p, launched, W, h_list);
     case 12: return mm16g_launch_one<MODE, 12>(st, p, launched, W, h_list);
     case 16: return mm16g_launch_one<MODE, 16>(st, p, launched, W, h_list);
+#endif
+    case 7: return mm16g_launch_one<MODE, 7>(st, p, launched, W, h_list);
+    case 8: return mm16g_launch_one<MODE, 8>(st, p, launched, W, h_list);
+    case 9: return mm16g_launch_one<MODE, 9>(st, p, launched, W, h_list);
   }
   return fail(ABV_ERR_ARGS, "no packed kernel for K=%d", K);
 }
@@ -594,6 +596,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   J.n_pairs_stream = n_pairs_stream;
   auto stream_ok = [&](int K) {
     if (g_opt.global_v1 || n_pairs_stream == 0) return false;
+    if (mm16g_border(K, mode == ABV_GLOCAL) && sc.go > sc.ge) return false;   // the border lane's fixed point needs Ec <= Hc (dp_core.cuh); never the pipeline's scoring
     if (!packed_exact_streaming(mode, 32 * K, tp_stride, maxabs, sc.ge)) return false;
     if (n_pairs_stream < n_pairs_all) {
       const int K2 = K + (K & 1);
@@ -603,14 +606,17 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   };
   std::vector<std::vector<int>> lists(MM16_NK);
   std::vector<int> wf32_list;
+  bool st_okv[MM16_NK];
+  for (int k = 0; k < MM16_NK; ++k) st_okv[k] = stream_ok(MM16_KS[k]);
   for (int i = 0; i < n_q; ++i) {
     const int lq = (int)(q_off[i + 1] - q_off[i]);
     int slot = -1;
     if (packed_ok) {
       for (int k = 0; k < MM16_NK; ++k) {
         const int K = MM16_KS[k];
-        if (K % 2 && !stream_ok(K)) continue;
-        if (32 * K >= lq) { slot = k; break; }
+        const bool st_ok = st_okv[k];
+        if (K % 2 && !st_ok) continue;
+        if ((st_ok ? mm16g_capacity(K, mode == ABV_GLOCAL) : 32 * K) >= lq) { slot = k; break; }   // the streaming kernel gives lane 31 to the border (dp_core.cuh)
       }
       if (slot >= 0) {
         const int K = MM16_KS[slot];

@@ -562,6 +562,25 @@ ABV_HD int variants_walk(const unsigned char *v, const unsigned char *r, int n, 
   return VAR_OK;
 }
 
+// The BORDER LANE of the streaming kernel.  Column -1 of the DP matrix (what lane 0 receives "from the left") is a constant
+// pair in drift form: (H~, E~) = (Hc, Ec) = (go + g, 2go) + level for global, (-inf, -inf) for glocal.  Selecting it into
+// lane 0's shuffle results costs two SEL per step on the pipe that bounds the kernel (7.7 % of its ALU-pipe instructions at
+// K = 8) and sits on the step's dependent chain.  Instead lane 31 owns no query columns: its profile is all zero, it receives
+// its OWN outputs (shuffle by index: lane 0 reads lane 31, lane 31 reads itself, lane t reads lane t-1), and with
+//   Hp[k] = hleft = Hc for all k,  e = Ec,  F[k] <= Hc      (Hc + (go - g) = Ec for global; all -inf for glocal)
+// the common row maps this state onto itself: h_k = max3(Hc + 0, Ec, F) = Hc, e' = max(Hc + go - g, Ec) = Ec.  So lane 31
+// emits (Hc, Ec) every step without a single extra instruction in the loops; its state is (re)written at the warp-uniform
+// points where the constants change (pair start of an explicitly reset pair, around the separator row of an injected one).
+// A strip width K then serves queries of up to 31K columns; the widest strip keeps the select form and all 32 lanes.
+#ifndef ABV_NO_BORDER
+#define ABV_NO_BORDER 0
+#endif
+// Measured (B200, 20k x 2k panel, profiles/r02_ab_*.jsonl): global +2.7 % per executed cell, +0.7 % net of the queries that move up
+// one strip width; glocal -2.2 % (its switching steps and parked rows dominate what the selects cost): glocal keeps the selects.
+ABV_HD constexpr bool mm16g_border(int K, bool glocal) { return !ABV_NO_BORDER && !glocal && K < 16; }
+ABV_HD constexpr int mm16g_capacity(int K, bool glocal) { return mm16g_border(K, glocal) ? 31 * K : 32 * K; }   // query columns a strip width serves
+constexpr int MM16G_BORDER_LANE = 31;
+
 // pair-row bookkeeping of the streaming kernel, shared by the kernel and its CPU mirror
 constexpr int MM16G_MIN_ROWS = 32;   // every pair occupies at least 32 steps: lane t switches pair t steps after lane 0
 ABV_HD int mm16g_rows(int l1, int l2) {

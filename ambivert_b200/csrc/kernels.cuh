@@ -44,6 +44,13 @@ constexpr int kGlSwitchUnroll = ABV_GL_SW_UNROLL;   // glocal (deferred last row
 #define ABV_INJ_UNROLL 4   // measured: 1: 8.065, 2: 8.040, 4: 8.084, 8: 8.088 TCUPS
 #endif
 constexpr int kInjUnroll = ABV_INJ_UNROLL;         // the same for the (lighter) switching segments of injected pairs   // steps of the pair-switching segments unrolled together (code size: instruction cache)
+#ifndef ABV_LDS_PTX
+#define ABV_LDS_PTX 1      // streaming kernel: profile vectors by ld.shared with one multiply-add of address arithmetic per step
+#endif
+#ifndef ABV_DYN_PAIRS
+#define ABV_DYN_PAIRS 1   // streaming kernel: the warps of a CTA take the target pairs of a work item from a shared counter (1) or strided (0)
+#endif
+constexpr bool kDynPairs = ABV_DYN_PAIRS != 0;
 #ifndef ABV_MINB8
 #define ABV_MINB8 3   // measured on B200: 3 CTAs (24 warps, <= 85 registers) beat 4 (32 warps, 64 registers) by 4 %; 2 and 5 are slower
 #endif
@@ -1015,6 +1022,23 @@ __device__ __forceinline__ void mm16_load_S(const uint32_t *lut_row, int lane, u
   }
 }
 
+// The streaming kernel addresses its profile row as ONE multiply-add per step: lane_addr (shared-window address of the lane's
+// first vector, fixed per CTA) + code * row bytes; the vectors of a row are 32 lanes apart (immediate offsets).
+template <int KP>
+__device__ __forceinline__ void mm16g_load_S(uint32_t lane_addr, int code, uint32_t (&S)[KP]) {
+  constexpr int V = (KP % 4 == 0) ? 4 : 2;
+  const uint32_t a = lane_addr + (uint32_t)code * (32u * KP * 4u);
+  if (V == 4) {
+#pragma unroll
+    for (int i = 0; i < KP / 4; ++i)
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(S[4 * i]), "=r"(S[4 * i + 1]), "=r"(S[4 * i + 2]), "=r"(S[4 * i + 3]) : "r"(a + i * 512u));
+  } else {
+#pragma unroll
+    for (int i = 0; i < KP / 2; ++i)
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(S[2 * i]), "=r"(S[2 * i + 1]) : "r"(a + i * 256u));
+  }
+}
+
 template <int K>
 __device__ __forceinline__ uint32_t mm16_pick(const uint32_t (&Hp)[K], int kstar) {
   uint32_t v = Hp[0];
@@ -1270,6 +1294,8 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
   static_assert(MODE == GLOBAL || MODE == GLOCAL, "the streaming kernel implements global and glocal");
   constexpr bool GL = (MODE == GLOCAL);
   constexpr bool DEFER = mm16g_defer(GL, K);
+  constexpr bool BORDER = mm16g_border(K, GL);          // lane 31 emits the constants of column -1 (dp_core.cuh)
+  constexpr int BL = MM16G_BORDER_LANE;
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int KP = StripCfg<K>::KP;
   constexpr int P = StripCfg<K>::P;
@@ -1309,7 +1335,7 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
   __syncthreads();
 
   for (;;) {
-    if (threadIdx.x == 0) misc[0] = (int)atomicAdd(p.q_counter, 1u);
+    if (threadIdx.x == 0) { misc[0] = (int)atomicAdd(p.q_counter, 1u); misc[1] = 0; }
     __syncthreads();
     const int item = misc[0];
     if (item >= p.n_items) break;
@@ -1325,22 +1351,33 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
       const int k = i * V + j;                                // k >= K: padding word of an odd strip, never used
       const int qa = (k < K ? (int)qcodes[t * K + k] : a1 - 1) * a1;
       const int a = code / a1, bsym = code - a * a1;
-      lut[idx] = b16::addend(mext[qa + a] - 2 * ge, mext[qa + bsym] - 2 * ge);
+      lut[idx] = (BORDER && t == BL) ? 0u : b16::addend(mext[qa + a] - 2 * ge, mext[qa + bsym] - 2 * ge);
     }
     __syncthreads();
 
-    const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;
+    const int tstar = (lq - 1) / K, kstar = (lq - 1) - tstar * K;      // BORDER: tstar <= 30 (the host's bucket capacity, mm16g_capacity)
     const int c0 = lane * K;
-    const uint32_t G0 = b16::biased(ge * (1 - c0), ge * (1 - c0));      // glocal: H~[c0][-1] of a starting pair (dp_core.cuh, MM16G_NO_EGAP)
-    const int n_mine = pair_hi - pair_lo;                          // this item's slice of the target pairs
-    const int n_i = warp < n_mine ? (n_mine - warp + W - 1) / W : 0;
-    const int pbase = pair_lo + warp;                              // this warp takes pairs pbase + i*W
+    // glocal: H~[c0][-1] of a starting pair (dp_core.cuh, MM16G_NO_EGAP).  The border lane takes a value from which its switch
+    // (Hp[k] = G0 + k|g|, hleft = G0 + g) lands at or below -inf: one row later it is back on its fixed point
+    const uint32_t G0 = (BORDER && lane == BL) ? NEGb + (uint32_t)(K - 1) * gew : b16::biased(ge * (1 - c0), ge * (1 - c0));
+    // The warps of the CTA share the item's slice [pair_lo, pair_hi) of the target pairs.  Each warp takes its next pair from a
+    // counter in shared memory at the moment it issues the pair's copy (two pairs ahead), so that all eight warps run out of pairs
+    // within one pair's duration of each other: handed out strided, the warps (two per SM sub-partition, progressing at different
+    // rates) reached the item-end barrier spread over 5.7 % of the kernel's warp time (ncu, profiles/r02_*).
+    auto take_pair = [&](int strided) {                            // warp-uniform; >= pair_hi: no pair left
+      if (!kDynPairs) return strided;
+      int v = 0;
+      if (lane == 0) v = atomicAdd(&misc[1], 1);
+      return pair_lo + __shfl_sync(ABV_FULL, v, 0);
+    };
+    int p_cur = take_pair(pair_lo + warp);
+    int p_next = p_cur < pair_hi ? take_pair(pair_lo + warp + W) : pair_hi;
     int wbest = INT_MIN, widx = INT_MAX;
 
-    if (n_i > 0) {
+    if (p_cur < pair_hi) {
       if (lane == 0) {
-        bulk_load(smem + tbuf0, p.tp_codes + (long long)pbase * p.tp_stride, p.tp_stride, &bar[0]);
-        if (n_i > 1) bulk_load(smem + tbuf0 + p.tp_stride, p.tp_codes + (long long)(pbase + W) * p.tp_stride, p.tp_stride, &bar[1]);
+        bulk_load(smem + tbuf0, p.tp_codes + (long long)p_cur * p.tp_stride, p.tp_stride, &bar[0]);
+        if (p_next < pair_hi) bulk_load(smem + tbuf0 + p.tp_stride, p.tp_codes + (long long)p_next * p.tp_stride, p.tp_stride, &bar[1]);
       }
       uint32_t Hp[K], F[K], S[KP];
 #pragma unroll
@@ -1349,23 +1386,46 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
       int tb_off = L.zero + 32 - lane;           // before its first pair a lane sweeps zero (valid) symbols
       int prev_rows = 0;
       int pend_s1 = -1, pend_s2 = -1, pend_i1 = -1, pend_i2 = -1, pend_d1 = 0, pend_d2 = 0;
-      int4 meta_next = p.tp_meta[pbase];
+      int4 meta_next = p.tp_meta[p_cur];
       // glocal: last-row events of the previous pair that are still to come (they are spread over the
       // lanes like the pair switches: lane t reaches row r at step r + t of the pair's own time line)
       const int NOEV = 1 << 20;
       int pend_e1 = NOEV, pend_e2 = NOEV, pend_r1 = 0, pend_r2 = 0;
       uint32_t lm0 = NEGb, lm1 = NEGb;       // glocal: this lane's last-row maxima of the pairs of even / odd parity (both halves)
 
+#if defined(ABV_DUMMY_FMA) || defined(ABV_DUMMY_ALU)
+      uint32_t dummy[4] = {(uint32_t)lane, (uint32_t)warp, 7u, 11u};
+#endif
       uint32_t Hc = Hc0, Ec = Ec0, H00 = H000;       // boundary constants of the pair lane 0 is on (its level added)
       int lv_i = 0;                                  // position of the current pair on the staircase of levels
+      const uint32_t lut_lane = smem_u32(lut) + (uint32_t)lane * (V * 4u);      // this lane's first vector of profile row 0
+      const int src_lane = lane == 0 ? BL : (lane == BL ? BL : lane - 1);   // BORDER: who a lane receives its left border from
       auto exchange = [&](uint32_t &h_sh, uint32_t &e_sh) {
-        h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
-        e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
-        if (lane == 0) { h_sh = Hc; e_sh = Ec; }
+        if (BORDER) {
+          h_sh = __shfl_sync(ABV_FULL, h_out, src_lane);
+          e_sh = __shfl_sync(ABV_FULL, e_out, src_lane);
+        } else {
+          h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
+          e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+          if (lane == 0) { h_sh = Hc; e_sh = Ec; }
+        }
       };
+      // the border lane on the fixed point of the constants (hc, ec) (dp_core.cuh, mm16g_border)
+      auto border_set = [&](uint32_t hc, uint32_t ec) {
+        if (BORDER && lane == BL) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) { Hp[k] = hc; F[k] = ec; }
+          hleft = hc; h_out = hc; e_out = ec;
+        }
+      };
+      if (GL) border_set(NEGb, NEGb);                // glocal: column -1 is minus infinity for every pair
       auto row_e = [&](int s, uint32_t h_sh, uint32_t e_sh, uint32_t gope) {   // one row of this lane; gope: addend of the row-gap chain
         const int code = smem[tb_off + s];
+#if ABV_LDS_PTX
+        mm16g_load_S<KP>(lut_lane, code, S);
+#else
         mm16_load_S<KP>(lut + code * P, lane, S);
+#endif
         uint32_t e = e_sh;
         mm16d_row<K, KP>(hleft, e, Hp, F, S, gop2, gope);
         hleft = h_sh; e_out = e; h_out = Hp[K - 1];
@@ -1375,6 +1435,14 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         uint32_t h_sh, e_sh;
         exchange(h_sh, e_sh);
         row(s, h_sh, e_sh);
+#ifdef ABV_DUMMY_FMA      // sensitivity experiment: extra FMA-pipe instructions per step (tools/sweep_builds.sh)
+#pragma unroll
+        for (int d = 0; d < ABV_DUMMY_FMA; ++d) asm volatile("mad.lo.u32 %0, %0, 3, 1;" : "+r"(dummy[d & 3]));
+#endif
+#ifdef ABV_DUMMY_ALU      // ... and extra ALU-pipe instructions per step
+#pragma unroll
+        for (int d = 0; d < ABV_DUMMY_ALU; ++d) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(dummy[d & 3]) : "r"(dummy[(d + 1) & 3]), "r"(dummy[(d + 2) & 3]));
+#endif
       };
       // glocal, the lane is on the last target row r of a half: the forced diagonal (glocal_align.c:172-183)
       // is what S[] holds after the row's first pass; every real query column competes for the end
@@ -1418,13 +1486,13 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         }
       };
 
-      for (int i = 0; i <= n_i; ++i) {
-        const bool real = i < n_i;
+      for (int i = 0;; ++i) {
+        const bool real = p_cur < pair_hi;                    // the iteration after the last pair drains the lane pipeline
         int4 meta = make_int4(0, 0, -1, -1);
         int rows = MM16G_MIN_ROWS, bufoff = L.zero + 32;
         if (real) {
           meta = meta_next;
-          if (i + 1 < n_i) meta_next = p.tp_meta[pbase + (i + 1) * W];
+          if (p_next < pair_hi) meta_next = p.tp_meta[p_next];
           rows = mm16g_rows(meta.x, meta.y);
           const int b = i % 3;
           bufoff = tbuf0 + b * p.tp_stride;
@@ -1441,19 +1509,22 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         // global: this pair's level; pair 0 of the item, every lv_n-th pair and the draining dummy pair are reset explicitly
         lv_i = (i == 0 || !real || lv_i + 1 >= lv_n) ? 0 : lv_i + 1;
         const bool inj = !GL && lv_i != 0;
-        const bool inj_next = !GL && i + 1 < n_i && lv_i + 1 < lv_n;
+        const bool inj_next = !GL && real && p_next < pair_hi && lv_i + 1 < lv_n;
         const int lvl = GL ? 0 : p.lv0 + lv_i * p.lv_step;
         if (!GL) {
           const uint32_t lw = b16::addend(lvl, lvl);
           Hc = Hc0 + lw; Ec = Ec0 + lw; H00 = H000 + lw;
+          if (!inj) border_set(Hc, Ec);              // an explicitly reset pair: lane 0 reads this level's constants from its step 0 on
         }
         const int dr1 = ge * (lq - 1 + meta.x - 1) - lvl, dr2 = ge * (lq - 1 + meta.y - 1) - lvl;   // undo drift and level at the corner
         const int par = i & 1;
+        int p_nn = pair_hi;
         auto issue_next_copy = [&]() {       // every lane has left pair i-1: its buffer can take pair i+2
           __syncwarp();
-          if (lane == 0 && i + 2 < n_i) {
+          if (p_next < pair_hi) p_nn = take_pair(p_next + W);
+          if (lane == 0 && p_nn < pair_hi) {
             const int b2 = (i + 2) % 3;
-            bulk_load(smem + tbuf0 + b2 * p.tp_stride, p.tp_codes + (long long)(pbase + (i + 2) * W) * p.tp_stride, p.tp_stride, &bar[b2]);
+            bulk_load(smem + tbuf0 + b2 * p.tp_stride, p.tp_codes + (long long)p_nn * p.tp_stride, p.tp_stride, &bar[b2]);
           }
         };
         if (DEFER) {
@@ -1674,10 +1745,17 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
             // the separator row (the pad row after the pair's last row): lane 0 takes E~ = Hc of the next level from the
             // left, and as its diagonal for the next pair's row 0 that level's H~[-1][-1]
             const uint32_t up = b16::addend(p.lv_step, p.lv_step);
-            uint32_t h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
-            uint32_t e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
-            if (lane == 0) { h_sh = H00 + up; e_sh = Hc + up; }
+            uint32_t h_sh, e_sh;
+            if (BORDER) {
+              if (lane == BL) { h_out = H00 + up; e_out = Hc + up; }
+              exchange(h_sh, e_sh);
+            } else {
+              h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
+              e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+              if (lane == 0) { h_sh = H00 + up; e_sh = Hc + up; }
+            }
             row(s, h_sh, e_sh);
+            border_set(Hc + up, Ec + up);              // from the next pair's step 0 on lane 0 reads the next level's constants
             captures(s);
             rows += 1;
           }
@@ -1687,7 +1765,12 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
         pend_e1 = ev1 == NOEV ? NOEV : ev1 - rows; pend_r1 = meta.x - 1;
         pend_e2 = ev2 == NOEV ? NOEV : ev2 - rows; pend_r2 = meta.y - 1;
         prev_rows = rows;
+        if (!real) break;
+        p_cur = p_next; p_next = p_nn;
       }
+#if defined(ABV_DUMMY_FMA) || defined(ABV_DUMMY_ALU)
+      if (dummy[0] + dummy[1] + dummy[2] + dummy[3] == 0x12345u) wbest = 0;      // keeps the experiment's chains alive
+#endif
     }
 
     if (lane == (GL ? 0 : tstar)) { wres[2 * warp] = wbest; wres[2 * warp + 1] = widx; }

@@ -250,6 +250,8 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
                         const unsigned char *const *t2s, const int *l2s, int alpha, const int *M, int go, int ge,
                         int *sc1_out, int *sc2_out) {
   constexpr int KP = StripCfg<K>::KP, V = StripCfg<K>::V, P = StripCfg<K>::P;
+  constexpr bool BORDER = mm16g_border(K, GL);      // lane 31 emits the constants of column -1 (dp_core.cuh)
+  constexpr int BL = MM16G_BORDER_LANE;
   const int a1 = alpha + 1, ncodes = a1 * a1;
   std::vector<int> mext((size_t)a1 * a1, 0);
   for (int x = 0; x < alpha; ++x) for (int y = 0; y < alpha; ++y) mext[x * a1 + y] = M[x * alpha + y];
@@ -262,7 +264,7 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
     const int k = i * V + j;
     const int qa = (k < K ? (int)qcodes[t * K + k] : a1 - 1) * a1;
     const int a = code / a1, b = code - a * a1;
-    lut[idx] = b16::addend(mext[qa + a] - 2 * ge, mext[qa + b] - 2 * ge);
+    lut[idx] = (BORDER && t == BL) ? 0u : b16::addend(mext[qa + a] - 2 * ge, mext[qa + b] - 2 * ge);
   }
   int max_lt = 1;
   for (int i = 0; i < n_pairs; ++i) max_lt = std::max(max_lt, std::max(l1s[i], l2s[i]));
@@ -334,9 +336,14 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
       }
     }
     uint32_t h_sh[32], e_sh[32];
-    for (int t = 0; t < 32; ++t) { h_sh[t] = t ? h_out[t - 1] : h_out[0]; e_sh[t] = t ? e_out[t - 1] : e_out[0]; }
-    h_sh[0] = Hc; e_sh[0] = Ec;
-    if (inject) { const uint32_t up = b16::addend(lv.step, lv.step); h_sh[0] = H00 + up; e_sh[0] = Hc + up; }
+    if (BORDER) {      // shuffle by index: lane 0 reads the border lane, the border lane reads itself
+      if (inject) { const uint32_t up = b16::addend(lv.step, lv.step); h_out[BL] = H00 + up; e_out[BL] = Hc + up; }
+      for (int t = 0; t < 32; ++t) { const int src = t == 0 ? BL : (t == BL ? BL : t - 1); h_sh[t] = h_out[src]; e_sh[t] = e_out[src]; }
+    } else {
+      for (int t = 0; t < 32; ++t) { h_sh[t] = t ? h_out[t - 1] : h_out[0]; e_sh[t] = t ? e_out[t - 1] : e_out[0]; }
+      h_sh[0] = Hc; e_sh[0] = Ec;
+      if (inject) { const uint32_t up = b16::addend(lv.step, lv.step); h_sh[0] = H00 + up; e_sh[0] = Hc + up; }
+    }
     for (int t = 0; t < 32; ++t) {
       const int at = tb_off[t] + s;
       if (at < buf_lo[t] || at >= buf_hi[t]) throw 2;      // a row read outside the buffer of the pair the lane is on
@@ -346,7 +353,7 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
       uint32_t gope = gop2;
       if (GL && t == sw) {      // row 0 of a starting pair through the common row (dp_core.cuh, MM16G_NO_EGAP), as the kernel does
         const int c0 = t * K;
-        const uint32_t G0 = b16::biased(ge * (1 - c0), ge * (1 - c0));
+        const uint32_t G0 = (BORDER && t == BL) ? NEGb + (uint32_t)(K - 1) * gew : b16::biased(ge * (1 - c0), ge * (1 - c0));
         for (int k = 0; k < K; ++k) { Hp[t][k] = G0 - (uint32_t)k * gew; F[t][k] = NEGb; }
         hleft[t] = G0 + gew;
         e_sh[t] = NEGb;
@@ -364,6 +371,12 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
     }
   };
   int lvl = 0, pend_lvl = 0, lv_i = 0;
+  auto border_set = [&](uint32_t hc, uint32_t ec) {      // the border lane on the fixed point of (hc, ec), as the kernel does
+    if (!BORDER) return;
+    for (int k = 0; k < K; ++k) { Hp[BL][k] = hc; F[BL][k] = ec; }
+    hleft[BL] = hc; h_out[BL] = hc; e_out[BL] = ec;
+  };
+  if (GL) border_set(NEGb, NEGb);
   auto capture = [&](int half, int idx, int par, int level) {
     if (GL) {
       (half ? sc2_out : sc1_out)[idx] = fold(half, (half ? l2s[idx] : l1s[idx]) - 1);
@@ -386,7 +399,10 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
     const bool inj_next = !GL && i + 1 < n_i && lv_i + 1 < lv.n;
     pend_lvl = lvl;
     lvl = GL ? 0 : lv.lvl0 + lv_i * lv.step;
-    if (!GL) { const uint32_t lw = b16::addend(lvl, lvl); Hc = Hc0 + lw; Ec = Ec0 + lw; H00 = H000 + lw; }
+    if (!GL) {
+      const uint32_t lw = b16::addend(lvl, lvl); Hc = Hc0 + lw; Ec = Ec0 + lw; H00 = H000 + lw;
+      if (explicit_reset) border_set(Hc, Ec);
+    }
     for (int s = 0; s < MM16G_MIN_ROWS; ++s) {
       step(s, s, bufoff, ev1, l1 - 1, ev2, l2 - 1, true, par);
       if (s == pend_s1) capture(0, pend_i1, par ^ 1, pend_lvl);
@@ -417,6 +433,7 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
         inject = true;
         step(s, -1, 0, NOEV, 0, NOEV, 0, false, par);
         inject = false;
+        { const uint32_t up = b16::addend(lv.step, lv.step); border_set(Hc + up, Ec + up); }
         if (s == cs1) capture(0, i, par, lvl);
         if (s == cs2) capture(1, i, par, lvl);
         rows += 1;
@@ -449,10 +466,13 @@ static int emu_mm16g_k(int K, const unsigned char *q, int lq, int n_pairs, const
   return -1;
 }
 
+extern "C" int emu_mm16g_capacity(int K, int glocal) { return mm16g_capacity(K, glocal != 0); }   // query columns the streaming kernel serves with strips of K
+
 extern "C" int emu_mm16g(int mode, int K, const unsigned char *q, int lq, int n_pairs, const unsigned char *const *t1s, const int *l1s,
                          const unsigned char *const *t2s, const int *l2s, int alpha, const int *M, int go, int ge,
                          int *sc1, int *sc2) {
-  if (32 * K < lq) return -1;
+  const bool glocal = mode == GLOCAL;
+  if (mm16g_capacity(K, glocal) < lq || (mm16g_border(K, glocal) && go > ge)) return -1;   // the border lane's fixed point needs Ec <= Hc, i.e. go <= ge (the host keeps such scorings off it)
   try {
     if (mode == GLOBAL) return emu_mm16g_k<false>(K, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2);
     if (mode == GLOCAL) return emu_mm16g_k<true>(K, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2);

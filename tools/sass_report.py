@@ -116,22 +116,28 @@ def main():
     print("\n== whole kernel, opcode histogram ==")
     for k, v in h.most_common(40):
         print("  %-28s %6d" % (k, v))
-    bl = blocks(ins)
+    # loops = regions [target, branch] of BACKWARD branches (the unrolled loops start with a BRA.DIV of the warp shuffle,
+    # so they are not single basic blocks); keep the innermost ones and take the one with the most DPX instructions
+    index = {a: i for i, (a, _) in enumerate(ins)}
+    regions = []
+    for i, (a, t) in enumerate(ins):
+        m = re.search(r"BRA(?:\.[A-Z.]+)?\s+(?:!?U?P\d,\s*)?0x([0-9a-f]+)", t)
+        if m and t.startswith("@") and opcode(t).startswith("BRA") and int(m.group(1), 16) <= a and int(m.group(1), 16) in index:   # loops close with a predicated branch
+            regions.append((index[int(m.group(1), 16)], i))
+    def dpx_of(blk):
+        return sum(v for k, v in histogram(blk).items() if k.startswith(ALU_HALF))
     loops = []
-    for blk in bl:
-        last = opcode(blk[-1][1])
-        m = re.search(r"0x([0-9a-f]+)", blk[-1][1])
-        if last.startswith("BRA") and m and int(m.group(1), 16) == blk[0][0]:
-            loops.append(blk)
-    print("\n== self-looping basic blocks (candidates for the steady-state loop), largest first ==")
-    for blk in sorted(loops, key=len, reverse=True)[:8]:
-        hh = histogram(blk)
-        dpx = sum(v for k, v in hh.items() if k.startswith(ALU_HALF))
-        print("  0x%05x..0x%05x  %5d instructions, %4d DPX/min-max" % (blk[0][0], blk[-1][0], len(blk), dpx))
+    for lo, hi in regions:
+        inner = [r for r in regions if r != (lo, hi) and r[0] >= lo and r[1] <= hi and dpx_of(ins[r[0]:r[1] + 1]) > 0]
+        if not inner:
+            loops.append(ins[lo:hi + 1])
+    print("\n== innermost loops (backward-branch regions), by DPX/min-max instructions ==")
+    for blk in sorted(loops, key=dpx_of, reverse=True)[:8]:
+        print("  0x%05x..0x%05x  %5d instructions, %4d DPX/min-max" % (blk[0][0], blk[-1][0], len(blk), dpx_of(blk)))
     if not loops:
         print("  (none)")
         return
-    hot = max(loops, key=lambda blk: sum(v for k, v in histogram(blk).items() if k.startswith(ALU_HALF)))
+    hot = max(loops, key=dpx_of)
     hh = histogram(hot)
     print("\n== steady-state loop 0x%05x..0x%05x: %d instructions ==" % (hot[0][0], hot[-1][0], len(hot)))
     for k, v in hh.most_common():
