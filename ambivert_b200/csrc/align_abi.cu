@@ -105,6 +105,8 @@ struct Options {
   int global_v1 = 0;            // 1 = use the first-generation packed kernel for global mode too
   int no_gop_imm = 0;           // 1 = never take the streaming kernel's instantiation with the gap addend as an immediate
   int no_levels = 0;            // 1 = streaming global kernel resets every pair explicitly (no level staircase, mm16g_levels)
+  int concurrent_buckets = 1;   // 1 = the packed launches of a job (one per strip width) go to streams of their own, largest first:
+                                //     the CTAs of the next launch fill the tail of the previous persistent grid
   int tb16 = 1;                 // 0 = one-to-one jobs always take the 32-bit kernel
   int pairs_chunk = 200000;     // one-to-one jobs of at least 2x this many pairs run as a pipeline of chunks (0 = never)
 };
@@ -506,9 +508,22 @@ struct abv_job {
     std::shared_ptr<WorkItems> items, items_short;      // work-item tables of its launch(es), built at the first launch
   };
   std::vector<int> h_lists;        // host copy of `lists`
-  std::vector<Bucket> buckets;     // packed-kernel launches (one per K class), lists at `offset`
+  std::vector<Bucket> buckets;     // packed-kernel launches (one per K class), lists at `offset`; largest first
+  // concurrent launches: bucket j runs on side[j] between the fork event (recorded on the caller's stream after the counter
+  // memsets) and its join event (which the caller's stream waits for before the finalize kernel).  side[0], the largest
+  // launch, has the highest stream priority: its persistent grid takes every SM slot first and the block scheduler hands the
+  // slots to the other launches as its CTAs retire (at equal priority the grids share the SMs from the start: same
+  // throughput, but no launch can be timed alone)
+  std::vector<cudaStream_t> side;
+  cudaEvent_t ev_fork = nullptr;
+  std::vector<cudaEvent_t> ev_join;
   long long n_launches = 0;        // abv_best_hits_launch calls so far
-  ~abv_job() { for (auto &b : buckets) for (auto e : b.ev) if (e) cudaEventDestroy(e); }
+  ~abv_job() {
+    for (auto &b : buckets) for (auto e : b.ev) if (e) cudaEventDestroy(e);
+    for (auto s : side) if (s) cudaStreamDestroy(s);
+    for (auto e : ev_join) if (e) cudaEventDestroy(e);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+  }
   int n_wf32 = 0, wf32_offset = 0; // queries served by the 32-bit kernel, list at `wf32_offset`
   int wf32_blocks = 0;             // its grid, fixed when `border` was sized (the option may change before the launch)
   int n_counters = 0;
@@ -641,6 +656,18 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
       J.buckets.push_back(b);
       flat.insert(flat.end(), lists[k].begin(), lists[k].end());
     }
+  // largest launch first: it is the one whose tail the others fill, and the one bench.py reports the roofline of
+  std::stable_sort(J.buckets.begin(), J.buckets.end(), [](const abv_job::Bucket &a, const abv_job::Bucket &b) { return a.cells > b.cells; });
+  if (J.buckets.size() > 1) {
+    CU(cudaEventCreateWithFlags(&J.ev_fork, cudaEventDisableTiming));
+    J.side.assign(J.buckets.size(), nullptr);
+    J.ev_join.assign(J.buckets.size(), nullptr);
+    int prio_least = 0, prio_greatest = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    for (size_t j = 0; j < J.side.size(); ++j)
+      CU(cudaStreamCreateWithPriority(&J.side[j], cudaStreamNonBlocking, j == 0 ? prio_greatest : prio_least));
+    for (auto &e : J.ev_join) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   J.wf32_offset = (int)flat.size();
   J.n_wf32 = (int)wf32_list.size();
   flat.insert(flat.end(), wf32_list.begin(), wf32_list.end());
@@ -734,7 +761,13 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
   if (!J.buckets.empty()) CU(cudaMemsetAsync(J.best_key.p, 0, sizeof(unsigned long long) * (size_t)J.n_q, st));
   int launched = 0;
   int ci = 0;
-  for (const auto &b : J.buckets) {
+  const bool fork = g_opt.concurrent_buckets && J.buckets.size() > 1;
+  if (fork) CU(cudaEventRecord(J.ev_fork, st));
+  cudaStream_t caller = st;
+  for (size_t bj = 0; bj < J.buckets.size(); ++bj) {
+    const auto &b = J.buckets[bj];
+    st = fork ? J.side[bj] : caller;
+    if (fork) CU(cudaStreamWaitEvent(st, J.ev_fork, 0));
     Mm16Params p{};
     p.q = J.q_codes.as<uint8_t>(); p.q_off = J.q_off.as<long long>();
     p.q_list = J.lists.as<int>() + b.offset; p.n_list = b.n;
@@ -762,7 +795,12 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
       if ((rc = mm16_launch(J.mode, b.K + (b.K & 1), false, st, r, launched, *b.items_short, J.h_lists.data() + b.offset))) return rc;
     } else if ((rc = mm16_launch(J.mode, b.K, b.streaming, st, p, launched, *b.items, J.h_lists.data() + b.offset))) return rc;
     CU(cudaEventRecord(b.ev[2 * slot + 1], st));
+    if (fork) {
+      CU(cudaEventRecord(J.ev_join[bj], st));
+      CU(cudaStreamWaitEvent(caller, J.ev_join[bj], 0));
+    }
   }
+  st = caller;
   if (!J.buckets.empty()) {   // seed rule + unpack, over the queries the packed kernels served
     const int n_packed = J.wf32_offset;
     best_key_finalize_kernel<<<(n_packed + 255) / 256, 256, 0, st>>>(J.best_key.as<unsigned long long>(), J.lists.as<int>(), n_packed,
@@ -962,6 +1000,7 @@ int abv_set_option(const char *key, int value) {
   }
   if (!strcmp(key, "split")) { g_opt.split = std::max(0, std::min(value, 64)); return ABV_OK; }
   if (!strcmp(key, "fine_tail")) { g_opt.fine_tail = value ? 1 : 0; return ABV_OK; }
+  if (!strcmp(key, "concurrent_buckets")) { g_opt.concurrent_buckets = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "tb16")) { g_opt.tb16 = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "global_v1")) { g_opt.global_v1 = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "no_gop_imm")) { g_opt.no_gop_imm = value ? 1 : 0; return ABV_OK; }
