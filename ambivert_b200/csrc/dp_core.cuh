@@ -433,12 +433,12 @@ ABV_HD uint32_t tb16_insert(uint32_t acc, uint32_t x, uint32_t m) {
 //   Slo,Shi : addend-packed substitution scores of the two pairs' columns for this row's symbols
 //   gow,gew : b16::addend(go,go), b16::addend(ge,ge);  zerob = b16::biased(0,0)
 //   sh,MJ : 15 - step % 16 and 0x80008000 >> sh: where this step's bits go in the plane words acc[k][plane]
-//   LOCAL : cand[k] = running best value of column c0+k (both halves), crow[k] = its row (lo | hi << 16);
-//           rr = r | r << 16.  '>=' so that the last row wins ties within a column (local_align.c:156-160)
+//   LOCAL : cand[k] = running best value of column c0+k (both halves), crl[k] / crh[k] = its row in the low / high half;
+//           r = this row.  '>=' so that the last row wins ties within a column (local_align.c:156-160)
 template <int MODE, int K>
 ABV_HD void tb16_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], const uint32_t *Slo, const uint32_t *Shi,
                      uint32_t gow, uint32_t gew, uint32_t zerob, int sh, uint32_t MJ, uint32_t (&acc)[K][TB16_PLANES],
-                     uint32_t (&cand)[K], uint32_t (&crow)[K], uint32_t rr) {
+                     uint32_t (&cand)[K], int (&crl)[K], int (&crh)[K], int r) {
   uint32_t d = hleft;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -456,8 +456,8 @@ ABV_HD void tb16_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&
       b1 = pb & pc;                                       // plane 1 holds the COMPLEMENT of source bit 1
       bool pn_h, pn_l;
       cand[k] = p16::bmax(hr, cand[k], pn_h, pn_l);       // a stop cell (hr < 0) never beats a candidate (>= -1)
-      if (pn_l) crow[k] = (crow[k] & 0xffff0000u) | (rr & 0x0000ffffu);
-      if (pn_h) crow[k] = (crow[k] & 0x0000ffffu) | (rr & 0xffff0000u);
+      if (pn_l) crl[k] = r;                                // one predicated move per half (a row packed into the halves of
+      if (pn_h) crh[k] = r;                                // one word took two logic ops per half: 8 % of the kernel's issue cycles)
     } else {
       b0 = ~pa & pb;
       b1 = pb;

@@ -267,6 +267,11 @@ constexpr int TB16_WARPS = 4;
 #ifndef TB16_UNROLL
 #define TB16_UNROLL 2
 #endif
+#ifndef TB16_MINB
+#define TB16_MINB 6
+#endif
+// resident CTAs the register allocation aims at: the shared memory of the profiles allows 6 CTAs of 4 warps at K <= 5 (85 registers)
+#define TB16_MIN_BLOCKS(K) ((K) <= 5 ? TB16_MINB : ((K) <= 8 ? 4 : 3))
 constexpr int kTb16Unroll = TB16_UNROLL;   // steps of the fill loop unrolled together (the whole 16 thrash the instruction cache)
 template <int K>
 __host__ __device__ inline int tb16_smem_per_warp(int a1, int rows_cap) {
@@ -339,7 +344,7 @@ __device__ __forceinline__ int tb16_walk(const Tb16Reader<K> &rd, int col, int r
 }
 
 template <int MODE, int K>
-__global__ void __launch_bounds__(TB16_WARPS * 32) tb16_kernel(Tb16Params p) {
+__global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kernel(Tb16Params p) {
   static_assert(MODE == LOCAL || MODE == GLOBAL, "tb16 implements local and global");
   constexpr int V = Tb16Cfg<K>::V, P = Tb16Cfg<K>::P;
   extern __shared__ __align__(16) unsigned char tb_smem[];
@@ -392,7 +397,8 @@ __global__ void __launch_bounds__(TB16_WARPS * 32) tb16_kernel(Tb16Params p) {
     }
     __syncwarp();
 
-    uint32_t Hp[K], F[K], acc[K][TB16_PLANES], cand[K], crow[K];
+    uint32_t Hp[K], F[K], acc[K][TB16_PLANES], cand[K];
+    int crl[K], crh[K];
     uint32_t hleft, h_out, e_out;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(TB16_WARPS * 32) tb16_kernel(Tb16Params p) {
       else { Hp[k] = zerob; F[k] = b16::biased(go, go); }
 #pragma unroll
       for (int q = 0; q < TB16_PLANES; ++q) acc[k][q] = 0;
-      cand[k] = b16::biased(-1, -1); crow[k] = 0;
+      cand[k] = b16::biased(-1, -1); crl[k] = 0; crh[k] = 0;
     }
     if (MODE == GLOBAL) hleft = c0 ? b16::biased(go + ge * (c0 - 1), go + ge * (c0 - 1)) : zerob;
     else hleft = zerob;
@@ -445,7 +451,7 @@ __global__ void __launch_bounds__(TB16_WARPS * 32) tb16_kernel(Tb16Params p) {
             for (int i = 0; i < K; ++i) { Slo[i] = rlo[i * 32 + lane]; Shi[i] = rhi[i * 32 + lane]; }
           }
           uint32_t e = e_sh;
-          tb16_row<MODE, K>(hleft, e, Hp, F, Slo, Shi, gow, gew, zerob, 15 - j, TB16_H >> (15 - j), acc, cand, crow, (uint32_t)r * 0x10001u);
+          tb16_row<MODE, K>(hleft, e, Hp, F, Slo, Shi, gow, gew, zerob, 15 - j, TB16_H >> (15 - j), acc, cand, crl, crh, r);
           hleft = h_sh; e_out = e; h_out = Hp[K - 1];
           if (MODE == GLOBAL) {                                   // the corner cell is the score (global_align.c:217)
             if (r == lb0 - 1 && lane == t0) corner0 = b16::lo(tb16_pick<K>(Hp, k0));
@@ -474,8 +480,8 @@ __global__ void __launch_bounds__(TB16_WARPS * 32) tb16_kernel(Tb16Params p) {
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const int v0 = b16::lo(cand[k]), v1 = b16::hi(cand[k]);
-        if (v0 >= 0 && v0 >= b0) { b0 = v0; bc0 = c0 + k; br0 = (int)(crow[k] & 0xffffu); }
-        if (v1 >= 0 && v1 >= b1) { b1 = v1; bc1 = c0 + k; br1 = (int)(crow[k] >> 16); }
+        if (v0 >= 0 && v0 >= b0) { b0 = v0; bc0 = c0 + k; br0 = crl[k]; }
+        if (v1 >= 0 && v1 >= b1) { b1 = v1; bc1 = c0 + k; br1 = crh[k]; }
       }
       long long key0 = b0 < 0 ? -1 : (((long long)b0 << 40) | ((long long)bc0 << 20) | br0);
       long long key1 = b1 < 0 ? -1 : (((long long)b1 << 40) | ((long long)bc1 << 20) | br1);

@@ -522,7 +522,7 @@ static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *t
   }
   const uint32_t gow = b16::addend(go, go), gew = b16::addend(ge, ge), zerob = b16::biased(0, 0);
   std::vector<uint32_t> dir((size_t)K * TB16_PLANES * steps16 * 32, 0xdeadbeefu);
-  struct Lane { uint32_t Hp[K], F[K], acc[K][TB16_PLANES], cand[K], crow[K], hleft, h_out, e_out; };
+  struct Lane { uint32_t Hp[K], F[K], acc[K][TB16_PLANES], cand[K], hleft, h_out, e_out; int crl[K], crh[K]; };
   std::vector<Lane> L(32);
   for (int t = 0; t < 32; ++t) {
     const int c0 = t * K;
@@ -531,7 +531,7 @@ static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *t
       if (MODE == GLOBAL) { L[t].Hp[k] = b16::biased(go + ge * c, go + ge * c); L[t].F[k] = b16::biased(2 * go + ge * c, 2 * go + ge * c); }
       else { L[t].Hp[k] = zerob; L[t].F[k] = b16::biased(go, go); }
       for (int q = 0; q < TB16_PLANES; ++q) L[t].acc[k][q] = 0;
-      L[t].cand[k] = b16::biased(-1, -1); L[t].crow[k] = 0;
+      L[t].cand[k] = b16::biased(-1, -1); L[t].crl[k] = 0; L[t].crh[k] = 0;
     }
     L[t].hleft = (MODE == GLOBAL && c0) ? b16::biased(go + ge * (c0 - 1), go + ge * (c0 - 1)) : zerob;
     L[t].h_out = zerob; L[t].e_out = zerob;
@@ -559,8 +559,7 @@ static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *t
             Shi[k] = prof[(a1 + (code >> 8)) * P + tb16_slot(t, k, V)];
           }
           uint32_t e = e_sh[t];
-          tb16_row<MODE, K>(L[t].hleft, e, L[t].Hp, L[t].F, Slo, Shi, gow, gew, zerob, 15 - j, TB16_H >> (15 - j), L[t].acc, L[t].cand, L[t].crow,
-                            (uint32_t)r * 0x10001u);
+          tb16_row<MODE, K>(L[t].hleft, e, L[t].Hp, L[t].F, Slo, Shi, gow, gew, zerob, 15 - j, TB16_H >> (15 - j), L[t].acc, L[t].cand, L[t].crl, L[t].crh, r);
           L[t].hleft = h_sh[t]; L[t].e_out = e; L[t].h_out = L[t].Hp[K - 1];
           if (MODE == GLOBAL) {
             if (r == lb0 - 1 && t == t0) corner0 = b16::lo(L[t].Hp[k0]);
@@ -584,8 +583,8 @@ static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *t
       int b[2] = {-1, -1}, bc[2] = {0, 0}, br[2] = {0, 0};
       for (int k = 0; k < K; ++k) {
         const int v0 = b16::lo(L[t].cand[k]), v1 = b16::hi(L[t].cand[k]);
-        if (v0 >= 0 && v0 >= b[0]) { b[0] = v0; bc[0] = t * K + k; br[0] = (int)(L[t].crow[k] & 0xffffu); }
-        if (v1 >= 0 && v1 >= b[1]) { b[1] = v1; bc[1] = t * K + k; br[1] = (int)(L[t].crow[k] >> 16); }
+        if (v0 >= 0 && v0 >= b[0]) { b[0] = v0; bc[0] = t * K + k; br[0] = L[t].crl[k]; }
+        if (v1 >= 0 && v1 >= b[1]) { b[1] = v1; bc[1] = t * K + k; br[1] = L[t].crh[k]; }
       }
       for (int h = 0; h < 2; ++h)
         key[h] = std::max(key[h], b[h] < 0 ? -1ll : (((long long)b[h] << 40) | ((long long)bc[h] << 20) | br[h]));
