@@ -218,6 +218,12 @@ def score_matrix(queries, targets, mode=GLOBAL, alpha_len=DNA_MAP[0], map256=DNA
     return out
 
 
+def _lanes(k_field):
+    """abv_job_profile reports K + 0.5 for a bucket that runs the border-lane instantiation of the streaming global kernel
+    (31 lanes own query columns: queries of up to 31K columns) and plain K where all 32 lanes do"""
+    return 31 if k_field != int(k_field) else 32
+
+
 class BestHitsJob:
     """A many-to-many job whose inputs stay resident in HBM (abv_best_hits_prepare/launch/fetch)."""
 
@@ -243,16 +249,17 @@ class BestHitsJob:
         return int(_lib.abv_job_kernel_launches(self._h))
 
     def profile(self):
-        """per packed-kernel launch of the last launch(): list of dict(K, queries, cells, ms)"""
+        """per packed-kernel launch of the last launch(): list of dict(K, lanes, queries, cells, ms); lanes = 31: the border-lane
+        instantiation of the streaming global kernel (queries of up to 31K columns), 32: every lane owns query columns"""
         out = np.zeros((16, 4), np.float64)
         n = _lib.abv_job_profile(self._h, out.ctypes.data_as(_vp), 16)
-        return [dict(K=int(r[0]), queries=int(r[1]), cells=float(r[2]), ms=float(r[3])) for r in out[:n]]
+        return [dict(K=int(r[0]), lanes=_lanes(r[0]), queries=int(r[1]), cells=float(r[2]), ms=float(r[3])) for r in out[:n]]
 
     def profile_history(self, last_launches):
         """the same for the last `last_launches` (<= 32) calls of launch(), timed back to back: dicts with `launch` added"""
         out = np.zeros((16 * 32, 5), np.float64)
         n = _lib.abv_job_profile_history(self._h, int(last_launches), out.ctypes.data_as(_vp), out.shape[0])
-        return [dict(K=int(r[0]), queries=int(r[1]), cells=float(r[2]), ms=float(r[3]), launch=int(r[4])) for r in out[:n]]
+        return [dict(K=int(r[0]), lanes=_lanes(r[0]), queries=int(r[1]), cells=float(r[2]), ms=float(r[3]), launch=int(r[4])) for r in out[:n]]
 
     def fetch(self):
         bs = np.empty(self.n_q, np.int32)

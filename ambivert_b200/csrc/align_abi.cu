@@ -22,6 +22,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "kernels.cuh"
+#include <cuda.h>      // CUstream / CUdeviceptr of cuStreamWaitValue32, which is looked up at run time (cudaGetDriverEntryPoint)
 
 namespace {
 
@@ -105,6 +106,7 @@ struct Options {
   int global_v1 = 0;            // 1 = use the first-generation packed kernel for global mode too
   int no_gop_imm = 0;           // 1 = never take the streaming kernel's instantiation with the gap addend as an immediate
   int no_levels = 0;            // 1 = streaming global kernel resets every pair explicitly (no level staircase, mm16g_levels)
+  int no_border = 0;            // 1 = streaming global never takes the border-lane instantiation (every query keeps all 32 lanes)
   int concurrent_buckets = 1;   // 1 = the packed launches of a job (one per strip width) go to streams of their own, largest first:
                                 //     the CTAs of the next launch fill the tail of the previous persistent grid
   int tb16 = 1;                 // 0 = one-to-one jobs always take the 32-bit kernel
@@ -169,6 +171,19 @@ int ctx_init() {
   for (auto &ev : c.ev) CU(cudaEventCreate(&ev));
   c.inited = true;
   return ABV_OK;
+}
+
+// cuStreamWaitValue32: a stream waits until a 32-bit word in device memory reaches a value.  The packed launches of a job use it
+// to start the grid of the next strip width exactly when the previous persistent grid begins to drain (Mm16Params::tail_flag).
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWaitValue32Fn stream_wait_value32() {
+  static StreamWaitValue32Fn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) { cudaGetLastError(); f = nullptr; }
+    return (StreamWaitValue32Fn)f;
+  }();
+  return fn;
 }
 
 // RAII device allocation
@@ -410,10 +425,10 @@ int mm16_launch_one(int grid_cap, cudaStream_t st, const Mm16Params &p, int &lau
   return ABV_OK;
 }
 
-template <int MODE, int K, int GOPC>
+template <int MODE, int K, int GOPC, bool BORDER>
 int mm16g_launch_gop(cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
   const Mm16gSmem L = mm16g_smem_layout(K, p.a1, p.tp_stride, mm16g_defer(MODE == GLOCAL, K));
-  auto kern = mm16g_kernel<MODE, K, GOPC>;
+  auto kern = mm16g_kernel<MODE, K, GOPC, BORDER>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MM16_WARPS * 32, L.total));
@@ -431,35 +446,42 @@ int mm16g_launch_gop(cudaStream_t st, const Mm16Params &p, int &launched, WorkIt
   return ABV_OK;
 }
 
-template <int MODE, int K>
-int mm16g_launch_one(cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
+template <int MODE, int K, bool BORDER>
+int mm16g_launch_var(cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
   // the pipeline's gap penalties (-7, -1) take the instantiation with the gap addend as an immediate
-  if (p.go - p.ge == MM16G_GOP_DNA && !g_opt.no_gop_imm) return mm16g_launch_gop<MODE, K, MM16G_GOP_DNA>(st, p, launched, W, h_list);
-  return mm16g_launch_gop<MODE, K, MM16G_GOP_RUNTIME>(st, p, launched, W, h_list);
+  if (p.go - p.ge == MM16G_GOP_DNA && !g_opt.no_gop_imm) return mm16g_launch_gop<MODE, K, MM16G_GOP_DNA, BORDER>(st, p, launched, W, h_list);
+  return mm16g_launch_gop<MODE, K, MM16G_GOP_RUNTIME, BORDER>(st, p, launched, W, h_list);
+}
+template <int MODE, int K>
+int mm16g_launch_one(bool border, cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
+  if constexpr (mm16g_border(K, MODE == GLOCAL)) {
+    if (border) return mm16g_launch_var<MODE, K, true>(st, p, launched, W, h_list);
+  }
+  return mm16g_launch_var<MODE, K, false>(st, p, launched, W, h_list);
 }
 
 template <int MODE>
-int mm16g_launch_mode(int K, cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
+int mm16g_launch_mode(int K, bool border, cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
   switch (K) {
 #ifndef ABV_TUNE_FAST   // tuning builds (tools/sweep_builds.sh) carry the strip widths of the 200..260 bp panel only
-    case 2: return mm16g_launch_one<MODE, 2>(st, p, launched, W, h_list);
-    case 3: return mm16g_launch_one<MODE, 3>(st, p, launched, W, h_list);
-    case 4: return mm16g_launch_one<MODE, 4>(st, p, launched, W, h_list);
-    case 5: return mm16g_launch_one<MODE, 5>(st, p, launched, W, h_list);
-    case 6: return mm16g_launch_one<MODE, 6>(st, p, launched, W, h_list);
-    case 10: return mm16g_launch_one<MODE, 10>(st, p, launched, W, h_list);
-    case 12: return mm16g_launch_one<MODE, 12>(st, p, launched, W, h_list);
-    case 16: return mm16g_launch_one<MODE, 16>(st, p, launched, W, h_list);
+    case 2: return mm16g_launch_one<MODE, 2>(border, st, p, launched, W, h_list);
+    case 3: return mm16g_launch_one<MODE, 3>(border, st, p, launched, W, h_list);
+    case 4: return mm16g_launch_one<MODE, 4>(border, st, p, launched, W, h_list);
+    case 5: return mm16g_launch_one<MODE, 5>(border, st, p, launched, W, h_list);
+    case 6: return mm16g_launch_one<MODE, 6>(border, st, p, launched, W, h_list);
+    case 10: return mm16g_launch_one<MODE, 10>(border, st, p, launched, W, h_list);
+    case 12: return mm16g_launch_one<MODE, 12>(border, st, p, launched, W, h_list);
+    case 16: return mm16g_launch_one<MODE, 16>(border, st, p, launched, W, h_list);
 #endif
-    case 7: return mm16g_launch_one<MODE, 7>(st, p, launched, W, h_list);
-    case 8: return mm16g_launch_one<MODE, 8>(st, p, launched, W, h_list);
-    case 9: return mm16g_launch_one<MODE, 9>(st, p, launched, W, h_list);
+    case 7: return mm16g_launch_one<MODE, 7>(border, st, p, launched, W, h_list);
+    case 8: return mm16g_launch_one<MODE, 8>(border, st, p, launched, W, h_list);
+    case 9: return mm16g_launch_one<MODE, 9>(border, st, p, launched, W, h_list);
   }
   return fail(ABV_ERR_ARGS, "no packed kernel for K=%d", K);
 }
 
-int mm16g_launch(int mode, int K, cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
-  return mode == ABV_GLOCAL ? mm16g_launch_mode<GLOCAL>(K, st, p, launched, W, h_list) : mm16g_launch_mode<GLOBAL>(K, st, p, launched, W, h_list);
+int mm16g_launch(int mode, int K, bool border, cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
+  return mode == ABV_GLOCAL ? mm16g_launch_mode<GLOCAL>(K, border, st, p, launched, W, h_list) : mm16g_launch_mode<GLOBAL>(K, border, st, p, launched, W, h_list);
 }
 
 template <int MODE>
@@ -476,8 +498,8 @@ int mm16_launch_mode(int K, cudaStream_t st, const Mm16Params &p, int &launched,
   return fail(ABV_ERR_ARGS, "no packed kernel for K=%d", K);
 }
 
-int mm16_launch(int mode, int K, bool streaming, cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
-  if ((mode == ABV_GLOBAL || mode == ABV_GLOCAL) && streaming) return mm16g_launch(mode, K, st, p, launched, W, h_list);
+int mm16_launch(int mode, int K, bool streaming, bool border, cudaStream_t st, const Mm16Params &p, int &launched, WorkItems &W, const int *h_list) {
+  if ((mode == ABV_GLOBAL || mode == ABV_GLOCAL) && streaming) return mm16g_launch(mode, K, border, st, p, launched, W, h_list);
   if (mode == ABV_GLOBAL) return mm16_launch_mode<GLOBAL>(K, st, p, launched, W, h_list);
   if (mode == ABV_LOCAL) return mm16_launch_mode<LOCAL>(K, st, p, launched, W, h_list);
   if (mode == ABV_GLOCAL) return mm16_launch_mode<GLOCAL>(K, st, p, launched, W, h_list);
@@ -505,15 +527,18 @@ struct abv_job {
   static constexpr int PROFILE_RING = 32;
   struct Bucket {
     int K, n, offset; double cells; std::vector<cudaEvent_t> ev; bool streaming;
+    bool border;                    // streaming global: the border-lane instantiation (queries of up to 31K columns)
     std::shared_ptr<WorkItems> items, items_short;      // work-item tables of its launch(es), built at the first launch
   };
   std::vector<int> h_lists;        // host copy of `lists`
   std::vector<Bucket> buckets;     // packed-kernel launches (one per K class), lists at `offset`; largest first
   // concurrent launches: bucket j runs on side[j] between the fork event (recorded on the caller's stream after the counter
-  // memsets) and its join event (which the caller's stream waits for before the finalize kernel).  side[0], the largest
-  // launch, has the highest stream priority: its persistent grid takes every SM slot first and the block scheduler hands the
-  // slots to the other launches as its CTAs retire (at equal priority the grids share the SMs from the start: same
-  // throughput, but no launch can be timed alone)
+  // memsets) and its join event (which the caller's stream waits for before the finalize kernel).  The launch of bucket j > 0
+  // additionally waits (cuStreamWaitValue32) for the tail flag of bucket j-1: the word its first CTA without a work item
+  // sets.  So the grids run one after the other, largest first, each starting exactly when the one before begins to drain
+  // and filling the SM slots that grid's CTAs give up; every launch is still timed alone by its event pair.  (Stream
+  // priorities alone did this on one GPU but not under torchrun with NCCL initialised: the grids then shared the SMs from
+  // the start -- same throughput, no clean per-launch time.)
   std::vector<cudaStream_t> side;
   cudaEvent_t ev_fork = nullptr;
   std::vector<cudaEvent_t> ev_join;
@@ -611,7 +636,6 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   J.n_pairs_stream = n_pairs_stream;
   auto stream_ok = [&](int K) {
     if (g_opt.global_v1 || n_pairs_stream == 0) return false;
-    if (mm16g_border(K, mode == ABV_GLOCAL) && sc.go > sc.ge) return false;   // the border lane's fixed point needs Ec <= Hc (dp_core.cuh); never the pipeline's scoring
     if (!packed_exact_streaming(mode, 32 * K, tp_stride, maxabs, sc.ge)) return false;
     if (n_pairs_stream < n_pairs_all) {
       const int K2 = K + (K & 1);
@@ -619,19 +643,23 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
     }
     return true;
   };
-  std::vector<std::vector<int>> lists(MM16_NK);
+  // lists[2k]: the bucket of strip width K; lists[2k + 1]: streaming global, its queries that fit the border-lane instantiation
+  // (up to 31K columns; the border lane's fixed point needs Ec <= Hc, i.e. go <= ge: dp_core.cuh, mm16g_border)
+  std::vector<std::vector<int>> lists(2 * MM16_NK);
   std::vector<int> wf32_list;
-  bool st_okv[MM16_NK];
-  for (int k = 0; k < MM16_NK; ++k) st_okv[k] = stream_ok(MM16_KS[k]);
+  bool st_okv[MM16_NK], border_okv[MM16_NK];
+  for (int k = 0; k < MM16_NK; ++k) {
+    st_okv[k] = stream_ok(MM16_KS[k]);
+    border_okv[k] = st_okv[k] && mm16g_border(MM16_KS[k], mode == ABV_GLOCAL) && sc.go <= sc.ge && !g_opt.no_border;
+  }
   for (int i = 0; i < n_q; ++i) {
     const int lq = (int)(q_off[i + 1] - q_off[i]);
     int slot = -1;
     if (packed_ok) {
       for (int k = 0; k < MM16_NK; ++k) {
         const int K = MM16_KS[k];
-        const bool st_ok = st_okv[k];
-        if (K % 2 && !st_ok) continue;
-        if ((st_ok ? mm16g_capacity(K, mode == ABV_GLOCAL) : 32 * K) >= lq) { slot = k; break; }   // the streaming kernel gives lane 31 to the border (dp_core.cuh)
+        if (K % 2 && !st_okv[k]) continue;
+        if (32 * K >= lq) { slot = k; break; }
       }
       if (slot >= 0) {
         const int K = MM16_KS[slot];
@@ -639,22 +667,23 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
         else if (std::max(mm16_smem_layout(K, a1, tp_stride).total, mm16g_smem_layout(K, a1, tp_stride, mm16g_defer(mode == ABV_GLOCAL, K)).total) > 100 * 1024) slot = -1;
       }
     }
-    if (slot >= 0) lists[slot].push_back(i); else wf32_list.push_back(i);
+    if (slot >= 0) lists[2 * slot + ((border_okv[slot] && 31 * MM16_KS[slot] >= lq) ? 1 : 0)].push_back(i); else wf32_list.push_back(i);
   }
   if (g_opt.path == ABV_PATH_PACKED && !wf32_list.empty())
     return fail(ABV_ERR_ARGS, "packed path forced but %zu queries are not eligible for it", wf32_list.size());
 
   std::vector<int> flat;
-  for (int k = 0; k < MM16_NK; ++k)
-    if (!lists[k].empty()) {
+  for (int k2 = 0; k2 < 2 * MM16_NK; ++k2)
+    if (!lists[k2].empty()) {
+      const int k = k2 / 2;
       double qlen = 0;
-      for (int i : lists[k]) qlen += (double)(q_off[i + 1] - q_off[i]);
-      abv_job::Bucket b{MM16_KS[k], (int)lists[k].size(), (int)flat.size(), qlen * (double)(t_off[n_t] - t_off[0]), {},
-                        stream_ok(MM16_KS[k]), std::make_shared<WorkItems>(), std::make_shared<WorkItems>()};
+      for (int i : lists[k2]) qlen += (double)(q_off[i + 1] - q_off[i]);
+      abv_job::Bucket b{MM16_KS[k], (int)lists[k2].size(), (int)flat.size(), qlen * (double)(t_off[n_t] - t_off[0]), {},
+                        st_okv[k], (k2 & 1) != 0, std::make_shared<WorkItems>(), std::make_shared<WorkItems>()};
       b.ev.assign(2 * abv_job::PROFILE_RING, nullptr);
       for (auto &e : b.ev) CU(cudaEventCreate(&e));
       J.buckets.push_back(b);
-      flat.insert(flat.end(), lists[k].begin(), lists[k].end());
+      flat.insert(flat.end(), lists[k2].begin(), lists[k2].end());
     }
   // largest launch first: it is the one whose tail the others fill, and the one bench.py reports the roofline of
   std::stable_sort(J.buckets.begin(), J.buckets.end(), [](const abv_job::Bucket &a, const abv_job::Bucket &b) { return a.cells > b.cells; });
@@ -676,7 +705,7 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   CU(cudaMemcpyAsync(J.lists.p, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));
   J.h2d_bytes += sizeof(int) * flat.size();
-  J.n_counters = 2 * (int)J.buckets.size() + 64;
+  J.n_counters = 2 * (int)J.buckets.size() + 64 + 16;      // the last 16 words (32 x 32 bits): tail flags of the packed launches
   CU(J.counters.alloc(sizeof(unsigned long long) * J.n_counters));
 
   // ---- target pairs for the packed kernel: sort by length, pair neighbours ----------------------
@@ -761,13 +790,18 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
   if (!J.buckets.empty()) CU(cudaMemsetAsync(J.best_key.p, 0, sizeof(unsigned long long) * (size_t)J.n_q, st));
   int launched = 0;
   int ci = 0;
-  const bool fork = g_opt.concurrent_buckets && J.buckets.size() > 1;
+  const bool fork = g_opt.concurrent_buckets && J.buckets.size() > 1 && stream_wait_value32() != nullptr;
+  unsigned int *flags = reinterpret_cast<unsigned int *>(J.counters.as<unsigned long long>() + J.n_counters - 16);   // zeroed with the counters
   if (fork) CU(cudaEventRecord(J.ev_fork, st));
   cudaStream_t caller = st;
   for (size_t bj = 0; bj < J.buckets.size(); ++bj) {
     const auto &b = J.buckets[bj];
     st = fork ? J.side[bj] : caller;
-    if (fork) CU(cudaStreamWaitEvent(st, J.ev_fork, 0));
+    if (fork) {
+      CU(cudaStreamWaitEvent(st, J.ev_fork, 0));
+      if (bj > 0 && stream_wait_value32()((CUstream)st, (CUdeviceptr)(uintptr_t)(flags + (bj - 1)), 1u, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+        return fail(ABV_ERR_CUDA, "cuStreamWaitValue32 failed");
+    }
     Mm16Params p{};
     p.q = J.q_codes.as<uint8_t>(); p.q_off = J.q_off.as<long long>();
     p.q_list = J.lists.as<int>() + b.offset; p.n_list = b.n;
@@ -779,6 +813,7 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
     p.all_scores = J.want_all_scores ? J.all_scores.as<int>() : nullptr; p.n_t = J.n_t;
     p.q_counter = reinterpret_cast<unsigned int *>(J.counters.as<unsigned long long>() + ci++);
     p.best_key = J.best_key.as<unsigned long long>();
+    p.tail_flag = (fork && bj + 1 < J.buckets.size() && bj < 32) ? flags + bj : nullptr;
     {
       const Mm16gLevels lv = (b.streaming && J.mode == ABV_GLOBAL && !g_opt.no_levels)
                                  ? mm16g_levels(32 * b.K, J.tp_stride, J.go, J.ge, J.maxabs, J.maxpos) : Mm16gLevels{1, 0, 0};
@@ -788,12 +823,13 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
     CU(cudaEventRecord(b.ev[2 * slot], st));
     if (b.streaming && J.n_pairs_stream < J.n_pairs) {
       Mm16Params r = p;                                  // the short target pairs at the end of the list
+      p.tail_flag = nullptr;                             // ... whose launch is the bucket's last one
       r.tp_codes += (size_t)J.n_pairs_stream * J.tp_stride; r.tp_meta += J.n_pairs_stream; r.n_pairs = J.n_pairs - J.n_pairs_stream;
       r.q_counter = reinterpret_cast<unsigned int *>(J.counters.as<unsigned long long>() + ci++);
       p.n_pairs = J.n_pairs_stream;
-      if ((rc = mm16_launch(J.mode, b.K, true, st, p, launched, *b.items, J.h_lists.data() + b.offset))) return rc;
-      if ((rc = mm16_launch(J.mode, b.K + (b.K & 1), false, st, r, launched, *b.items_short, J.h_lists.data() + b.offset))) return rc;
-    } else if ((rc = mm16_launch(J.mode, b.K, b.streaming, st, p, launched, *b.items, J.h_lists.data() + b.offset))) return rc;
+      if ((rc = mm16_launch(J.mode, b.K, true, b.border, st, p, launched, *b.items, J.h_lists.data() + b.offset))) return rc;
+      if ((rc = mm16_launch(J.mode, b.K + (b.K & 1), false, false, st, r, launched, *b.items_short, J.h_lists.data() + b.offset))) return rc;
+    } else if ((rc = mm16_launch(J.mode, b.K, b.streaming, b.border, st, p, launched, *b.items, J.h_lists.data() + b.offset))) return rc;
     CU(cudaEventRecord(b.ev[2 * slot + 1], st));
     if (fork) {
       CU(cudaEventRecord(J.ev_join[bj], st));
@@ -822,8 +858,8 @@ int job_launch(abv_job &J, cudaStream_t st, int *d_best_score, int *d_best_idx) 
       p.q_list = J.lists.as<int>() + J.wf32_offset;
       p.matrix = J.matrix.as<int>(); p.alpha = J.alpha; p.go = J.go; p.ge = J.ge;
       p.border = J.border.as<int>(); p.border_len = J.max_lt;
-      if (ci >= J.n_counters) {   // counters exhausted: reset and reuse (launches are stream-ordered)
-        CU(cudaMemsetAsync(J.counters.p, 0, sizeof(unsigned long long) * J.n_counters, st));
+      if (ci >= J.n_counters - 16) {   // counters exhausted: reset and reuse (launches are stream-ordered); the last 16 words are the tail flags
+        CU(cudaMemsetAsync(J.counters.p, 0, sizeof(unsigned long long) * (J.n_counters - 16), st));
         ci = 0;
       }
       p.pair_counter = J.counters.as<unsigned long long>() + ci++;
@@ -1000,6 +1036,7 @@ int abv_set_option(const char *key, int value) {
   }
   if (!strcmp(key, "split")) { g_opt.split = std::max(0, std::min(value, 64)); return ABV_OK; }
   if (!strcmp(key, "fine_tail")) { g_opt.fine_tail = value ? 1 : 0; return ABV_OK; }
+  if (!strcmp(key, "no_border")) { g_opt.no_border = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "concurrent_buckets")) { g_opt.concurrent_buckets = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "tb16")) { g_opt.tb16 = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "global_v1")) { g_opt.global_v1 = value ? 1 : 0; return ABV_OK; }
@@ -1056,7 +1093,7 @@ int abv_job_profile(abv_job *job, double *out, int max_rows) {
     if (n >= max_rows) break;
     float ms = 0;
     if (cudaEventElapsedTime(&ms, b.ev[2 * slot], b.ev[2 * slot + 1]) != cudaSuccess) { cudaGetLastError(); ms = -1; }
-    out[4 * n] = b.K; out[4 * n + 1] = b.n; out[4 * n + 2] = b.cells; out[4 * n + 3] = ms;
+    out[4 * n] = b.K + (b.border ? 0.5 : 0.0); out[4 * n + 1] = b.n; out[4 * n + 2] = b.cells; out[4 * n + 3] = ms;
     ++n;
   }
   return n;
@@ -1074,7 +1111,7 @@ int abv_job_profile_history(abv_job *job, int last_launches, double *out, int ma
       if (n >= max_rows) return n;
       float ms = 0;
       if (cudaEventElapsedTime(&ms, b.ev[2 * slot], b.ev[2 * slot + 1]) != cudaSuccess) { cudaGetLastError(); ms = -1; }
-      out[5 * n] = b.K; out[5 * n + 1] = b.n; out[5 * n + 2] = b.cells; out[5 * n + 3] = ms; out[5 * n + 4] = (double)l;
+      out[5 * n] = b.K + (b.border ? 0.5 : 0.0); out[5 * n + 1] = b.n; out[5 * n + 2] = b.cells; out[5 * n + 3] = ms; out[5 * n + 4] = (double)l;
       ++n;
     }
   }

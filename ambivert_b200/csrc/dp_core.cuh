@@ -571,14 +571,14 @@ ABV_HD int variants_walk(const unsigned char *v, const unsigned char *r, int n, 
 // the common row maps this state onto itself: h_k = max3(Hc + 0, Ec, F) = Hc, e' = max(Hc + go - g, Ec) = Ec.  So lane 31
 // emits (Hc, Ec) every step without a single extra instruction in the loops; its state is (re)written at the warp-uniform
 // points where the constants change (pair start of an explicitly reset pair, around the separator row of an injected one).
-// A strip width K then serves queries of up to 31K columns; the widest strip keeps the select form and all 32 lanes.
+// A strip width K then serves queries of up to 31K columns; the queries of (31K, 32K] columns, the widest strip and glocal take the
+// instantiation that keeps the selects and all 32 lanes (template parameter BORDER of mm16g_kernel).
 #ifndef ABV_NO_BORDER
 #define ABV_NO_BORDER 0
 #endif
-// Measured (B200, 20k x 2k panel, profiles/r02_ab_*.jsonl): global +2.7 % per executed cell, +0.7 % net of the queries that move up
-// one strip width; glocal -2.2 % (its switching steps and parked rows dominate what the selects cost): glocal keeps the selects.
+// Measured (B200, 20k x 2k panel, profiles/r02_ab_*.jsonl): global +2.7 % per executed cell; glocal +1 % per executed cell, less than
+// the queries that would move up a strip width cost (its switching steps and parked rows dominate): glocal keeps the selects.
 ABV_HD constexpr bool mm16g_border(int K, bool glocal) { return !ABV_NO_BORDER && !glocal && K < 16; }
-ABV_HD constexpr int mm16g_capacity(int K, bool glocal) { return mm16g_border(K, glocal) ? 31 * K : 32 * K; }   // query columns a strip width serves
 constexpr int MM16G_BORDER_LANE = 31;
 
 // pair-row bookkeeping of the streaming kernel, shared by the kernel and its CPU mirror

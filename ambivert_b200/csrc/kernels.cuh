@@ -972,6 +972,8 @@ struct Mm16Params {
   int *best_score, *best_idx;                 // indexed by query
   int *all_scores; int n_t;                   // optional full score matrix [query*n_t + target]
   unsigned int *q_counter;
+  unsigned int *tail_flag;                    // optional: set to 1 by the first CTA that finds no work item left -- the launch of the next
+                                              // strip width waits for it on its own stream (cuStreamWaitValue32) and fills this grid's tail
   unsigned long long *best_key;               // per query: packed (score, target) of the best hit so far, see best_key_pack
   const int4 *items; int n_items;             // work items of this launch, built by the host: {query, first target pair, end target pair, -};
                                               // a persistent CTA takes the next one with an atomic counter
@@ -1107,7 +1109,10 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16_
     if (threadIdx.x == 0) misc[0] = (int)atomicAdd(p.q_counter, 1u);
     __syncthreads();
     const int item = misc[0];
-    if (item >= p.n_items) break;
+    if (item >= p.n_items) {
+      if (threadIdx.x == 0 && p.tail_flag) atomicExch(p.tail_flag, 1u);
+      break;
+    }
     const int4 work = p.items[item];
     const int qi = work.x, pair_lo = work.y, pair_hi = work.z;
     const uint8_t *qs = p.q + p.q_off[qi];
@@ -1295,12 +1300,14 @@ __host__ __device__ inline Mm16gSmem mm16g_smem_layout(int K, int a1, int tp_str
 // register-bank conflicts on the half-rate pipe that bounds the kernel) and one register is freed.
 constexpr int MM16G_GOP_RUNTIME = 1;
 constexpr int MM16G_GOP_DNA = -6;
-template <int MODE, int K, int GOPC>
+// BORDER: lane 31 emits the constants of column -1 (dp_core.cuh, mm16g_border) and the strip width serves 31K columns; the
+// queries of (31K, 32K] columns take the instantiation that keeps all 32 lanes and selects the constants into lane 0.
+template <int MODE, int K, int GOPC, bool BORDER>
 __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g_kernel(Mm16Params p) {
   static_assert(MODE == GLOBAL || MODE == GLOCAL, "the streaming kernel implements global and glocal");
   constexpr bool GL = (MODE == GLOCAL);
+  static_assert(!BORDER || mm16g_border(K, GL), "no border lane for this strip width / mode");
   constexpr bool DEFER = mm16g_defer(GL, K);
-  constexpr bool BORDER = mm16g_border(K, GL);          // lane 31 emits the constants of column -1 (dp_core.cuh)
   constexpr int BL = MM16G_BORDER_LANE;
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int KP = StripCfg<K>::KP;
@@ -1344,7 +1351,10 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16g
     if (threadIdx.x == 0) { misc[0] = (int)atomicAdd(p.q_counter, 1u); misc[1] = 0; }
     __syncthreads();
     const int item = misc[0];
-    if (item >= p.n_items) break;
+    if (item >= p.n_items) {
+      if (threadIdx.x == 0 && p.tail_flag) atomicExch(p.tail_flag, 1u);
+      break;
+    }
     const int4 work = p.items[item];
     const int qi = work.x, pair_lo = work.y, pair_hi = work.z;
     const uint8_t *qs = p.q + p.q_off[qi];

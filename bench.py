@@ -483,7 +483,7 @@ def cuda_arm(args, rank, world, local_rank):
         ev1.record()
         torch.cuda.synchronize(); barrier()
         for row in sh.job.profile_history(steps):                       # per-launch CUDA-event times of the timed steps (the last 32 at most)
-            p = prof.setdefault(row["K"], {"ms": 0.0, "cells": row["cells"], "queries": row["queries"], "n": 0})
+            p = prof.setdefault((row["K"], row["lanes"]), {"ms": 0.0, "cells": row["cells"], "queries": row["queries"], "n": 0})
             p["ms"] += row["ms"]; p["n"] += 1
         out = {"clocks": sampler.stop() if sampler else None, "elapsed_ms": max_over_ranks(ev0.elapsed_time(ev1)),
                "launches": sh.job.kernel_launches() * steps, "prof": prof, "steps": steps, "warmup": warmup}
@@ -498,11 +498,11 @@ def cuda_arm(args, rank, world, local_rank):
             return None
         # the launch with the most cells: it goes first, on the caller's stream, so its event pair times it alone (the launches of
         # the other strip widths run on side streams and fill its tail; their event pairs include the time they wait for SMs)
-        K, p = max(run["prof"].items(), key=lambda kv: kv[1]["cells"])
+        (K, lanes), p = max(run["prof"].items(), key=lambda kv: kv[1]["cells"])
         avg_ms = p["ms"] / p["n"]
         achieved = p["cells"] / (avg_ms * 1e-3) / 1e9
         streaming = mode_name in ("global", "glocal")
-        return {"bound": "int_alu", "kernel": ("mm16g_kernel<%s,K=%d>" if streaming else "mm16_kernel<%s,K=%d>") % (mode_name, K),
+        return {"bound": "int_alu", "kernel": ("mm16g_kernel<%s,K=%d>" if streaming else "mm16_kernel<%s,K=%d>") % (mode_name, K) + (" (border lane: 31 x %d columns)" % K if lanes == 31 else ""),
                 "achieved": achieved, "peak": pk["gcups"], "unit": "GCUPS", "frac": achieved / pk["gcups"],
                 "peak_source": "measured in this run by abv_int_peak(%d): register-only chains of the kernel's cell mix (%d lane-ops per cell pair: %s + VIMNMX3.S16x2 + 2 VIADDMNMX.S16x2), %.3e lane-ops/s" % (
                     pk["which"], pk["cell_ops"], "1 add" if pk["cell_ops"] == 4 else "2 adds", pk["lane_ops"]),

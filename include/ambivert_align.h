@@ -200,8 +200,8 @@ int abv_best_hits_fetch(abv_job *job, int *best_score, int *best_idx);
 double abv_job_cells(const abv_job *job);
 int abv_job_kernel_launches(const abv_job *job);   /* kernels one abv_best_hits_launch enqueues */
 /* Per packed-kernel launch of the LAST abv_best_hits_launch (call after it completed): rows of
- * 4 doubles {K = packed columns per lane, queries, cells, milliseconds by CUDA events on the
- * launch stream}.  Returns the number of rows written (<= max_rows). */
+ * 4 doubles {K = packed columns per lane (K + 0.5: the bucket runs the border-lane instantiation of the streaming global
+ * kernel, 31 lanes x K columns), queries, cells, milliseconds by CUDA events on the launch's stream}.  Returns the number of rows written (<= max_rows). */
 int abv_job_profile(abv_job *job, double *out, int max_rows);
 /* The same for the last `last_launches` calls of abv_best_hits_launch (the library keeps the event pairs of the last 32), so
  * that many launches can be timed back to back without a host synchronisation between them: rows of 5 doubles

@@ -245,12 +245,12 @@ extern "C" void emu_set_level_cap(int cap) { g_level_cap = cap < 1 ? 1 : cap; }
 // Mirrors the control flow of the kernel: three row buffers, 32 switch steps per pair, pending corner
 // captures, the zero-symbol prefix before the first pair and the dummy pair that drains the pipeline;
 // for glocal the dependency-free row 0 at the switch step and the last-row maxima collected per lane.
-template <bool GL, int K>
+template <bool GL, int K, bool BORDER>
 static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsigned char *const *t1s, const int *l1s,
                         const unsigned char *const *t2s, const int *l2s, int alpha, const int *M, int go, int ge,
                         int *sc1_out, int *sc2_out) {
   constexpr int KP = StripCfg<K>::KP, V = StripCfg<K>::V, P = StripCfg<K>::P;
-  constexpr bool BORDER = mm16g_border(K, GL);      // lane 31 emits the constants of column -1 (dp_core.cuh)
+  static_assert(!BORDER || mm16g_border(K, GL), "no border lane for this strip width / mode");   // BORDER: lane 31 emits the constants of column -1
   constexpr int BL = MM16G_BORDER_LANE;
   const int a1 = alpha + 1, ncodes = a1 * a1;
   std::vector<int> mext((size_t)a1 * a1, 0);
@@ -447,35 +447,47 @@ static void emu_mm16g_t(const unsigned char *q, int lq, int n_pairs, const unsig
   }
 }
 
+template <bool GL, int K>
+static void emu_mm16g_v(bool border, const unsigned char *q, int lq, int n_pairs, const unsigned char *const *t1s, const int *l1s,
+                        const unsigned char *const *t2s, const int *l2s, int alpha, const int *M, int go, int ge, int *sc1, int *sc2) {
+  if constexpr (mm16g_border(K, GL)) {
+    if (border) { emu_mm16g_t<GL, K, true>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return; }
+  }
+  emu_mm16g_t<GL, K, false>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2);
+}
+
 template <bool GL>
-static int emu_mm16g_k(int K, const unsigned char *q, int lq, int n_pairs, const unsigned char *const *t1s, const int *l1s,
+static int emu_mm16g_k(int K, bool border, const unsigned char *q, int lq, int n_pairs, const unsigned char *const *t1s, const int *l1s,
                        const unsigned char *const *t2s, const int *l2s, int alpha, const int *M, int go, int ge, int *sc1, int *sc2) {
   switch (K) {
-    case 2: emu_mm16g_t<GL, 2>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-    case 3: emu_mm16g_t<GL, 3>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-    case 4: emu_mm16g_t<GL, 4>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-    case 5: emu_mm16g_t<GL, 5>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-    case 6: emu_mm16g_t<GL, 6>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-    case 7: emu_mm16g_t<GL, 7>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-    case 8: emu_mm16g_t<GL, 8>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-    case 9: emu_mm16g_t<GL, 9>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-    case 10: emu_mm16g_t<GL, 10>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-    case 12: emu_mm16g_t<GL, 12>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
-    case 16: emu_mm16g_t<GL, 16>(q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 2: emu_mm16g_v<GL, 2>(border, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 3: emu_mm16g_v<GL, 3>(border, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 4: emu_mm16g_v<GL, 4>(border, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 5: emu_mm16g_v<GL, 5>(border, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 6: emu_mm16g_v<GL, 6>(border, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 7: emu_mm16g_v<GL, 7>(border, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 8: emu_mm16g_v<GL, 8>(border, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 9: emu_mm16g_v<GL, 9>(border, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 10: emu_mm16g_v<GL, 10>(border, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 12: emu_mm16g_v<GL, 12>(border, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
+    case 16: emu_mm16g_v<GL, 16>(border, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2); return 0;
   }
   return -1;
 }
 
-extern "C" int emu_mm16g_capacity(int K, int glocal) { return mm16g_capacity(K, glocal != 0); }   // query columns the streaming kernel serves with strips of K
+// query columns the border-lane instantiation of the streaming kernel serves with strips of K (0: there is none for this mode / width)
+extern "C" int emu_mm16g_border_capacity(int K, int glocal) { return mm16g_border(K, glocal != 0) ? 31 * K : 0; }
 
-extern "C" int emu_mm16g(int mode, int K, const unsigned char *q, int lq, int n_pairs, const unsigned char *const *t1s, const int *l1s,
+extern "C" int emu_mm16g(int mode, int K, int border, const unsigned char *q, int lq, int n_pairs, const unsigned char *const *t1s, const int *l1s,
                          const unsigned char *const *t2s, const int *l2s, int alpha, const int *M, int go, int ge,
                          int *sc1, int *sc2) {
   const bool glocal = mode == GLOCAL;
-  if (mm16g_capacity(K, glocal) < lq || (mm16g_border(K, glocal) && go > ge)) return -1;   // the border lane's fixed point needs Ec <= Hc, i.e. go <= ge (the host keeps such scorings off it)
+  if (32 * K < lq) return -1;
+  // the border-lane instantiation: up to 31K columns, and its fixed point needs Ec <= Hc, i.e. go <= ge (align_abi.cu keeps other jobs off it)
+  if (border && (!mm16g_border(K, glocal) || 31 * K < lq || go > ge)) return -1;
   try {
-    if (mode == GLOBAL) return emu_mm16g_k<false>(K, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2);
-    if (mode == GLOCAL) return emu_mm16g_k<true>(K, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2);
+    if (mode == GLOBAL) return emu_mm16g_k<false>(K, border != 0, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2);
+    if (mode == GLOCAL) return emu_mm16g_k<true>(K, border != 0, q, lq, n_pairs, t1s, l1s, t2s, l2s, alpha, M, go, ge, sc1, sc2);
   } catch (...) { return -2; }   // an out-of-range symbol read: a pointer bookkeeping error
   return -1;
 }

@@ -161,7 +161,10 @@ def test_streaming_logic_vs_oracle(emu, oracle_port, mode):
         # short staircases make a handful of pairs wrap around, 1 = every pair reset explicitly
         emu.emu_set_level_cap(C.c_int(rng.choice([1, 2, 3, 5, 1 << 20])))
         K = rng.choice(KS + [7, 7, 3, 5, 9])
-        cap = emu.emu_mm16g_capacity(C.c_int(K), C.c_int(1 if mode == O.GLOCAL else 0))             # 31K where lane 31 is the border lane (dp_core.cuh, mm16g_border), else 32K
+        # global: the border-lane instantiation (lane 31 emits column -1, up to 31K columns: dp_core.cuh, mm16g_border) or the one with all 32 lanes
+        bcap = emu.emu_mm16g_border_capacity(C.c_int(K), C.c_int(1 if mode == O.GLOCAL else 0))
+        border = 1 if (bcap and rng.random() < 0.6) else 0
+        cap = bcap if border else 32 * K
         lq = rng.randint(max(1, cap - 70), cap) if rng.random() < 0.7 else rng.randint(1, cap)
         q = bytes(rng.choice([0, 1, 2, 3, 0, 1, 2, 3, 4]) for _ in range(lq))
         n_pairs = rng.choice([1, 2, 3, 4, 7, 12])
@@ -187,8 +190,8 @@ def test_streaming_logic_vs_oracle(emu, oracle_port, mode):
         else:
             M = np.array([rng.randint(-4, 4) for _ in range(25)], np.int32)
             go, ge = -rng.randint(0, 8), -rng.randint(0, 3)
-            if go > ge and cap < 32 * K:
-                go = ge              # an opening cheaper than an extension stays off the border-lane kernel (align_abi.cu, stream_ok)
+            if go > ge and border:
+                go = ge              # an opening cheaper than an extension stays off the border-lane instantiation (align_abi.cu, job_prepare)
         M = np.ascontiguousarray(M, dtype=np.int32)
         t1 = [targets[2 * i] for i in range(n_pairs)]
         t2 = [targets[2 * i + 1] for i in range(n_pairs)]
@@ -197,7 +200,7 @@ def test_streaming_logic_vs_oracle(emu, oracle_port, mode):
         l2 = np.array([len(x) for x in t2], np.int32)
         s1 = np.full(n_pairs, -99999, np.int32)
         s2 = np.full(n_pairs, -99999, np.int32)
-        rc = emu.emu_mm16g(C.c_int(mode), C.c_int(K), q, C.c_int(lq), C.c_int(n_pairs), arr(t1), l1.ctypes.data_as(C.c_void_p), arr(t2),
+        rc = emu.emu_mm16g(C.c_int(mode), C.c_int(K), C.c_int(border), q, C.c_int(lq), C.c_int(n_pairs), arr(t1), l1.ctypes.data_as(C.c_void_p), arr(t2),
                            l2.ctypes.data_as(C.c_void_p), C.c_int(5), M.ctypes.data_as(C.c_void_p), C.c_int(go), C.c_int(ge),
                            s1.ctypes.data_as(C.c_void_p), s2.ctypes.data_as(C.c_void_p))
         assert rc == 0, (it, rc)
