@@ -110,6 +110,7 @@ struct Options {
   int concurrent_buckets = 1;   // 1 = the packed launches of a job (one per strip width) go to streams of their own, largest first:
                                 //     the CTAs of the next launch fill the tail of the previous persistent grid
   int tb16 = 1;                 // 0 = one-to-one jobs always take the 32-bit kernel
+  int tb16_extra_smem = 0;      // experiment knob: unused dynamic shared memory per CTA of the packed traceback kernel (lowers its occupancy)
   int pairs_chunk = 200000;     // one-to-one jobs of at least 2x this many pairs run as a pipeline of chunks (0 = never)
 };
 Options g_opt;                  // process-wide
@@ -889,7 +890,7 @@ constexpr int TB16_MAX_ALPHA = 7;
 template <int MODE, int K>
 int tb16_launch_one(cudaStream_t st, Tb16Params p, size_t dir_bytes_total, size_t tmp_entries_total) {
   auto kern = tb16_kernel<MODE, K>;
-  const int smem = ((p.a1 * p.a1 * 4 + 15) & ~15) + TB16_WARPS * tb16_smem_per_warp<K>(p.a1, p.rows_cap);
+  const int smem = ((p.a1 * p.a1 * 4 + 15) & ~15) + TB16_WARPS * tb16_smem_per_warp<K>(p.a1, p.rows_cap) + g_opt.tb16_extra_smem;
   if (smem > 200 * 1024) return fail(ABV_ERR_ARGS, "tb16: %d bytes of shared memory", smem);
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int per_sm = 0;
@@ -1039,6 +1040,7 @@ int abv_set_option(const char *key, int value) {
   if (!strcmp(key, "no_border")) { g_opt.no_border = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "concurrent_buckets")) { g_opt.concurrent_buckets = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "tb16")) { g_opt.tb16 = value ? 1 : 0; return ABV_OK; }
+  if (!strcmp(key, "tb16_extra_smem")) { g_opt.tb16_extra_smem = value < 0 ? 0 : value; return ABV_OK; }
   if (!strcmp(key, "global_v1")) { g_opt.global_v1 = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "no_gop_imm")) { g_opt.no_gop_imm = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "no_levels")) { g_opt.no_levels = value ? 1 : 0; return ABV_OK; }
