@@ -576,9 +576,12 @@ ABV_HD int variants_walk(const unsigned char *v, const unsigned char *r, int n, 
 #ifndef ABV_NO_BORDER
 #define ABV_NO_BORDER 0
 #endif
+#ifndef ABV_GLOCAL_BORDER
+#define ABV_GLOCAL_BORDER 1
+#endif
 // Measured (B200, 20k x 2k panel, profiles/r02_ab_*.jsonl): global +2.7 % per executed cell; glocal +1 % per executed cell, less than
 // the queries that would move up a strip width cost (its switching steps and parked rows dominate): glocal keeps the selects.
-ABV_HD constexpr bool mm16g_border(int K, bool glocal) { return !ABV_NO_BORDER && !glocal && K < 16; }
+ABV_HD constexpr bool mm16g_border(int K, bool glocal) { return !ABV_NO_BORDER && K < 16 && (ABV_GLOCAL_BORDER || !glocal); }
 constexpr int MM16G_BORDER_LANE = 31;
 
 // pair-row bookkeeping of the streaming kernel, shared by the kernel and its CPU mirror

@@ -226,12 +226,12 @@ def as_shipped_measurement(queries, targets, gpu_score, gpu_idx, n_sample=64):
                                   "what": "%s: %d merged amplicons x %d manifest targets (BASELINE.json configs[0] data)" % (bundled["what"], bundled["amplicons"], bundled["targets"])}}
 
 
-def ncu_traffic(mode, K):
+def ncu_traffic(mode, K, lanes=32):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this workload, from the
     committed ncu capture (profiles/traffic.json); None if that kernel/workload was not captured"""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get("mm16g_kernel<%s,K=%d>" % (mode, K))
+            return json.load(f).get("mm16g_kernel<%s,K=%d,lanes=%d>" % (mode, K, lanes))
     except (OSError, ValueError):
         return None
 
@@ -510,7 +510,7 @@ def cuda_arm(args, rank, world, local_rank):
                 "share_of_step": avg_ms / max(1e-9, run["elapsed_ms"] / run["steps"]),
                 "launch_overlap": "packed launches of one step run concurrently (largest first); share_of_step = this launch's duration / step time",
                 "launches_timed": p["n"], "rank": 0,
-                "traffic": ncu_traffic(mode_name, K) if (world == 1 and args.workload == "config4" and not (args.queries or args.targets)) else None,
+                "traffic": ncu_traffic(mode_name, K, lanes) if (world == 1 and args.workload == "config4" and not (args.queries or args.targets)) else None,
                 "hbm": hbm_info(p["cells"], p["queries"], len(targets), total_cells / world, io_bytes, avg_ms)}
 
     with torch.cuda.stream(stream):
