@@ -504,6 +504,7 @@ int mm16_launch(int mode, int K, bool streaming, bool border, cudaStream_t st, c
   if (mode == ABV_GLOBAL) return mm16_launch_mode<GLOBAL>(K, st, p, launched, W, h_list);
   if (mode == ABV_LOCAL) return mm16_launch_mode<LOCAL>(K, st, p, launched, W, h_list);
   if (mode == ABV_GLOCAL) return mm16_launch_mode<GLOCAL>(K, st, p, launched, W, h_list);
+  if (mode == ABV_OVERLAP) return mm16_launch_mode<OVERLAP>(K, st, p, launched, W, h_list);
   return fail(ABV_ERR_ARGS, "packed kernel does not implement mode %d", mode);
 }
 
@@ -562,7 +563,7 @@ namespace {
 // is the packed kernel exact for queries padded to P columns against these targets?
 bool packed_exact(int mode, int P, int max_lt, int maxabs) {
   const long long bound = (long long)(P + max_lt + 8) * maxabs;
-  return bound <= (mode == ABV_GLOCAL ? p16::P16_LIMIT : 30000);
+  return bound <= ((mode == ABV_GLOCAL || mode == ABV_OVERLAP) ? p16::P16_LIMIT : 30000);      // these two keep half the range for their minus-infinity sentinel
 }
 
 int mm_validate(int mode, const char *q, const long long *q_off, int n_q, const char *t, const long long *t_off, int n_t,
@@ -620,8 +621,9 @@ int job_prepare(abv_job &J, int mode, const char *q, const long long *q_off, int
   for (int i = 0; i < sc.alpha * sc.alpha; ++i) maxpos = std::max(maxpos, sc.matrix[i]);
   J.maxabs = maxabs; J.maxpos = maxpos;
   const int a1 = sc.alpha + 1;
+  // overlap: the packed form is exact where re-opening a gap state from itself cannot win, go <= ge (dp_core.cuh, mm16_overlap_cands)
   bool packed_ok = g_opt.path != ABV_PATH_WF32 && n_t > 0 && a1 * a1 <= 64 &&
-                   (mode == ABV_GLOBAL || mode == ABV_LOCAL || mode == ABV_GLOCAL);
+                   (mode == ABV_GLOBAL || mode == ABV_LOCAL || mode == ABV_GLOCAL || (mode == ABV_OVERLAP && sc.go <= sc.ge));
   // the streaming kernel sweeps at least 32 rows per pair, plus one pad row after every pair (its separator row, mm16g_levels)
   const int tp_stride = (std::max(max_lt, MM16G_MIN_ROWS) + 1 + 15) & ~15;
   // glocal streams only target pairs whose members have >= 32 rows (deferred last rows, kernels.cuh): the targets are paired

@@ -316,6 +316,31 @@ ABV_HD void mm16_row_glocal_last(uint32_t d, uint32_t &e, uint32_t (&Hp)[K], uin
 }
 
 
+// Overlap mode (align.c:68-243) in the packed kernel, score only.  The cells follow the common recurrences except
+//   * the first query column is forced, H[0][r] = S, and opens the row gap with H + go (align.c:114-125): the lane that owns it
+//     takes diagonal 0 and "minus infinity" for both gap states on every row;
+//   * the first target row is forced, H[c][0] = S, F = H + go (align.c:135-138); its row gap only feeds forced cells;
+//   * gap states are not re-opened from themselves before the last column (align.c:157, :164): for go <= ge that never changes a
+//     value (re-opening from the state's own value loses or ties against extending it), which is what the host requires;
+//   * the score is the best cell of the last query column (any row) or of the last target row (any column) (align.c:172-176,
+//     :185-192, :211-215).  With two targets per word the rows of the shorter one end earlier: rowmask has 0xffff in the halves
+//     whose target still has row r, lastmask in those for which r is the last row; kstar >= 0 on the lane that owns column lq-1.
+template <int K>
+ABV_HD void mm16_overlap_cands(const uint32_t (&Hp)[K], int c0, int lq, int kstar, uint32_t rowmask, uint32_t lastmask, uint32_t &best) {
+  const uint32_t NEG2 = p16::pack(p16::NEG16, p16::NEG16);
+  if (kstar >= 0) {
+    uint32_t h = Hp[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) h = (k == kstar) ? Hp[k] : h;
+    best = p16::max2(best, (h & rowmask) | (NEG2 & ~rowmask));
+  }
+  if (lastmask) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (c0 + k < lq) best = p16::max2(best, (Hp[k] & lastmask) | (NEG2 & ~lastmask));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Biased packed form used by the streaming global kernel (mm16g_kernel).  Every score-like value
 // (H, E, F) is stored as true + BIAS in each half, so both halves are always positive.  Then

@@ -1203,6 +1203,37 @@ __global__ void __launch_bounds__(MM16_WARPS * 32, Mm16Cfg<K>::MIN_BLOCKS) mm16_
         }
         best2 = warp_max2(best2);
         sc1 = p16::lo(best2); sc2 = p16::hi(best2);
+      } else if (MODE == OVERLAP) {
+        // row 0 has no dependencies: H[c][0] = S, F = H + go (align.c:135-138); see dp_core.cuh, mm16_overlap_cands
+        mm16_load_S<K>(lut + (int)tb[0] * P, lane, S);
+#pragma unroll
+        for (int k = 0; k < K; ++k) { Hp[k] = S[k]; F[k] = p16::add(S[k], go2); }
+        hleft_prev = __shfl_up_sync(ABV_FULL, Hp[K - 1], 1);
+        if (lane == 0) hleft_prev = 0;                       // the first column is forced: diagonal 0, no gap states
+        best2 = NEG2;
+        if (lane <= tstar)
+          mm16_overlap_cands<K>(Hp, c0, lq, lane == tstar ? kstar : -1, 0xffffffffu,
+                                (L1m1 == 0 ? 0x0000ffffu : 0u) | (L2m1 == 0 ? 0xffff0000u : 0u), best2);
+        const int nsteps = lmax - 1 + tstar;
+        for (int s = 0; s < nsteps; ++s) {
+          uint32_t h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
+          uint32_t e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+          if (lane == 0) { h_sh = 0; e_sh = NEG2; }
+          const int r = 1 + s - lane;
+          if (r >= 1 && r < lmax && lane <= tstar) {
+            mm16_load_S<K>(lut + (int)tb[r] * P, lane, S);
+            if (lane == 0) F[0] = NEG2;
+            uint32_t e = e_sh, dummy = 0;
+            mm16_row<K, false, false>(hleft_prev, e, Hp, F, S, go2, ge2, dummy);
+            hleft_prev = h_sh; e_out = e; h_out = Hp[K - 1];
+            const bool l1 = (r == L1m1), l2 = (r == L2m1);
+            if (lane == tstar || l1 || l2)
+              mm16_overlap_cands<K>(Hp, c0, lq, lane == tstar ? kstar : -1, (r <= L1m1 ? 0x0000ffffu : 0u) | (r <= L2m1 ? 0xffff0000u : 0u),
+                                    (l1 ? 0x0000ffffu : 0u) | (l2 ? 0xffff0000u : 0u), best2);
+          }
+        }
+        best2 = warp_max2(best2);
+        sc1 = p16::lo(best2); sc2 = p16::hi(best2);
       } else {  // GLOCAL
         // row 0 has no dependencies: H[c][0] = S(q[c], t[0]), F = H + go (glocal_align.c:128-136)
         mm16_load_S<K>(lut + (int)tb[0] * P, lane, S);

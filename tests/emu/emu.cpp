@@ -160,6 +160,39 @@ static void emu_mm16_t(const unsigned char *q, int lq, const unsigned char *t1, 
     uint32_t b = 0;
     for (int t = 0; t < 32; ++t) b = p16::max2(b, best2[t]);
     sc1 = p16::lo(b); sc2 = p16::hi(b);
+  } else if (MODE == OVERLAP) {      // mm16_kernel<OVERLAP>: forced first row and first column, candidates on the last column / last rows
+    for (int t = 0; t < 32; ++t) {
+      load_S<K>(&lut[(size_t)tb[0] * P], t, S);
+      for (int k = 0; k < K; ++k) { Hp[t][k] = S[k]; F[t][k] = p16::add(S[k], go2); }
+      best2[t] = NEG2;
+    }
+    for (int t = 31; t > 0; --t) hleft_prev[t] = Hp[t - 1][K - 1];
+    hleft_prev[0] = 0;
+    for (int t = 0; t <= tstar; ++t)
+      mm16_overlap_cands<K>(Hp[t], t * K, lq, t == tstar ? kstar : -1, 0xffffffffu, (L1m1 == 0 ? 0x0000ffffu : 0u) | (L2m1 == 0 ? 0xffff0000u : 0u), best2[t]);
+    const int nsteps = lmax - 1 + tstar;
+    for (int s = 0; s < nsteps; ++s) {
+      uint32_t h_sh[32], e_sh[32];
+      for (int t = 0; t < 32; ++t) { h_sh[t] = t ? h_out[t - 1] : h_out[0]; e_sh[t] = t ? e_out[t - 1] : e_out[0]; }
+      h_sh[0] = 0; e_sh[0] = NEG2;
+      for (int t = 0; t < 32; ++t) {
+        const int r = 1 + s - t;
+        if (r >= 1 && r < lmax && t <= tstar) {
+          load_S<K>(&lut[(size_t)tb[r] * P], t, S);
+          if (t == 0) F[t][0] = NEG2;
+          uint32_t e = e_sh[t], dummy = 0;
+          mm16_row<K, false, false>(hleft_prev[t], e, Hp[t], F[t], S, go2, ge2, dummy);
+          hleft_prev[t] = h_sh[t]; e_out[t] = e; h_out[t] = Hp[t][K - 1];
+          const bool a = (r == L1m1), b = (r == L2m1);
+          if (t == tstar || a || b)
+            mm16_overlap_cands<K>(Hp[t], t * K, lq, t == tstar ? kstar : -1, (r <= L1m1 ? 0x0000ffffu : 0u) | (r <= L2m1 ? 0xffff0000u : 0u),
+                                  (a ? 0x0000ffffu : 0u) | (b ? 0xffff0000u : 0u), best2[t]);
+        }
+      }
+    }
+    uint32_t b = NEG2;
+    for (int t = 0; t < 32; ++t) b = p16::max2(b, best2[t]);
+    sc1 = p16::lo(b); sc2 = p16::hi(b);
   } else {
     for (int t = 0; t < 32; ++t) {
       load_S<K>(&lut[(size_t)tb[0] * P], t, S);
@@ -233,6 +266,7 @@ int emu_mm16(int mode, int K, const unsigned char *q, int lq, const unsigned cha
     case LOCAL: return emu_mm16_k<LOCAL>(K, q, lq, t1, l1, t2, l2, alpha, M, go, ge, s1, s2);
     case GLOBAL: return emu_mm16_k<GLOBAL>(K, q, lq, t1, l1, t2, l2, alpha, M, go, ge, s1, s2);
     case GLOCAL: return emu_mm16_k<GLOCAL>(K, q, lq, t1, l1, t2, l2, alpha, M, go, ge, s1, s2);
+    case OVERLAP: return (lq < 2 || go > ge) ? -1 : emu_mm16_k<OVERLAP>(K, q, lq, t1, l1, t2, l2, alpha, M, go, ge, s1, s2);   // as align_abi.cu: exact for go <= ge
   }
   return -1;
 }
