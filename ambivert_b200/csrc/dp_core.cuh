@@ -379,18 +379,66 @@ struct StripCfg {
   static constexpr int P = 32 * KP;                         // profile row length in words
 };
 
+#ifndef ABV_ROW_ADDS
+#define ABV_ROW_ADDS 0
+#endif
+#ifndef ABV_MAX3_ORDER
+#define ABV_MAX3_ORDER 1      // max3(S, F, e) and the F update before the e update: cheapest of 108 scanned forms at unroll 8 for K = 7, 8, 9,
+#endif                        // global and glocal (static model), measured +1.0 % global / +0.8 % glocal against max3(S, e, F), e first
+#ifndef ABV_FE_ORDER
+#define ABV_FE_ORDER 1
+#endif
 template <int K, int KP>
 ABV_HD void mm16d_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], uint32_t (&S)[KP], uint32_t gop2, uint32_t gope) {
+#if ABV_ROW_ADDS == 2
+  uint32_t Hn[K];
+#endif
+  // The statement and operand orders below are semantically equivalent; they steer ptxas' register allocation, i.e. the number of
+  // moves and register-bank conflicts of the steady loop (tools/sass_cost.py; scanned with tools/scan_row_variants.sh).
+#if ABV_ROW_ADDS == 1
+  S[0] += hleft;
+#pragma unroll
+  for (int k = 1; k < K; ++k) S[k] += Hp[k - 1];
+#elif ABV_ROW_ADDS == 0
 #pragma unroll
   for (int k = K - 1; k >= 1; --k) S[k] += Hp[k - 1];
   S[0] += hleft;
+#endif
 #pragma unroll
   for (int k = 0; k < K; ++k) {
+#if ABV_ROW_ADDS == 2
+    S[k] += k ? Hp[k - 1] : hleft;        // Hp[k-1] still holds the previous row here only if written after use: see below
+#endif
+#if ABV_MAX3_ORDER == 1
+    const uint32_t h = p16::max3(S[k], F[k], e);
+#elif ABV_MAX3_ORDER == 2
+    const uint32_t h = p16::max3(e, S[k], F[k]);
+#elif ABV_MAX3_ORDER == 3
+    const uint32_t h = p16::max3(e, F[k], S[k]);
+#elif ABV_MAX3_ORDER == 4
+    const uint32_t h = p16::max3(F[k], S[k], e);
+#elif ABV_MAX3_ORDER == 5
+    const uint32_t h = p16::max3(F[k], e, S[k]);
+#else
     const uint32_t h = p16::max3(S[k], e, F[k]);
+#endif
+#if ABV_FE_ORDER == 1
+    F[k] = p16::addmax(h, gop2, F[k]);
+    e = p16::addmax(h, gope, e);
+#else
     e = p16::addmax(h, gope, e);
     F[k] = p16::addmax(h, gop2, F[k]);
+#endif
+#if ABV_ROW_ADDS == 2
+    Hn[k] = h;
+#else
     Hp[k] = h;
+#endif
   }
+#if ABV_ROW_ADDS == 2
+#pragma unroll
+  for (int k = 0; k < K; ++k) Hp[k] = Hn[k];
+#endif
 }
 template <int K, int KP>
 ABV_HD void mm16d_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], uint32_t (&S)[KP], uint32_t gop2) {

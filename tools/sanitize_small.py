@@ -17,12 +17,19 @@ targets = [dna(rng.randint(32, 70)) for _ in range(700)]
 queries = [dna(n) for n in (20, 60, 70, 100, 150, 200, 230, 280)]
 q = [s.encode() for s in queries]
 t = [s.encode() for s in targets]
-for mode in (B.GLOBAL, B.GLOCAL):
+for mode in (B.GLOBAL, B.GLOCAL, B.OVERLAP):          # overlap: the packed form of mm16_kernel
     got = B.score_matrix(q, t, mode)
     B.set_option("path", B.PATH_WF32)
     want = B.score_matrix(q, t, mode)
     B.set_option("path", B.PATH_AUTO)
     assert (got == want).all(), mode
+# several strip widths and both instantiations per width: the packed launches chained by tail flags on their own streams
+queries2 = [dna(n) for n in (200, 217, 218, 224, 225, 240, 248, 249, 256, 257, 260) for _ in range(3)]
+hits = B.best_hits([s.encode() for s in queries2], t)
+B.set_option("path", B.PATH_WF32)
+hits32 = B.best_hits([s.encode() for s in queries2], t)
+B.set_option("path", B.PATH_AUTO)
+assert (hits[0] == hits32[0]).all() and (hits[1] == hits32[1]).all()
 fwd = [dna(150) for _ in range(64)]
 rev = [f[rng.randint(40, 120):] + dna(rng.randint(10, 60)) for f in fwd]
 sc, st, cn, fr = B.align_pairs([s.encode() for s in fwd], [s.encode() for s in rev], B.LOCAL)
