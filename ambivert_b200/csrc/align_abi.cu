@@ -103,6 +103,9 @@ struct Options {
   int mm16_blocks_per_sm = 0;   // 0 = what the occupancy query returns
   int split = 0;                // 0 = automatic; otherwise slices of the target pairs per query
   int fine_tail = 1;            // 1 = the last work items of a packed launch are cut finer (short tail of the persistent grid)
+  int split_min_items = 4;      // a launch with fewer work items per resident CTA than this cuts every query into slices of the target pairs
+                                // (measured on a rank-sized shard of 12.5k queries: 24 -> 8617, 12 -> 8683, 6 -> 8696, 3 -> 8698, 1 -> 8661 GCUPS:
+                                // every slice rebuilds the query profile, and the finer tail items already keep the tail short)
   int global_v1 = 0;            // 1 = use the first-generation packed kernel for global mode too
   int no_gop_imm = 0;           // 1 = never take the streaming kernel's instantiation with the gap addend as an immediate
   int no_levels = 0;            // 1 = streaming global kernel resets every pair explicitly (no level staircase, mm16g_levels)
@@ -364,7 +367,7 @@ constexpr int MM16_NK = 11;
 int pick_split(int n_list, int n_pairs, int resident_ctas) {
   if (g_opt.split > 0) return std::max(1, std::min(g_opt.split, std::max(1, n_pairs / MM16_WARPS)));
   int split = 1;
-  while (split < 16 && (long long)n_list * split < 24ll * resident_ctas && n_pairs / (split * 2) >= 4 * MM16_WARPS) split *= 2;
+  while (split < 16 && (long long)n_list * split < (long long)g_opt.split_min_items * resident_ctas && n_pairs / (split * 2) >= 4 * MM16_WARPS) split *= 2;
   return split;
 }
 // Work items of one packed launch, built on the host and kept on the device: item = (query, slice of the target pairs).
@@ -379,7 +382,7 @@ struct WorkItems {
   int key[5] = {-1, -1, -1, -1, -1};   // resident CTAs, n_pairs, n_list, split option, fine_tail option
 };
 int build_work_items(WorkItems &W, const int *h_list, int n_list, int n_pairs, int resident_ctas, cudaStream_t st) {
-  const int key[5] = {resident_ctas, n_pairs, n_list, g_opt.split, g_opt.fine_tail};
+  const int key[5] = {resident_ctas, n_pairs, n_list, g_opt.split * 1000 + g_opt.split_min_items, g_opt.fine_tail};
   if (W.dev.p && !memcmp(key, W.key, sizeof key)) return ABV_OK;
   const int split = pick_split(n_list, n_pairs, resident_ctas);
   int fine = split, n_fine = 0;
@@ -1039,6 +1042,7 @@ int abv_set_option(const char *key, int value) {
   }
   if (!strcmp(key, "split")) { g_opt.split = std::max(0, std::min(value, 64)); return ABV_OK; }
   if (!strcmp(key, "fine_tail")) { g_opt.fine_tail = value ? 1 : 0; return ABV_OK; }
+  if (!strcmp(key, "split_min_items")) { g_opt.split_min_items = value < 1 ? 1 : value; return ABV_OK; }
   if (!strcmp(key, "no_border")) { g_opt.no_border = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "concurrent_buckets")) { g_opt.concurrent_buckets = value ? 1 : 0; return ABV_OK; }
   if (!strcmp(key, "tb16")) { g_opt.tb16 = value ? 1 : 0; return ABV_OK; }
