@@ -185,7 +185,9 @@ def test_score_matrix_packed_and_wf32_vs_oracle(B, oracle_port, mode):
     against the oracle; query lengths straddle every K bucket boundary (overlap: the packed form of round 2, align.c:68-243)"""
     rng = random.Random(77 + mode)
     queries, targets = _amplicon_set(rng, 37, 60, 180, 262)
-    for L in (1, 2, 31, 63, 64, 65, 127, 128, 129, 191, 192, 193, 223, 224, 225, 256, 257, 300, 320, 321, 383, 384, 385, 500, 512):
+    # ... and, for the streaming kernels, the 31K boundaries between the border-lane and the all-32-lanes instantiation of a strip width
+    for L in (1, 2, 31, 62, 63, 64, 65, 93, 94, 127, 128, 129, 155, 156, 186, 187, 191, 192, 193, 217, 218, 223, 224, 225, 248, 249, 256, 257, 279, 280, 288, 289,
+              300, 310, 311, 320, 321, 372, 373, 383, 384, 385, 496, 497, 500, 512):
         if L == 1 and mode == O.OVERLAP:
             continue                                         # undefined in the reference (align.c:183): the library rejects the job
         queries.append(rand_dna(rng, L))
