@@ -550,7 +550,7 @@ struct abv_job {
   long long n_launches = 0;        // abv_best_hits_launch calls so far
   ~abv_job() {
     for (auto &b : buckets) for (auto e : b.ev) if (e) cudaEventDestroy(e);
-    for (auto s : side) if (s) cudaStreamDestroy(s);
+    for (auto s : side) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }   // (a failed launch may have left forked work unjoined)
     for (auto e : ev_join) if (e) cudaEventDestroy(e);
     if (ev_fork) cudaEventDestroy(ev_fork);
   }
