@@ -155,6 +155,12 @@ def merge_overlaps(self, threshold=0, minimum_overlap=10):
                 self.merged[key] = text[offs[k]:offs[k + 1]]
             else:
                 self.unmergable.append(key)
+        # The merged reads left the device packed (one buffer + offsets): keep them that way for match_to_reference, which
+        # would otherwise join and encode the strings again.  Unmergable pairs have length 0 in the buffer, so the kept reads are
+        # adjacent.  (keys, buffer, offsets); used only while self.merged still holds exactly these reads in this order.
+        ok = status == 1
+        self._merged_pack = ([key for key, good in zip(keys, ok.tolist()) if good],
+                             np.ascontiguousarray(merged, dtype=np.uint8), np.concatenate([off[:-1][ok], off[-1:]]).astype(np.int64))
     logging.info("\nSuccessfully merged {0} reads. {1} reads could not be merged".format(len(self.merged), len(self.unmergable)))
 
 
@@ -172,13 +178,19 @@ def match_to_reference(self, min_score=0.1, trim_primers=0, global_align=True, s
     if not keys:
         return
     merged = self.merged
-    seqs = [merged[k][trim_primers:-trim_primers] for k in keys] if trim_primers else [merged[k] for k in keys]
+    pack = getattr(self, "_merged_pack", None)
+    if pack is not None and not trim_primers and len(keys) == len(merged) == len(pack[0]) and keys == pack[0]:
+        seqs = None                      # the packed merged reads of merge_overlaps are exactly the amplicons to score
+    else:
+        pack = None
+        seqs = [merged[k][trim_primers:-trim_primers] for k in keys] if trim_primers else [merged[k] for k in keys]
     targets = [self.reference_sequences[x].upper() for x in ref_keys]
     seed = B.SEED_GLOBAL if global_align else B.SEED_LOCAL
     logging.info("Matching read bins to references - {0} amplicons x {1} targets on the GPU".format(len(keys), len(ref_keys)))
     many = not isinstance(gpus, int) or gpus > 1
     try:
-        q, t = B.pack_text(seqs), B.pack_text(targets)          # one join + one encode per set, not one bytes object per amplicon
+        # one join + one encode per set, not one bytes object per amplicon; the amplicons not even that when they come packed
+        q, t = (pack[1], pack[2]) if pack is not None else B.pack_text(seqs), B.pack_text(targets)
         if many:
             best_score, best_idx = B.best_hits_multi(q, t, gpus, B.GLOBAL, seed)
         else:
