@@ -41,7 +41,7 @@ constexpr int kSwitchUnroll = ABV_SWITCH_UNROLL;
 #endif
 constexpr int kGlSwitchUnroll = ABV_GL_SW_UNROLL;   // glocal (deferred last rows): steps of a switching segment unrolled together
 #ifndef ABV_INJ_UNROLL
-#define ABV_INJ_UNROLL 4   // measured: 1: 8.065, 2: 8.040, 4: 8.084, 8: 8.088 TCUPS
+#define ABV_INJ_UNROLL 2   // round 1 build: 1: 8.065, 2: 8.040, 4: 8.084, 8: 8.088 TCUPS; round 2 build (20k x 2k): 1: 8.706, 2: 8.748, 4: 8.725, 8: 8.680
 #endif
 constexpr int kInjUnroll = ABV_INJ_UNROLL;         // the same for the (lighter) switching segments of injected pairs   // steps of the pair-switching segments unrolled together (code size: instruction cache)
 #ifndef ABV_LDS_PTX
