@@ -128,6 +128,11 @@ const char *abv_version(void);
  *   "tb16"               1                     0: one-to-one jobs always take the 32-bit kernel
  *   "global_v1"          0                     1: first-generation packed kernel for global mode
  *   "no_levels"          0                     1: streaming global kernel resets every pair explicitly (no level staircase)
+ *   "no_border"          0                     1: the streaming kernels never take the border-lane instantiation (every query keeps 32 lanes)
+ *   "no_gop_imm"         0                     1: never the instantiation with the gap addend as an immediate
+ *   "concurrent_buckets" 1                     the packed launches of a job run on streams of their own, chained by tail flags; 0: one stream
+ *   "split_min_items"    4                     a launch with fewer work items per resident CTA cuts every query into slices of the target pairs
+ *   "tb16_extra_smem"    0                     experiment knob: unused shared memory per CTA of the packed traceback kernel (lowers occupancy)
  *   "pairs_chunk"        200000                one-to-one jobs of >= 2x this many pairs run as a pipeline of chunks; 0: never
  *   "wf32_blocks_per_sm", "mm16_blocks_per_sm", "cache_mb" (device allocation cache) */
 int abv_set_option(const char *key, int value);
