@@ -43,7 +43,10 @@ def main():
             total.append(e0.elapsed_time(e1))
             for r in job.profile():
                 rows.setdefault("%d%s" % (r["K"], "b" if r["lanes"] == 31 else ""), []).append((r["ms"], r["cells"]))
-    out = {"lib": os.environ.get("AMBIVERT_B200_LIB", "default"), "mode": args.mode, "opt": args.opt, "step_ms": min(total),
+    import hashlib
+    sc, ix = job.fetch()
+    digest = hashlib.sha256(sc.tobytes() + ix.tobytes()).hexdigest()[:12]
+    out = {"digest": digest, "lib": os.environ.get("AMBIVERT_B200_LIB", "default"), "mode": args.mode, "opt": args.opt, "step_ms": min(total),
            "tcups_step": job.cells / min(total) / 1e9,
            "per_K": {K: {"ms": min(m for m, _ in v), "tcups": v[0][1] / min(m for m, _ in v) / 1e9} for K, v in sorted(rows.items())}}
     print(json.dumps(out))
