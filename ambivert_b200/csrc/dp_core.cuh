@@ -463,8 +463,12 @@ constexpr int MM16G_NO_EGAP = -32000;
 //   pa = ge(diag, F) (diag wins ties), pb = ge(max(diag,F), E) (both win ties over E), pc = ge(value, 0) (local: else stop),
 //   fo = ge(h + go, F + ge), eo = ge(h + go, E + ge) (opening wins ties)
 //   direction = SRC_* of wf32: bit0 = (!pa & pb) | !pc, bit1 = !(pb & pc) (stored complemented); plus the two "gap re-opened" bits
-// Each of the four direction bits goes to its own bit PLANE: one word per column and 16 steps, bit j (low half) and
-// 16 + j (high half) = step 16*w + j.
+// The four direction bits of a cell ("planes" 0..3: bit0, complemented bit1, F re-opened, E re-opened) of both halves share ONE
+// word per column and 4 steps.  Two byte permutes with sign replication turn the bits 15 / 31 of four decision words into whole
+// bytes (X = planes 0,1; Y = planes 2,3; byte = 2*(plane & 1) + half), one logic op interleaves them (X on the odd bits, Y on the
+// even ones, every bit pair of a byte alike) and one more keeps the pair of this step: 4 instructions per cell pair where one word
+// per plane and 16 steps took a shift and a logic op per plane (8).
+//     bit of (plane, half, step s) in word s / 4 of the column = 8 * (2*(plane & 1) + half) + 2 * (s % 4) + (plane < 2)
 namespace p16 {
 #if defined(__CUDA_ARCH__)
 ABV_HD uint32_t bmax(uint32_t a, uint32_t b, bool &p_hi, bool &p_lo) { return __vibmax_s16x2(a, b, &p_hi, &p_lo); }
@@ -489,7 +493,7 @@ ABV_HD int tb16_steps16(int rows_cap) { return (rows_cap + 31 + 15) >> 4; }
 // word of the profile row that holds column k of lane t: the lanes of one shared-memory phase read 32 distinct banks
 ABV_HD int tb16_slot(int t, int k, int V) { return ((k / V) * 32 + t) * V + k % V; }
 ABV_HD uint32_t tb16_ge(uint32_t a, uint32_t b) { return a + TB16_H - b; }
-// acc | (x & m) as ONE 3-input logic op (left to itself the compiler masks with the immediate first: 3 ops per plane)
+// acc | (x & m) as ONE 3-input logic op (left to itself the compiler may mask first)
 ABV_HD uint32_t tb16_insert(uint32_t acc, uint32_t x, uint32_t m) {
 #if defined(__CUDA_ARCH__)
   uint32_t d;
@@ -499,18 +503,39 @@ ABV_HD uint32_t tb16_insert(uint32_t acc, uint32_t x, uint32_t m) {
   return acc | (x & m);
 #endif
 }
+// bytes (a.bit15, a.bit31, b.bit15, b.bit31), each replicated over its whole byte (prmt with the sign-replication flag)
+ABV_HD uint32_t tb16_signs(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+#else
+  return ((a >> 15) & 1u ? 0x000000ffu : 0u) | ((a >> 31) & 1u ? 0x0000ff00u : 0u) | ((b >> 15) & 1u ? 0x00ff0000u : 0u) | ((b >> 31) & 1u ? 0xff000000u : 0u);
+#endif
+}
+// (x & 0xAAAAAAAA) | (y & 0x55555555) as one logic op
+ABV_HD uint32_t tb16_interleave(uint32_t x, uint32_t y) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(d) : "r"(0xAAAAAAAAu), "r"(x), "r"(y));      // a ? b : c
+  return d;
+#else
+  return (x & 0xAAAAAAAAu) | (y & 0x55555555u);
+#endif
+}
+ABV_HD int tb16_steps4(int rows_cap) { return tb16_steps16(rows_cap) * 4; }
 
 // One row of one lane.  All score-like values are b16-biased.
 //   hleft : H[c0-1][r-1]        e : in E[r] entering the strip, out E[r] leaving it
 //   Hp,F  : H[.][r-1] -> H[.][r]; column gap states
 //   Slo,Shi : addend-packed substitution scores of the two pairs' columns for this row's symbols
 //   gow,gew : b16::addend(go,go), b16::addend(ge,ge);  zerob = b16::biased(0,0)
-//   sh,MJ : 15 - step % 16 and 0x80008000 >> sh: where this step's bits go in the plane words acc[k][plane]
+//   mj    : 0x03030303 << 2*(step % 4): the bit pair of this step in every byte of the direction word acc[k]
 //   LOCAL : cand[k] = running best value of column c0+k (both halves), crl[k] / crh[k] = its row in the low / high half;
 //           r = this row.  '>=' so that the last row wins ties within a column (local_align.c:156-160)
 template <int MODE, int K>
 ABV_HD void tb16_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], const uint32_t *Slo, const uint32_t *Shi,
-                     uint32_t gow, uint32_t gew, uint32_t zerob, int sh, uint32_t MJ, uint32_t (&acc)[K][TB16_PLANES],
+                     uint32_t gow, uint32_t gew, uint32_t zerob, uint32_t mj, uint32_t (&acc)[K],
                      uint32_t (&cand)[K], int (&crl)[K], int (&crh)[K], int r) {
   uint32_t d = hleft;
 #pragma unroll
@@ -541,27 +566,28 @@ ABV_HD void tb16_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&
     e = p16::max2(hg, ee);
     const uint32_t eo = tb16_ge(hg, ee);
     Hp[k] = h;
-    acc[k][0] = tb16_insert(acc[k][0], b0 >> sh, MJ);
-    acc[k][1] = tb16_insert(acc[k][1], b1 >> sh, MJ);
-    acc[k][2] = tb16_insert(acc[k][2], fo >> sh, MJ);
-    acc[k][3] = tb16_insert(acc[k][3], eo >> sh, MJ);
+    acc[k] = tb16_insert(acc[k], tb16_interleave(tb16_signs(b0, b1), tb16_signs(fo, eo)), mj);
   }
 }
 
-// direction planes of one warp's two pairs: word(k, plane, s, t) = ((k*4 + plane)*steps16 + s/16)*32 + t,
-// bit s%16 + 16*half, where column c = t*K + k and s = row + t is the step at which lane t worked on that row
+// directions of one warp's two pairs: word(k, s, t) = (k*steps4 + s/4)*32 + t holds the four bits of both halves for the 4 steps
+// s/4*4 .. +3 (bit layout above), where column c = t*K + k and s = row + t is the step at which lane t worked on that row
 template <int K>
 struct Tb16Reader {
   const uint32_t *w;
-  int steps16, half;
-  ABV_HD unsigned plane_bit(int plane, int col, int row) const {
+  int steps4, half;
+  ABV_HD uint32_t cell(int col, int row) const {      // the word of the cell, shifted so that bits 0,1 = planes 2,0 and bits 16,17 = planes 3,1
     const int t = col / K, k = col - t * K, s = row + t;
-    const uint32_t v = w[((long long)(k * TB16_PLANES + plane) * steps16 + (s >> 4)) * 32 + t];
-    return (v >> ((s & 15) + 16 * half)) & 1u;
+    return w[((long long)k * steps4 + (s >> 2)) * 32 + t] >> (8 * half + 2 * (s & 3));
   }
-  ABV_HD unsigned src(int col, int row) const { return plane_bit(0, col, row) | ((plane_bit(1, col, row) ^ 1u) << 1); }
+  ABV_HD unsigned plane_bit(int plane, int col, int row) const { return (cell(col, row) >> (16 * (plane & 1) + (plane < 2))) & 1u; }
+  ABV_HD unsigned src(int col, int row) const {
+    const uint32_t v = cell(col, row);
+    return ((v >> 1) & 1u) | ((((v >> 17) & 1u) ^ 1u) << 1);
+  }
   ABV_HD unsigned get(int col, int row) const {       // the nibble of wf32 (for the generic walk)
-    return src(col, row) | (plane_bit(2, col, row) ? BIT_FOPEN : 0u) | (plane_bit(3, col, row) ? BIT_EOPEN : 0u);
+    const uint32_t v = cell(col, row);
+    return ((v >> 1) & 1u) | ((((v >> 17) & 1u) ^ 1u) << 1) | ((v & 1u) ? BIT_FOPEN : 0u) | (((v >> 16) & 1u) ? BIT_EOPEN : 0u);
   }
 };
 

@@ -243,8 +243,8 @@ __global__ void __launch_bounds__(WF32_WARPS * 32) wf32_kernel(Wf32Params p) {
 // adds), and the two targets interleaved as one 16-bit code per row.  Sequences shorter than their partner's
 // are padded with an extra symbol whose score is negative against everything: with gap_open < 0 a padded cell
 // is always strictly below the best real cell it derives from, so it never becomes the local end cell, and
-// real cells never depend on padded ones.  Directions: four bit planes per column (dp_core.cuh::Tb16Reader),
-// written as whole 128-byte lines every 16 steps.  The walk back is done by the whole warp, one pair after
+// real cells never depend on padded ones.  Directions: one word per column and 4 steps with the four direction bits of
+// both halves (dp_core.cuh::Tb16Reader), written as whole 128-byte lines every 4 steps.  The walk back is done by the whole warp, one pair after
 // the other: the lanes probe 32 cells of the current diagonal (or 32 cells up / left for a gap) at once and a
 // ballot finds where the run ends, so a fragment costs one or two memory round trips instead of one per cell.
 struct Tb16Params {
@@ -256,7 +256,7 @@ struct Tb16Params {
   int a1, go, ge;
   int rows_cap;                                  // staged target rows per warp (multiple of 16, <= TB16_MAX_ROWS)
   int *scores;
-  uint32_t *dir; long long dir_words_per_warp;   // K * 4 planes * steps16 * 32 words
+  uint32_t *dir; long long dir_words_per_warp;   // K * steps4 * 32 words (steps4 = 4 * steps16)
   FragOut *frag_tmp; int frag_tmp_cap;           // frag_tmp_cap entries per warp
   FragOut *frags; long long frag_cap;
   unsigned long long *frag_total;
@@ -265,14 +265,14 @@ struct Tb16Params {
 };
 constexpr int TB16_WARPS = 4;
 #ifndef TB16_UNROLL
-#define TB16_UNROLL 2
+#define TB16_UNROLL 4
 #endif
 #ifndef TB16_MINB
 #define TB16_MINB 6
 #endif
 // resident CTAs the register allocation aims at: the shared memory of the profiles allows 6 CTAs of 4 warps at K <= 5 (85 registers)
 #define TB16_MIN_BLOCKS(K) ((K) <= 5 ? TB16_MINB : ((K) <= 8 ? 4 : 3))
-constexpr int kTb16Unroll = TB16_UNROLL;   // steps of the fill loop unrolled together (the whole 16 thrash the instruction cache)
+constexpr int kTb16Unroll = TB16_UNROLL;   // steps of the fill loop unrolled together (a direction word holds 4 steps)
 template <int K>
 __host__ __device__ inline int tb16_smem_per_warp(int a1, int rows_cap) {
   return (2 * a1 * Tb16Cfg<K>::P * 4 + rows_cap * 2 + 2 * Tb16Cfg<K>::P + 15) & ~15;
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
   __syncthreads();
 
   const uint32_t gow = b16::addend(go, go), gew = b16::addend(ge, ge), zerob = b16::biased(0, 0);
-  const int steps16 = tb16_steps16(p.rows_cap);
+  const int steps4 = tb16_steps4(p.rows_cap);
   uint32_t *dir = p.dir + gwarp * p.dir_words_per_warp;
   FragOut *tmp = p.frag_tmp + gwarp * (long long)p.frag_tmp_cap;
   const int c0 = lane * K;
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
     }
     __syncwarp();
 
-    uint32_t Hp[K], F[K], acc[K][TB16_PLANES], cand[K];
+    uint32_t Hp[K], F[K], acc[K], cand[K];
     int crl[K], crh[K];
     uint32_t hleft, h_out, e_out;
 #pragma unroll
@@ -405,8 +405,7 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
       const int c = c0 + k;
       if (MODE == GLOBAL) { Hp[k] = b16::biased(go + ge * c, go + ge * c); F[k] = b16::biased(2 * go + ge * c, 2 * go + ge * c); }
       else { Hp[k] = zerob; F[k] = b16::biased(go, go); }
-#pragma unroll
-      for (int q = 0; q < TB16_PLANES; ++q) acc[k][q] = 0;
+      acc[k] = 0;
       cand[k] = b16::biased(-1, -1); crl[k] = 0; crh[k] = 0;
     }
     if (MODE == GLOBAL) hleft = c0 ? b16::biased(go + ge * (c0 - 1), go + ge * (c0 - 1)) : zerob;
@@ -418,10 +417,10 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
     const int t0 = (la0 - 1) / K, k0 = (la0 - 1) - t0 * K, t1 = (la1 - 1) / K, k1 = (la1 - 1) - t1 * K;
     int corner0 = 0, corner1 = 0;
 
-    for (int s16 = 0; s16 < nsteps; s16 += 16) {
+    for (int s4 = 0; s4 < nsteps; s4 += 4) {
 #pragma unroll kTb16Unroll
-      for (int j = 0; j < 16; ++j) {
-        const int s = s16 + j;
+      for (int j = 0; j < 4; ++j) {
+        const int s = s4 + j;
         uint32_t h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
         uint32_t e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
         const int r = s - lane;
@@ -451,7 +450,7 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
             for (int i = 0; i < K; ++i) { Slo[i] = rlo[i * 32 + lane]; Shi[i] = rhi[i * 32 + lane]; }
           }
           uint32_t e = e_sh;
-          tb16_row<MODE, K>(hleft, e, Hp, F, Slo, Shi, gow, gew, zerob, 15 - j, TB16_H >> (15 - j), acc, cand, crl, crh, r);
+          tb16_row<MODE, K>(hleft, e, Hp, F, Slo, Shi, gow, gew, zerob, 0x03030303u << (2 * j), acc, cand, crl, crh, r);
           hleft = h_sh; e_out = e; h_out = Hp[K - 1];
           if (MODE == GLOBAL) {                                   // the corner cell is the score (global_align.c:217)
             if (r == lb0 - 1 && lane == t0) corner0 = b16::lo(tb16_pick<K>(Hp, k0));
@@ -459,14 +458,12 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
           }
         }
       }
-      const long long wbase = (long long)(s16 >> 4) * 32 + lane;
+      const long long wbase = (long long)(s4 >> 2) * 32 + lane;
 #pragma unroll
-      for (int k = 0; k < K; ++k)
-#pragma unroll
-        for (int q = 0; q < TB16_PLANES; ++q) {
-          dir[(long long)(k * TB16_PLANES + q) * steps16 * 32 + wbase] = acc[k][q];
-          acc[k][q] = 0;
-        }
+      for (int k = 0; k < K; ++k) {
+        dir[(long long)k * steps4 * 32 + wbase] = acc[k];
+        acc[k] = 0;
+      }
     }
 
     // end cell and score of each half
@@ -500,7 +497,7 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (h == 1 && i1 < 0) break;
-      Tb16Reader<K> rd; rd.w = dir; rd.steps16 = steps16; rd.half = h;
+      Tb16Reader<K> rd; rd.w = dir; rd.steps4 = steps4; rd.half = h;
       const int n = tb16_walk<MODE, K>(rd, h ? ec1 : ec0, h ? er1 : er0, tmp, p.frag_tmp_cap, lane);
       unsigned long long base = 0;
       if (lane == 0) {

@@ -237,6 +237,28 @@ def ncu_traffic(mode, K, lanes=32):
         return None
 
 
+def tb16_hbm(n_pairs, kernel_ms):
+    """the traceback stream of the merge stage against the HBM peak: the direction planes (4 bits per cell) are written once, the walk
+    reads its path from L2; traffic per pair from the committed ncu capture (profiles/traffic.json)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            per_pair = json.load(f).get("tb16_kernel<local,K=5> bytes per read pair")
+    except (OSError, ValueError):
+        per_pair = None
+    peak = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = json.load(f).get("hbm_gbs")
+    except (OSError, ValueError):
+        pass
+    alg = 150 * 150 * 4 / 8.0 + 300 + 16                       # direction planes + the two reads + score / fragment record, per pair
+    out = {"algorithmic_bytes_per_pair": alg, "achieved_gbs": alg * n_pairs / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peak if peak else 6650.0,
+           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peak else "fallback of B200_PROFILING.md",
+           "traffic_bytes_per_pair_ncu": per_pair}
+    out["frac_of_hbm"] = out["achieved_gbs"] / out["peak_gbs"]
+    return out
+
+
 def hbm_info(cells, n_q, n_t, total_cells, io_bytes_step, avg_ms):
     """the sequence and result streams of the dominant launch against the measured HBM peak: for information,
     the path is compute-bound (hundreds of thousands of cells per byte)"""
@@ -298,7 +320,7 @@ def merge_measurement(n_pairs):
                 "peak_source": "%d SMs x 4 schedulers x %.0f MHz = %.3e warp-inst/s x 64 cells / %.1f instructions per cell pair (SASS of the fill loop: "
                                "%d instructions per 2 steps of 5 cell pairs; profiles/r02_sass_tb16_local_k5_step.txt)" % (
                                    sms, mhz, issue, per_cell_pair, TB16_LOCAL_K5_LOOP_INSTR),
-                "avg_launch_ms": tm["kernel_ms"], "note": "fill + walk of every chunk (CUDA events in the library); 29-step ramp per item and "
+                "avg_launch_ms": tm["kernel_ms"], "hbm": tb16_hbm(n_pairs, tm["kernel_ms"]), "note": "fill + walk of every chunk (CUDA events in the library); 29-step ramp per item and "
                 "2 idle lanes at K = 5 are inside the achieved figure (profiles/r02_issue_sensitivity.md section 6)"}
     except Exception as e:                                           # noqa: BLE001  (the block is informative)
         roof = {"unavailable": repr(e)}

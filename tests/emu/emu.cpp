@@ -554,7 +554,7 @@ static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *t
   std::vector<int> mext((size_t)a1 * a1, pad_score);
   for (int i = 0; i < alpha; ++i) for (int j = 0; j < alpha; ++j) mext[i * a1 + j] = M[i * alpha + j];
   const int rows = std::max(lb0, lb1), tl = (std::max(la0, la1) - 1) / K, nsteps = rows + tl;
-  const int rows_cap = (rows + 15) & ~15, steps16 = tb16_steps16(rows_cap);
+  const int rows_cap = (rows + 15) & ~15, steps4 = tb16_steps4(rows_cap);
   std::vector<uint16_t> tb(rows);
   for (int r = 0; r < rows; ++r) tb[r] = (uint16_t)((r < lb0 ? tb0[r] : pad) | ((r < lb1 ? tb1[r] : pad) << 8));
   std::vector<uint8_t> qc(2 * P, (uint8_t)pad);
@@ -567,8 +567,8 @@ static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *t
     prof[a1 * P + idx] = b16::addend(0, mext[qc[P + t * K + k] * a1 + sym]);
   }
   const uint32_t gow = b16::addend(go, go), gew = b16::addend(ge, ge), zerob = b16::biased(0, 0);
-  std::vector<uint32_t> dir((size_t)K * TB16_PLANES * steps16 * 32, 0xdeadbeefu);
-  struct Lane { uint32_t Hp[K], F[K], acc[K][TB16_PLANES], cand[K], hleft, h_out, e_out; int crl[K], crh[K]; };
+  std::vector<uint32_t> dir((size_t)K * steps4 * 32, 0xdeadbeefu);
+  struct Lane { uint32_t Hp[K], F[K], acc[K], cand[K], hleft, h_out, e_out; int crl[K], crh[K]; };
   std::vector<Lane> L(32);
   for (int t = 0; t < 32; ++t) {
     const int c0 = t * K;
@@ -576,7 +576,7 @@ static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *t
       const int c = c0 + k;
       if (MODE == GLOBAL) { L[t].Hp[k] = b16::biased(go + ge * c, go + ge * c); L[t].F[k] = b16::biased(2 * go + ge * c, 2 * go + ge * c); }
       else { L[t].Hp[k] = zerob; L[t].F[k] = b16::biased(go, go); }
-      for (int q = 0; q < TB16_PLANES; ++q) L[t].acc[k][q] = 0;
+      L[t].acc[k] = 0;
       L[t].cand[k] = b16::biased(-1, -1); L[t].crl[k] = 0; L[t].crh[k] = 0;
     }
     L[t].hleft = (MODE == GLOBAL && c0) ? b16::biased(go + ge * (c0 - 1), go + ge * (c0 - 1)) : zerob;
@@ -586,9 +586,9 @@ static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *t
   const uint32_t Ev0 = MODE == GLOBAL ? b16::biased(2 * go, 2 * go) : b16::biased(go, go);
   const int t0 = (la0 - 1) / K, k0 = (la0 - 1) - t0 * K, t1 = (la1 - 1) / K, k1 = (la1 - 1) - t1 * K;
   int corner0 = 0, corner1 = 0;
-  for (int s16 = 0; s16 < nsteps; s16 += 16) {
-    for (int j = 0; j < 16; ++j) {
-      const int s = s16 + j;
+  for (int s4 = 0; s4 < nsteps; s4 += 4) {
+    for (int j = 0; j < 4; ++j) {
+      const int s = s4 + j;
       uint32_t h_sh[32], e_sh[32];
       for (int t = 0; t < 32; ++t) { h_sh[t] = L[t ? t - 1 : 0].h_out; e_sh[t] = L[t ? t - 1 : 0].e_out; }
       for (int t = 0; t < 32; ++t) {
@@ -605,7 +605,7 @@ static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *t
             Shi[k] = prof[(a1 + (code >> 8)) * P + tb16_slot(t, k, V)];
           }
           uint32_t e = e_sh[t];
-          tb16_row<MODE, K>(L[t].hleft, e, L[t].Hp, L[t].F, Slo, Shi, gow, gew, zerob, 15 - j, TB16_H >> (15 - j), L[t].acc, L[t].cand, L[t].crl, L[t].crh, r);
+          tb16_row<MODE, K>(L[t].hleft, e, L[t].Hp, L[t].F, Slo, Shi, gow, gew, zerob, 0x03030303u << (2 * j), L[t].acc, L[t].cand, L[t].crl, L[t].crh, r);
           L[t].hleft = h_sh[t]; L[t].e_out = e; L[t].h_out = L[t].Hp[K - 1];
           if (MODE == GLOBAL) {
             if (r == lb0 - 1 && t == t0) corner0 = b16::lo(L[t].Hp[k0]);
@@ -615,11 +615,10 @@ static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *t
       }
     }
     for (int t = 0; t < 32; ++t)
-      for (int k = 0; k < K; ++k)
-        for (int q = 0; q < TB16_PLANES; ++q) {
-          dir[((size_t)(k * TB16_PLANES + q) * steps16 + (s16 >> 4)) * 32 + t] = L[t].acc[k][q];
-          L[t].acc[k][q] = 0;
-        }
+      for (int k = 0; k < K; ++k) {
+        dir[((size_t)k * steps4 + (s4 >> 2)) * 32 + t] = L[t].acc[k];
+        L[t].acc[k] = 0;
+      }
   }
   int sc[2], ec[2], er[2];
   if (MODE == GLOBAL) { sc[0] = corner0; sc[1] = corner1; ec[0] = la0 - 1; er[0] = lb0 - 1; ec[1] = la1 - 1; er[1] = lb1 - 1; }
@@ -641,7 +640,7 @@ static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *t
     }
   }
   for (int h = 0; h < 2; ++h) {
-    Tb16Reader<K> rd; rd.w = dir.data(); rd.steps16 = steps16; rd.half = h;
+    Tb16Reader<K> rd; rd.w = dir.data(); rd.steps4 = steps4; rd.half = h;
     score[h] = sc[h];
     nfrag[h] = walk_back<MODE>(rd, ec[h], er[h], h ? frags1 : frags0, cap);
   }
