@@ -503,6 +503,16 @@ ABV_HD uint32_t tb16_insert(uint32_t acc, uint32_t x, uint32_t m) {
   return acc | (x & m);
 #endif
 }
+// (~pa & pb) | ~pc as one logic op on pa, pb, pc themselves (left to itself the compiler builds ~pc with a second add)
+ABV_HD uint32_t tb16_b0_local(uint32_t pa, uint32_t pb, uint32_t pc) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x5D;" : "=r"(d) : "r"(pa), "r"(pb), "r"(pc));
+  return d;
+#else
+  return (~pa & pb) | ~pc;
+#endif
+}
 // bytes (a.bit15, a.bit31, b.bit15, b.bit31), each replicated over its whole byte (prmt with the sign-replication flag)
 ABV_HD uint32_t tb16_signs(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
@@ -550,7 +560,7 @@ ABV_HD void tb16_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&
     if (MODE == LOCAL) {
       h = p16::max2(hr, zerob);
       const uint32_t pc = tb16_ge(hr, zerob);             // value >= 0, else the cell is a stop
-      b0 = (~pa & pb) | ~pc;
+      b0 = tb16_b0_local(pa, pb, pc);                     // (~pa & pb) | ~pc
       b1 = pb & pc;                                       // plane 1 holds the COMPLEMENT of source bit 1
       bool pn_h, pn_l;
       cand[k] = p16::bmax(hr, cand[k], pn_h, pn_l);       // a stop cell (hr < 0) never beats a candidate (>= -1)
