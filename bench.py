@@ -31,7 +31,8 @@ sys.path.insert(0, ROOT)
 # lane-ops per packed cell pair of the two kernel generations and the abv_int_peak mix that measures each
 CELL_OPS_STREAMING = 4       # mm16g_kernel: 1 add + VIMNMX3.S16x2 + 2 VIADDMNMX.S16x2          -> abv_int_peak(8)
 CELL_OPS_FIRST_GEN = 5       # mm16_kernel:  2 VIADD.16x2 + VIMNMX3.S16x2 + 2 VIADDMNMX.S16x2   -> abv_int_peak(4)
-TB16_LOCAL_K5_LOOP_INSTR = 374   # SASS instructions of tb16_kernel<local,K=5>'s fill loop (2 steps): profiles/r02_sass_tb16_local_k5_step.txt
+TB16_LOCAL_K5_LOOP_INSTR = 663   # SASS instructions of tb16_kernel<local,K=5>'s fill loop (4 steps): profiles/r02_sass_tb16_local_k5_step.txt
+TB16_LOOP_STEPS = 4
 MODE_NAMES = {"global": 2, "glocal": 3, "local": 1}
 WORKLOADS = {"config4": (100000, 2000), "config5": (1000000, 10000)}
 
@@ -305,7 +306,7 @@ def merge_measurement(n_pairs):
             stage = (w, int((mst == 1).sum()), int(mbuf.size))
     # Issue-rate roofline of tb16_kernel<local,K=5>: one warp instruction per scheduler and clock, every warp instruction of the
     # fill loop advances 32 lanes x 2 halves = 64 cells by 1 / (instructions per cell pair).  The count is the steady loop of the
-    # shipped binary (two steps of K = 5 cell pairs per lane: tools/sass_report.py 'tb16_kernel<1, 5>', committed as
+    # shipped binary (four steps of K = 5 cell pairs per lane: tools/sass_report.py 'tb16_kernel<1, 5>', committed as
     # profiles/r02_sass_tb16_local_k5_step.txt); the clock is the maximum SM clock nvidia-smi reports.
     roof = None
     try:
@@ -313,13 +314,13 @@ def merge_measurement(n_pairs):
         mhz = float(subprocess.run(["nvidia-smi", "-i", "0", "--query-gpu=clocks.max.sm", "--format=csv,noheader,nounits"],
                                    stdout=subprocess.PIPE, text=True, timeout=20).stdout.split()[0])
         issue = sms * 4 * mhz * 1e6                                  # warp instructions per second, all schedulers
-        per_cell_pair = TB16_LOCAL_K5_LOOP_INSTR / (2.0 * 5)
+        per_cell_pair = TB16_LOCAL_K5_LOOP_INSTR / (TB16_LOOP_STEPS * 5.0)
         peak = issue * 64 / per_cell_pair / 1e9
         ach = tm["cells"] / tm["kernel_ms"] / 1e6
         roof = {"bound": "issue", "kernel": "tb16_kernel<local,K=5>", "achieved": ach, "peak": peak, "unit": "GCUPS", "frac": ach / peak,
                 "peak_source": "%d SMs x 4 schedulers x %.0f MHz = %.3e warp-inst/s x 64 cells / %.1f instructions per cell pair (SASS of the fill loop: "
-                               "%d instructions per 2 steps of 5 cell pairs; profiles/r02_sass_tb16_local_k5_step.txt)" % (
-                                   sms, mhz, issue, per_cell_pair, TB16_LOCAL_K5_LOOP_INSTR),
+                               "%d instructions per %d steps of 5 cell pairs; profiles/r02_sass_tb16_local_k5_step.txt)" % (
+                                   sms, mhz, issue, per_cell_pair, TB16_LOCAL_K5_LOOP_INSTR, TB16_LOOP_STEPS),
                 "avg_launch_ms": tm["kernel_ms"], "hbm": tb16_hbm(n_pairs, tm["kernel_ms"]), "note": "fill + walk of every chunk (CUDA events in the library); 29-step ramp per item and "
                 "2 idle lanes at K = 5 are inside the achieved figure (profiles/r02_issue_sensitivity.md section 6)"}
     except Exception as e:                                           # noqa: BLE001  (the block is informative)

@@ -99,3 +99,16 @@ def test_add_reads_keys_are_md5_of_trimmed_pair(H):
     key = hashlib.md5(b"CCG" + b"GGC").hexdigest()
     assert list(amp.data) == [key] and amp.readpairs == 1
     assert amp.get_above_threshold(0) == [key] and amp.get_above_threshold(1) == []
+
+
+def test_bench_merge_roofline_uses_the_committed_sass_count():
+    """bench.py's issue-rate roofline of the traceback kernel divides by the instruction count of the fill loop in the committed
+    SASS report (tools/sass_report.py): the two must not drift apart"""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bench = open(os.path.join(root, "bench.py")).read()
+    rep = open(os.path.join(root, "profiles", "r02_sass_tb16_local_k5_step.txt")).read()
+    want = int(re.search(r"steady-state loop 0x[0-9a-f]+\.\.0x[0-9a-f]+: (\d+) instructions", rep).group(1))
+    got = int(re.search(r"^TB16_LOCAL_K5_LOOP_INSTR = (\d+)", bench, re.M).group(1))
+    assert got == want
