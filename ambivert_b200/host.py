@@ -46,6 +46,20 @@ def reverse_complement(seq):
     return complement(seq)[::-1]
 
 
+_COMP_TABLE_NL = _CompTable(_COMP)
+_COMP_TABLE_NL[10] = "\n"
+
+
+def reverse_complement_many(seqs):
+    """[reverse_complement(s) for s in seqs] with three string operations for the whole list (join, translate, reverse)
+    instead of two per sequence"""
+    seqs = list(seqs)
+    joined = "\n".join(seqs)
+    if joined.count("\n") != max(len(seqs) - 1, 0):          # a sequence with a line break in it: one by one
+        return [reverse_complement(s) for s in seqs]
+    return joined.translate(_COMP_TABLE_NL)[::-1].split("\n")[::-1] if seqs else []
+
+
 def encode_ambiguous(bases):
     """IUPAC symbol of a set of bases; N if any is N (sequence_utilities.py:130-156)"""
     s = "".join(sorted(set(b.upper() for b in bases)))
@@ -87,7 +101,18 @@ def gapped_strings(seq1, seq2, frags):
 
 
 def _ascii(seqs):
-    return [bytes(s, "ascii") for s in seqs]       # same conversion (and same UnicodeEncodeError) as ambivert.py:84
+    """str sequences -> the packed (buffer, offsets) form of the batched calls with ONE join and ONE encode for the whole set (a
+    bytes object per sequence costs more than the device work of the stage at 1e5 sequences); same conversion and same
+    UnicodeEncodeError / TypeError as bytes(seq, "ascii") at the reference's call sites (ambivert.py:84)"""
+    return B.pack_text(seqs if isinstance(seqs, list) else list(seqs))
+
+
+def _reject_gapped(seqs1, seqs2):
+    """ambivert.py:80-81, :121-122: the first pair with a gap character raises (one scan of the joined text unless there is one)"""
+    if "-" in "".join(seqs1) or "-" in "".join(seqs2):
+        for s1, s2 in zip(seqs1, seqs2):
+            if "-" in s1 or "-" in s2:
+                raise RuntimeError("Aligning Sequences with gaps is not supported", s1, s2)
 
 
 def batched_pairwise(seqs1, seqs2, local):
@@ -95,9 +120,7 @@ def batched_pairwise(seqs1, seqs2, local):
     whole batch: -> list of (align_seq1, align_seq2, start_seq1, start_seq2).  The aligner sees
     seq2.upper() in the reference; DNA_MAP is case-insensitive, so seq2 goes in as it is and the gapped
     rows, built on the device, keep its case as the reference's slices do."""
-    for s1, s2 in zip(seqs1, seqs2):
-        if "-" in s1 or "-" in s2:
-            raise RuntimeError("Aligning Sequences with gaps is not supported", s1, s2)
+    _reject_gapped(seqs1, seqs2)
     try:
         sc, status, st1, st2, off, rows1, rows2 = B.gapped_pairs(_ascii(seqs1), _ascii(seqs2), B.LOCAL if local else B.GLOBAL)
     except B.AlignError as e:
@@ -133,10 +156,8 @@ def merge_overlaps(self, threshold=0, minimum_overlap=10):
     logging.info("Merging overlaps for {0} unique pairs".format(len(keys)))
     if keys:
         fwds = [self.data[k][0][0][1] for k in keys]
-        revs = [reverse_complement(self.data[k][0][1][1]) for k in keys]
-        for s1, s2 in zip(fwds, revs):
-            if "-" in s1 or "-" in s2:
-                raise RuntimeError("Aligning Sequences with gaps is not supported", s1, s2)
+        revs = reverse_complement_many(self.data[k][0][1][1] for k in keys)
+        _reject_gapped(fwds, revs)
         try:
             sc, status, off, merged = B.merge_pairs(_ascii(fwds), _ascii(revs), minimum_overlap)
         except B.AlignError as e:
@@ -213,17 +234,17 @@ def match_to_reference(self, min_score=0.1, trim_primers=0, global_align=True, s
 def align_to_reference(self, global_align=True):
     """ambivert.py:543-574 with one batched alignment (+ traceback) for all matched amplicons"""
     keys = [k for k in self.reference if k in self.merged]
-    queries, refs = [], []
-    for k in keys:
-        ref_key = self.reference[k]
-        if ref_key[-1] == "-":          # minus-strand probe: both sequences to the plus strand
-            queries.append(reverse_complement(self.merged[k]))
-            refs.append(reverse_complement(self.reference_sequences[ref_key]))
-        else:
-            queries.append(self.merged[k])
-            refs.append(self.reference_sequences[ref_key])
     if not keys:
         return
+    ref_keys = [self.reference[k] for k in keys]
+    queries = [self.merged[k] for k in keys]
+    refs = [self.reference_sequences[rk] for rk in ref_keys]
+    minus = [i for i, rk in enumerate(ref_keys) if rk[-1] == "-"]      # minus-strand probes: both sequences to the plus strand
+    if minus:
+        rc = reverse_complement_many([queries[i] for i in minus] + [refs[i] for i in minus])
+        for j, i in enumerate(minus):
+            queries[i] = rc[j]
+            refs[i] = rc[len(minus) + j]
     for k, (sample, ref, _s, ref_start) in zip(keys, batched_pairwise(queries, refs, not global_align)):
         if ref.upper() != sample:
             self.potential_variants.append(k)
