@@ -952,7 +952,7 @@ void tb16_plan(Tb16Plan &P, int mode, const long long *a_off, const long long *b
   int max_la[TB16_NK + 1] = {0};
   int la_limit[TB16_NK], lb_limit[TB16_NK];          // per bucket: longest query, longest target that keeps values in range
   for (int b = 0; b < TB16_NK; ++b) {
-    la_limit[b] = 32 * TB16_KS[b];
+    la_limit[b] = tb16_max_la(mode == ABV_LOCAL, TB16_KS[b]);      // local keeps lane 31 free (dp_core.cuh)
     lb_limit[b] = (int)std::min<long long>(TB16_MAX_ROWS, (b16::LIMIT + 2ll * sc.go) / unit - 32ll * TB16_KS[b] - 2);
   }
   P.rest_max_la = P.rest_max_lb = 0;

@@ -487,6 +487,10 @@ struct Tb16Cfg {
   static constexpr int MAX_LA = 32 * K;
 };
 constexpr int TB16_MAX_ROWS = 1024;
+// Local mode keeps lane 31 free of columns (queries up to 31*K): it never runs a row, so its outputs stay the constants of
+// column -1 (H = 0, E = gap_open: local_align.c:123-128) and lane 0 reads them through the same indexed shuffle that hands every
+// other lane its left neighbour's border -- no select after the shuffles.  Global's column -1 changes with the row: selects.
+ABV_HD constexpr int tb16_max_la(bool local, int K) { return (local ? 31 : 32) * K; }
 constexpr int TB16_PLANES = 4;                    // bit0, bit1 of the source, F re-opened, E re-opened
 constexpr uint32_t TB16_H = 0x80008000u;
 ABV_HD int tb16_steps16(int rows_cap) { return (rows_cap + 31 + 15) >> 4; }
@@ -540,12 +544,12 @@ ABV_HD int tb16_steps4(int rows_cap) { return tb16_steps16(rows_cap) * 4; }
 //   Hp,F  : H[.][r-1] -> H[.][r]; column gap states
 //   Slo,Shi : addend-packed substitution scores of the two pairs' columns for this row's symbols
 //   gow,gew : b16::addend(go,go), b16::addend(ge,ge);  zerob = b16::biased(0,0)
-//   mj    : 0x03030303 << 2*(step % 4): the bit pair of this step in every byte of the direction word acc[k]
+//   mj    : 0x03030303 << 2*(step % 4): the bit pair of this step in every byte of the direction word acc[k]; first = step % 4 == 0
 //   LOCAL : cand[k] = running best value of column c0+k (both halves), crl[k] / crh[k] = its row in the low / high half;
 //           r = this row.  '>=' so that the last row wins ties within a column (local_align.c:156-160)
 template <int MODE, int K>
 ABV_HD void tb16_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&F)[K], const uint32_t *Slo, const uint32_t *Shi,
-                     uint32_t gow, uint32_t gew, uint32_t zerob, uint32_t mj, uint32_t (&acc)[K],
+                     uint32_t gow, uint32_t gew, uint32_t zerob, uint32_t mj, bool first, uint32_t (&acc)[K],
                      uint32_t (&cand)[K], int (&crl)[K], int (&crh)[K], int r) {
   uint32_t d = hleft;
 #pragma unroll
@@ -576,7 +580,10 @@ ABV_HD void tb16_row(uint32_t hleft, uint32_t &e, uint32_t (&Hp)[K], uint32_t (&
     e = p16::max2(hg, ee);
     const uint32_t eo = tb16_ge(hg, ee);
     Hp[k] = h;
-    acc[k] = tb16_insert(acc[k], tb16_interleave(tb16_signs(b0, b1), tb16_signs(fo, eo)), mj);
+    // the first step of a direction word overwrites it (nothing to clear after the store of the previous one); a lane that
+    // enters the matrix later in the group still holds the zero of the item start, one that has left it is never read there
+    const uint32_t T = tb16_interleave(tb16_signs(b0, b1), tb16_signs(fo, eo));
+    acc[k] = first ? (T & mj) : tb16_insert(acc[k], T, mj);
   }
 }
 

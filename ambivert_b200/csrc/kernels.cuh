@@ -5,7 +5,7 @@
 //                        over 32-column blocks with shuffle exchange; all four modes with the reference's
 //                        tie rules; optional 4-bit direction matrix + traceback (bit-exact fragment lists)
 //   tb16_kernel          one-to-one alignments WITH traceback, two pairs per warp in 16x2 DPX words (local, global):
-//                        predicate-free tie decisions, bit-plane direction matrices, warp-parallel walk back
+//                        predicate-free tie decisions, byte-packed direction words (4 steps x 4 bits x 2 halves), warp-parallel walk back
 //   variants_kernel      variant scan of aligned row pairs (call_variants.py caller()), one thread per pair
 //   md5_pairs_kernel     MD5 keys of read pairs (the clustering front end), grouped by radix sort
 //   assemble_*_kernel    gapped rows / merged reads built from the fragment pool (the string work that
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(WF32_WARPS * 32) wf32_kernel(Wf32Params p) {
 // global.  Lane t owns query columns [tK, (t+1)K) of both pairs and sweeps the target rows one row behind its
 // left neighbour; strip borders (H, E) move with two shuffles per step.  Per warp in shared memory: the two
 // pairs' substitution profiles (prof[half][symbol][column], addend-packed so that hdiag + lo + hi is two plain
-// adds), and the two targets interleaved as one 16-bit code per row.  Sequences shorter than their partner's
+// adds), and per target row the byte offsets of the two halves' profile rows (16 bits each: at most 2*8 rows of 2 KB).  Sequences shorter than their partner's
 // are padded with an extra symbol whose score is negative against everything: with gap_open < 0 a padded cell
 // is always strictly below the best real cell it derives from, so it never becomes the local end cell, and
 // real cells never depend on padded ones.  Directions: one word per column and 4 steps with the four direction bits of
@@ -264,18 +264,14 @@ struct Tb16Params {
   unsigned long long *item_counter;
 };
 constexpr int TB16_WARPS = 4;
-#ifndef TB16_UNROLL
-#define TB16_UNROLL 4
-#endif
 #ifndef TB16_MINB
 #define TB16_MINB 6
 #endif
 // resident CTAs the register allocation aims at: the shared memory of the profiles allows 6 CTAs of 4 warps at K <= 5 (85 registers)
 #define TB16_MIN_BLOCKS(K) ((K) <= 5 ? TB16_MINB : ((K) <= 8 ? 4 : 3))
-constexpr int kTb16Unroll = TB16_UNROLL;   // steps of the fill loop unrolled together (a direction word holds 4 steps)
 template <int K>
 __host__ __device__ inline int tb16_smem_per_warp(int a1, int rows_cap) {
-  return (2 * a1 * Tb16Cfg<K>::P * 4 + rows_cap * 2 + 2 * Tb16Cfg<K>::P + 15) & ~15;
+  return (2 * a1 * Tb16Cfg<K>::P * 4 + rows_cap * 4 + 2 * Tb16Cfg<K>::P + 15) & ~15;
 }
 
 template <int K>
@@ -292,7 +288,7 @@ template <int MODE, int K>
 __device__ __forceinline__ int tb16_walk(const Tb16Reader<K> &rd, int col, int row, FragOut *tmp, int cap, int lane) {
   int n = 0;
   while (col >= 0 && row >= 0) {
-    const unsigned src0 = rd.src(col, row);                     // warp-uniform address: one broadcast load per plane
+    const unsigned src0 = rd.src(col, row);                     // warp-uniform address: one broadcast load for all four bits
     if (MODE == LOCAL && src0 == SRC_STOP) break;
     FragOut f;
     if (src0 == SRC_F) {              // back to the nearest row above where the column gap was (re)opened
@@ -354,8 +350,8 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
   int *mext = reinterpret_cast<int *>(tb_smem);
   unsigned char *mine = tb_smem + ((a1 * a1 * 4 + 15) & ~15) + (size_t)warp * tb16_smem_per_warp<K>(a1, p.rows_cap);
   uint32_t *prof = reinterpret_cast<uint32_t *>(mine);                  // [half][symbol][P]
-  uint16_t *tb = reinterpret_cast<uint16_t *>(mine + 2 * a1 * P * 4);   // [rows_cap] lo | hi << 8
-  uint8_t *qc = mine + 2 * a1 * P * 4 + p.rows_cap * 2;                 // [half][P] query codes by column
+  uint32_t *tb = reinterpret_cast<uint32_t *>(mine + 2 * a1 * P * 4);   // [rows_cap] byte offset of the row's profile row: lo half | hi half << 16
+  uint8_t *qc = mine + 2 * a1 * P * 4 + p.rows_cap * 4;                 // [half][P] query codes by column
   for (int i = threadIdx.x; i < a1 * a1; i += blockDim.x) mext[i] = p.matrix_ext[i];
   __syncthreads();
 
@@ -382,7 +378,7 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
 
     __syncwarp();
     for (int r = lane; r < rows; r += 32)
-      tb[r] = (uint16_t)((r < lb0 ? tb0[r] : pad) | ((r < lb1 ? tb1[r] : pad) << 8));
+      tb[r] = (uint32_t)((r < lb0 ? tb0[r] : pad) * (P * 4)) | ((uint32_t)((a1 + (r < lb1 ? tb1[r] : pad)) * (P * 4)) << 16);
     for (int c = lane; c < 32 * K; c += 32) {
       qc[c] = c < la0 ? qa0[c] : (uint8_t)pad;
       qc[P + c] = c < la1 ? qa1[c] : (uint8_t)pad;
@@ -410,28 +406,33 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
     }
     if (MODE == GLOBAL) hleft = c0 ? b16::biased(go + ge * (c0 - 1), go + ge * (c0 - 1)) : zerob;
     else hleft = zerob;
-    h_out = zerob; e_out = zerob;
     // column -1 as seen by lane 0 at row r: H = go + ge*r, E = 2go + ge*r (global_align.c:136-140); 0, go (local_align.c:123-128)
     const uint32_t Hv0 = MODE == GLOBAL ? b16::biased(go, go) : zerob;
     const uint32_t Ev0 = MODE == GLOBAL ? b16::biased(2 * go, 2 * go) : b16::biased(go, go);
+    // local: lane 31 owns no column (tb16_max_la) and keeps the constants of column -1 for lane 0's indexed shuffle
+    h_out = zerob; e_out = (MODE == LOCAL && lane == 31) ? Ev0 : zerob;
     const int t0 = (la0 - 1) / K, k0 = (la0 - 1) - t0 * K, t1 = (la1 - 1) / K, k1 = (la1 - 1) - t1 * K;
     int corner0 = 0, corner1 = 0;
 
     for (int s4 = 0; s4 < nsteps; s4 += 4) {
-#pragma unroll kTb16Unroll
-      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {              // fully unrolled: a direction word holds 4 steps, the first one overwrites it
         const int s = s4 + j;
-        uint32_t h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
-        uint32_t e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+        uint32_t h_sh, e_sh;
         const int r = s - lane;
-        if (lane == 0) {
-          h_sh = MODE == GLOBAL ? Hv0 + (uint32_t)r * gew : Hv0;
-          e_sh = MODE == GLOBAL ? Ev0 + (uint32_t)r * gew : Ev0;
+        if (MODE == LOCAL) {
+          h_sh = __shfl_sync(ABV_FULL, h_out, (lane + 31) & 31);
+          e_sh = __shfl_sync(ABV_FULL, e_out, (lane + 31) & 31);
+        } else {
+          h_sh = __shfl_up_sync(ABV_FULL, h_out, 1);
+          e_sh = __shfl_up_sync(ABV_FULL, e_out, 1);
+          if (lane == 0) { h_sh = Hv0 + (uint32_t)r * gew; e_sh = Ev0 + (uint32_t)r * gew; }
         }
         if (r >= 0 && r < rows && lane <= tl) {
-          const unsigned code = tb[r];
+          const uint32_t code = tb[r];
           uint32_t Slo[K], Shi[K];
-          const uint32_t *rlo = prof + (code & 255u) * P, *rhi = prof + (a1 + (code >> 8)) * P;
+          const uint32_t *rlo = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(prof) + (code & 0xffffu));
+          const uint32_t *rhi = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(prof) + (code >> 16));
           if (V == 4) {
 #pragma unroll
             for (int i = 0; i < K / 4; ++i) {
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
             for (int i = 0; i < K; ++i) { Slo[i] = rlo[i * 32 + lane]; Shi[i] = rhi[i * 32 + lane]; }
           }
           uint32_t e = e_sh;
-          tb16_row<MODE, K>(hleft, e, Hp, F, Slo, Shi, gow, gew, zerob, 0x03030303u << (2 * j), acc, cand, crl, crh, r);
+          tb16_row<MODE, K>(hleft, e, Hp, F, Slo, Shi, gow, gew, zerob, 0x03030303u << (2 * j), j == 0, acc, cand, crl, crh, r);
           hleft = h_sh; e_out = e; h_out = Hp[K - 1];
           if (MODE == GLOBAL) {                                   // the corner cell is the score (global_align.c:217)
             if (r == lb0 - 1 && lane == t0) corner0 = b16::lo(tb16_pick<K>(Hp, k0));
@@ -460,10 +461,7 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
       }
       const long long wbase = (long long)(s4 >> 2) * 32 + lane;
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        dir[(long long)k * steps4 * 32 + wbase] = acc[k];
-        acc[k] = 0;
-      }
+      for (int k = 0; k < K; ++k) dir[(long long)k * steps4 * 32 + wbase] = acc[k];
     }
 
     // end cell and score of each half

@@ -543,7 +543,7 @@ extern "C" int emu_variants(const unsigned char *sample, int ls, const unsigned 
 // ---------------------------------------------------------------------------------------------
 // tb16 (kernels.cuh::tb16_kernel): two pairs in the 16-bit halves, lane t owns columns [tK, (t+1)K), rows skewed
 // by lane.  Mirrors the kernel's item loop for ONE item with the device row function (dp_core.cuh::tb16_row) and
-// the device plane layout (Tb16Reader); the walk back uses the generic walk over the reader's nibble view.
+// the device direction-word layout (Tb16Reader); the walk back uses the generic walk over the reader's nibble view.
 template <int MODE, int K>
 static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *tb0, int lb0,
                        const unsigned char *qa1, int la1, const unsigned char *tb1, int lb1,
@@ -584,19 +584,17 @@ static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *t
   }
   const uint32_t Hv0 = MODE == GLOBAL ? b16::biased(go, go) : zerob;
   const uint32_t Ev0 = MODE == GLOBAL ? b16::biased(2 * go, 2 * go) : b16::biased(go, go);
+  if (MODE == LOCAL) L[31].e_out = Ev0;          // local: lane 31 owns no column and holds column -1 for lane 0 (tb16_max_la)
   const int t0 = (la0 - 1) / K, k0 = (la0 - 1) - t0 * K, t1 = (la1 - 1) / K, k1 = (la1 - 1) - t1 * K;
   int corner0 = 0, corner1 = 0;
   for (int s4 = 0; s4 < nsteps; s4 += 4) {
     for (int j = 0; j < 4; ++j) {
       const int s = s4 + j;
       uint32_t h_sh[32], e_sh[32];
-      for (int t = 0; t < 32; ++t) { h_sh[t] = L[t ? t - 1 : 0].h_out; e_sh[t] = L[t ? t - 1 : 0].e_out; }
+      for (int t = 0; t < 32; ++t) { h_sh[t] = L[(t + 31) & 31].h_out; e_sh[t] = L[(t + 31) & 31].e_out; }
       for (int t = 0; t < 32; ++t) {
         const int r = s - t;
-        if (t == 0) {
-          h_sh[0] = MODE == GLOBAL ? Hv0 + (uint32_t)r * gew : Hv0;
-          e_sh[0] = MODE == GLOBAL ? Ev0 + (uint32_t)r * gew : Ev0;
-        }
+        if (t == 0 && MODE == GLOBAL) { h_sh[0] = Hv0 + (uint32_t)r * gew; e_sh[0] = Ev0 + (uint32_t)r * gew; }
         if (r >= 0 && r < rows && t <= tl) {
           const unsigned code = tb[r];
           uint32_t Slo[K], Shi[K];
@@ -605,7 +603,7 @@ static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *t
             Shi[k] = prof[(a1 + (code >> 8)) * P + tb16_slot(t, k, V)];
           }
           uint32_t e = e_sh[t];
-          tb16_row<MODE, K>(L[t].hleft, e, L[t].Hp, L[t].F, Slo, Shi, gow, gew, zerob, 0x03030303u << (2 * j), L[t].acc, L[t].cand, L[t].crl, L[t].crh, r);
+          tb16_row<MODE, K>(L[t].hleft, e, L[t].Hp, L[t].F, Slo, Shi, gow, gew, zerob, 0x03030303u << (2 * j), j == 0, L[t].acc, L[t].cand, L[t].crl, L[t].crh, r);
           L[t].hleft = h_sh[t]; L[t].e_out = e; L[t].h_out = L[t].Hp[K - 1];
           if (MODE == GLOBAL) {
             if (r == lb0 - 1 && t == t0) corner0 = b16::lo(L[t].Hp[k0]);
@@ -615,10 +613,7 @@ static void emu_tb16_t(const unsigned char *qa0, int la0, const unsigned char *t
       }
     }
     for (int t = 0; t < 32; ++t)
-      for (int k = 0; k < K; ++k) {
-        dir[((size_t)k * steps4 + (s4 >> 2)) * 32 + t] = L[t].acc[k];
-        L[t].acc[k] = 0;
-      }
+      for (int k = 0; k < K; ++k) dir[((size_t)k * steps4 + (s4 >> 2)) * 32 + t] = L[t].acc[k];
   }
   int sc[2], ec[2], er[2];
   if (MODE == GLOBAL) { sc[0] = corner0; sc[1] = corner1; ec[0] = la0 - 1; er[0] = lb0 - 1; ec[1] = la1 - 1; er[1] = lb1 - 1; }
@@ -662,6 +657,7 @@ static int emu_tb16_k(int K, const unsigned char *qa0, int la0, const unsigned c
 extern "C" int emu_tb16(int mode, int K, const unsigned char *qa0, int la0, const unsigned char *tb0, int lb0,
                         const unsigned char *qa1, int la1, const unsigned char *tb1, int lb1,
                         int alpha, const int *M, int go, int ge, int pad_score, int *score, int *nfrag, FragOut *f0, FragOut *f1, int cap) {
+  if (std::max(la0, la1) > tb16_max_la(mode == LOCAL, K)) return -1;      // what the host plan never sends (local: lane 31 stays free)
   if (mode == LOCAL) return emu_tb16_k<LOCAL>(K, qa0, la0, tb0, lb0, qa1, la1, tb1, lb1, alpha, M, go, ge, pad_score, score, nfrag, f0, f1, cap);
   if (mode == GLOBAL) return emu_tb16_k<GLOBAL>(K, qa0, la0, tb0, lb0, qa1, la1, tb1, lb1, alpha, M, go, ge, pad_score, score, nfrag, f0, f1, cap);
   return -1;

@@ -554,7 +554,8 @@ def test_packed_traceback_kernel_vs_32bit_kernel_sweep(B, oracle_port, mode):
     rng = random.Random(77 + mode)
     a_list, b_list = [], []
     for i in range(6001):
-        la = rng.choice([1, 2, 31, 33, 64, 65, 128, 129, 150, 160, 161, 192, 224, 225, 256, 257, 320, rng.randint(1, 330)])
+        la = rng.choice([1, 2, 31, 33, 64, 65, 128, 129, 150, 160, 161, 192, 224, 225, 256, 257, 320, rng.randint(1, 330),
+                         62, 63, 124, 125, 155, 156, 186, 187, 217, 218, 248, 249, 310, 311])     # 31*K and 31*K + 1: the local-mode capacity
         a = rand_dna(rng, la, "ACGTN" if rng.random() < 0.1 else "ACGT")
         x = rng.random()
         if x < 0.5:
