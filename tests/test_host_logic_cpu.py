@@ -112,3 +112,28 @@ def test_bench_merge_roofline_uses_the_committed_sass_count():
     want = int(re.search(r"steady-state loop 0x[0-9a-f]+\.\.0x[0-9a-f]+: (\d+) instructions", rep).group(1))
     got = int(re.search(r"^TB16_LOCAL_K5_LOOP_INSTR = (\d+)", bench, re.M).group(1))
     assert got == want
+
+
+def test_bulk_string_helpers_match_the_per_sequence_forms():
+    """reverse_complement_many / _reject_gapped / _ascii are bulk forms of per-sequence operations of the reference
+    (sequence_utilities.py:96-128, ambivert.py:80-84): same results, same exceptions"""
+    import random
+    import numpy as np
+    import pytest
+    from ambivert_b200 import host as H
+    rng = random.Random(5)
+    seqs = ["".join(rng.choice("ACGTNacgtnRYKMxz.-") for _ in range(rng.randint(0, 40))) for _ in range(500)]
+    assert H.reverse_complement_many(seqs) == [H.reverse_complement(s) for s in seqs]
+    assert H.reverse_complement_many(iter(seqs[:7])) == [H.reverse_complement(s) for s in seqs[:7]]
+    assert H.reverse_complement_many([]) == [] and H.reverse_complement_many([""]) == [""]
+    assert H.reverse_complement_many(["A\nC", "G"]) == ["G\nT".replace("\n", "n"), "C"]      # a line break is an unknown character: 'n'
+    H._reject_gapped(["ACGT", "AC"], ["A", "T"])
+    with pytest.raises(RuntimeError) as e:
+        H._reject_gapped(["ACGT", "A-C", "-"], ["A", "T", "G"])
+    assert e.value.args[1:] == ("A-C", "T")                       # the FIRST offending pair, as the reference's loop reports it
+    buf, off = H._ascii(["ACG", "", "TT"])
+    assert bytes(buf) == b"ACGTT" and off.tolist() == [0, 3, 3, 5] and off.dtype == np.int64
+    with pytest.raises(UnicodeEncodeError):
+        H._ascii(["ACé"])
+    with pytest.raises(TypeError):
+        H._ascii([b"ACGT"])
