@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(WF32_WARPS * 32) wf32_kernel(Wf32Params p) {
 // global.  Lane t owns query columns [tK, (t+1)K) of both pairs and sweeps the target rows one row behind its
 // left neighbour; strip borders (H, E) move with two shuffles per step.  Per warp in shared memory: the two
 // pairs' substitution profiles (prof[half][symbol][column], addend-packed so that hdiag + lo + hi is two plain
-// adds), and per target row the byte offsets of the two halves' profile rows (16 bits each: at most 2*8 rows of 2 KB).  Sequences shorter than their partner's
+// adds), and per target row the offsets of the two halves' profile rows (8 bits each, in units of 128 bytes).  Sequences shorter than their partner's
 // are padded with an extra symbol whose score is negative against everything: with gap_open < 0 a padded cell
 // is always strictly below the best real cell it derives from, so it never becomes the local end cell, and
 // real cells never depend on padded ones.  Directions: one word per column and 4 steps with the four direction bits of
@@ -271,7 +271,9 @@ constexpr int TB16_WARPS = 4;
 #define TB16_MIN_BLOCKS(K) ((K) <= 5 ? TB16_MINB : ((K) <= 8 ? 4 : 3))
 template <int K>
 __host__ __device__ inline int tb16_smem_per_warp(int a1, int rows_cap) {
-  return (2 * a1 * Tb16Cfg<K>::P * 4 + rows_cap * 4 + 2 * Tb16Cfg<K>::P + 15) & ~15;
+  // profiles + one area that holds the query codes while the profiles are built and the target rows afterwards
+  const int rows_bytes = rows_cap * 2, qc_bytes = 2 * Tb16Cfg<K>::P;
+  return (2 * a1 * Tb16Cfg<K>::P * 4 + (rows_bytes > qc_bytes ? rows_bytes : qc_bytes) + 15) & ~15;
 }
 
 template <int K>
@@ -342,6 +344,7 @@ __device__ __forceinline__ int tb16_walk(const Tb16Reader<K> &rd, int col, int r
 template <int MODE, int K>
 __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kernel(Tb16Params p) {
   static_assert(MODE == LOCAL || MODE == GLOBAL, "tb16 implements local and global");
+  static_assert(15 * K < 256, "profile-row offsets of a target row are 8 bits per half (alphabet + padding symbol <= 8 rows per half)");
   constexpr int V = Tb16Cfg<K>::V, P = Tb16Cfg<K>::P;
   extern __shared__ __align__(16) unsigned char tb_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -350,8 +353,10 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
   int *mext = reinterpret_cast<int *>(tb_smem);
   unsigned char *mine = tb_smem + ((a1 * a1 * 4 + 15) & ~15) + (size_t)warp * tb16_smem_per_warp<K>(a1, p.rows_cap);
   uint32_t *prof = reinterpret_cast<uint32_t *>(mine);                  // [half][symbol][P]
-  uint32_t *tb = reinterpret_cast<uint32_t *>(mine + 2 * a1 * P * 4);   // [rows_cap] byte offset of the row's profile row: lo half | hi half << 16
-  uint8_t *qc = mine + 2 * a1 * P * 4 + p.rows_cap * 4;                 // [half][P] query codes by column
+  // [rows_cap] per target row the offsets of the two halves' profile rows in units of 128 bytes (a row is K units; at most
+  // 2*8 rows of 16 units): lo half | hi half << 8.  The same bytes hold the query codes [half][P] while the profiles are built.
+  uint16_t *tb = reinterpret_cast<uint16_t *>(mine + 2 * a1 * P * 4);
+  uint8_t *qc = mine + 2 * a1 * P * 4;
   for (int i = threadIdx.x; i < a1 * a1; i += blockDim.x) mext[i] = p.matrix_ext[i];
   __syncthreads();
 
@@ -377,8 +382,6 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
     const int nsteps = rows + tl;
 
     __syncwarp();
-    for (int r = lane; r < rows; r += 32)
-      tb[r] = (uint32_t)((r < lb0 ? tb0[r] : pad) * (P * 4)) | ((uint32_t)((a1 + (r < lb1 ? tb1[r] : pad)) * (P * 4)) << 16);
     for (int c = lane; c < 32 * K; c += 32) {
       qc[c] = c < la0 ? qa0[c] : (uint8_t)pad;
       qc[P + c] = c < la1 ? qa1[c] : (uint8_t)pad;
@@ -391,6 +394,9 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
       prof[idx] = b16::addend(mext[qc[t * K + k] * a1 + sym], 0);
       prof[a1 * P + idx] = b16::addend(0, mext[qc[P + t * K + k] * a1 + sym]);
     }
+    __syncwarp();                                 // the query codes are dead: their bytes take the target rows
+    for (int r = lane; r < rows; r += 32)
+      tb[r] = (uint16_t)(((r < lb0 ? tb0[r] : pad) * K) | (((a1 + (r < lb1 ? tb1[r] : pad)) * K) << 8));
     __syncwarp();
 
     uint32_t Hp[K], F[K], acc[K], cand[K];
@@ -431,8 +437,7 @@ __global__ void __launch_bounds__(TB16_WARPS * 32, TB16_MIN_BLOCKS(K)) tb16_kern
         if (r >= 0 && r < rows && lane <= tl) {
           const uint32_t code = tb[r];
           uint32_t Slo[K], Shi[K];
-          const uint32_t *rlo = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(prof) + (code & 0xffffu));
-          const uint32_t *rhi = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(prof) + (code >> 16));
+          const uint32_t *rlo = prof + (code & 0xffu) * 32u, *rhi = prof + (code >> 8) * 32u;
           if (V == 4) {
 #pragma unroll
             for (int i = 0; i < K / 4; ++i) {

@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 # lane-ops per packed cell pair of the two kernel generations and the abv_int_peak mix that measures each
 CELL_OPS_STREAMING = 4       # mm16g_kernel: 1 add + VIMNMX3.S16x2 + 2 VIADDMNMX.S16x2          -> abv_int_peak(8)
 CELL_OPS_FIRST_GEN = 5       # mm16_kernel:  2 VIADD.16x2 + VIMNMX3.S16x2 + 2 VIADDMNMX.S16x2   -> abv_int_peak(4)
-TB16_LOCAL_K5_LOOP_INSTR = 656   # SASS instructions of tb16_kernel<local,K=5>'s fill loop (4 steps): profiles/r02_sass_tb16_local_k5_step.txt
+TB16_LOCAL_K5_LOOP_INSTR = 646   # SASS instructions of tb16_kernel<local,K=5>'s fill loop (4 steps): profiles/r02_sass_tb16_local_k5_step.txt
 TB16_LOOP_STEPS = 4
 MODE_NAMES = {"global": 2, "glocal": 3, "local": 1}
 WORKLOADS = {"config4": (100000, 2000), "config5": (1000000, 10000)}
