@@ -285,16 +285,33 @@ class BestHitsJob:
             pass
 
 
+def align_pairs_buffers(n, frag_cap):
+    """page-locked result buffers for align_pairs(out=...): (scores int32[n], frag_start int64[n], frag_count int32[n],
+    frags int32[frag_cap, 4]).  Results land in them at bus speed and without holding the calling thread; reuse them from call to call."""
+    return (pinned_empty(n, np.int32), pinned_empty(n, np.int64), pinned_empty(n, np.int32), pinned_empty(4 * int(frag_cap), np.int32).reshape(-1, 4))
+
+
 def align_pairs(seqs_a, seqs_b, mode, alpha_len=DNA_MAP[0], map256=DNA_MAP[1], matrix=DNA_SCORE,
-                gap_open=GAP_OPEN, gap_extend=GAP_EXTEND, frag_cap=None):
+                gap_open=GAP_OPEN, gap_extend=GAP_EXTEND, frag_cap=None, out=None):
     """One-to-one alignments with traceback.
     -> (scores int32[n], frag_start int64[n], frag_count int32[n], frags int32[total, 4])
-    frags rows are (type, sa_start, sb_start, hsp_len); pair k owns rows frag_start[k] .. +frag_count[k]."""
+    frags rows are (type, sa_start, sb_start, hsp_len); pair k owns rows frag_start[k] .. +frag_count[k].
+    out: optional result buffers (align_pairs_buffers: page-locked); the returned arrays are views of them and the size of
+    out[3] is the fragment pool (AlignError ERR_FRAG_CAP if it is too small)."""
     a, ao = pack(seqs_a)
     b, bo = pack(seqs_b)
     n = len(ao) - 1
     assert len(bo) - 1 == n, "align_pairs needs as many b sequences as a sequences"
     mp, m = _scoring(alpha_len, map256, matrix)
+    if out is not None:
+        scores, start, count, frags = out
+        assert scores.dtype == np.int32 and start.dtype == np.int64 and count.dtype == np.int32 and frags.dtype == np.int32
+        assert scores.size >= n and start.size >= n and count.size >= n and frags.ndim == 2 and frags.shape[1] == 4
+        assert all(x.flags.c_contiguous for x in out)
+        total = C.c_longlong(0)
+        _check(_lib.abv_align_pairs(mode, _ptr(a), _ptr(ao), _ptr(b), _ptr(bo), n, alpha_len, _ptr(mp), _ptr(m), gap_open, gap_extend,
+                                    _ptr(scores), _ptr(start), _ptr(count), _ptr(frags), frags.shape[0], C.byref(total)))
+        return scores[:n], start[:n], count[:n], frags[:total.value]
     scores = np.empty(n, np.int32)
     start = np.empty(n, np.int64)
     count = np.empty(n, np.int32)

@@ -92,6 +92,36 @@ struct DevCache {
   }
 };
 
+// Page-locked host staging blocks, cached like the device blocks.  A copy from pageable memory holds the calling thread until the
+// driver has staged it (0.3-0.5 ms per 1.6 MB offsets array); from a pinned block it is queued and the host goes on.
+struct PinCache {
+  struct Block { void *p; size_t bytes; };
+  std::vector<Block> free_blocks;
+  size_t cached_bytes = 0;
+  cudaError_t get(size_t n, void **out, size_t *got) {
+    int best = -1;
+    for (int i = 0; i < (int)free_blocks.size(); ++i)
+      if (free_blocks[i].bytes >= n && free_blocks[i].bytes <= 2 * n + 4096 && (best < 0 || free_blocks[i].bytes < free_blocks[best].bytes)) best = i;
+    if (best >= 0) {
+      *out = free_blocks[best].p; *got = free_blocks[best].bytes;
+      cached_bytes -= free_blocks[best].bytes;
+      free_blocks.erase(free_blocks.begin() + best);
+      return cudaSuccess;
+    }
+    *got = n;
+    return cudaHostAlloc(out, n, cudaHostAllocDefault);
+  }
+  void put(void *p, size_t bytes) {
+    free_blocks.push_back({p, bytes});
+    cached_bytes += bytes;
+    while (cached_bytes > ((size_t)256 << 20) && !free_blocks.empty()) {      // at most 256 MB stay locked
+      cudaFreeHost(free_blocks.front().p);
+      cached_bytes -= free_blocks.front().bytes;
+      free_blocks.erase(free_blocks.begin());
+    }
+  }
+};
+
 // ---- device contexts -----------------------------------------------------------------------------------------------
 // One context per CUDA device (streams, events, pinned words, allocation cache, a mutex).  A call works on the context of
 // the CALLING THREAD's device: the process default (abv_set_device; one process per GPU under torchrun) unless the thread
@@ -130,6 +160,7 @@ struct Ctx {
   unsigned long long *pin64 = nullptr; // 64 pinned words: counters read back per chunk (a copy into pageable memory would block the host until the chunk has finished)
   cudaEvent_t ev[6] = {};
   DevCache cache;
+  PinCache pin_cache;
   bool md5_ready = false;              // constant memory is per device: the MD5 table has been uploaded here
 };
 Ctx g_ctx[ABV_MAX_DEVICES];
@@ -210,6 +241,25 @@ struct DevMem {
   template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// RAII page-locked host block from the context's cache
+struct PinMem {
+  void *p = nullptr;
+  size_t bytes = 0;
+  Ctx *owner = nullptr;
+  PinMem() = default;
+  PinMem(const PinMem &) = delete;
+  PinMem &operator=(const PinMem &) = delete;
+  ~PinMem() { release(); }
+  void release() { if (p) owner->pin_cache.put(p, bytes); p = nullptr; bytes = 0; }
+  cudaError_t alloc(size_t n) {
+    if (p && bytes >= n) return cudaSuccess;
+    release();
+    owner = &cur_ctx();
+    return owner->pin_cache.get(std::max<size_t>(n, 256), &p, &bytes);
+  }
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
 struct Scoring {
   int alpha, go, ge;
   const unsigned char *map256;   // may be NULL (inputs are codes)
@@ -266,7 +316,7 @@ int check_mode_lengths(int mode, int min_la, int min_lb) {
 // upload a concatenated sequence set and encode it on the device
 // Host buffers an upload reads asynchronously; they must outlive the stream work (the caller syncs before dropping them).
 struct UploadKeep {
-  std::vector<long long> rel[4];
+  PinMem rel[4];               // offsets relative to the first sequence, page-locked: their copies do not hold the host
   unsigned char clamped[256];
   int used = 0;
 };
@@ -283,11 +333,12 @@ int upload_encoded(const char *buf, const long long *off, int n, const Scoring &
   UploadKeep &K = keep ? *keep : local;
   const long long total = n ? off[n] - off[0] : 0;
   if (phase != 2) {
-    std::vector<long long> &rel = K.rel[K.used++ & 3];
-    rel.resize((size_t)n + 1);
+    PinMem &relm = K.rel[K.used++ & 3];
+    CU(relm.alloc(sizeof(long long) * ((size_t)n + 1)));
+    long long *rel = relm.as<long long>();
     for (int i = 0; i <= n; ++i) rel[i] = n ? off[i] - off[0] : 0;
     CU(d_off.alloc(sizeof(long long) * (n + 1)));
-    CU(cudaMemcpyAsync(d_off.p, rel.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_off.p, rel, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
     unsigned char ident[256];
     const unsigned char *m = sc.map256;
     if (!m) { for (int i = 0; i < 256; ++i) ident[i] = (unsigned char)i; m = ident; }

@@ -134,3 +134,25 @@ def test_chunk_pipeline_equals_one_piece():
         assert str(e0.value) == str(e1.value)
     finally:
         B.set_option("pairs_chunk", 200000)
+
+
+def test_align_pairs_into_pinned_result_buffers():
+    """align_pairs(out=align_pairs_buffers(...)): same results as the plain call, returned as views of the page-locked buffers;
+    a fragment pool that is too small raises ERR_FRAG_CAP with scores and counts valid"""
+    import random
+    from ambivert_b200 import batch as B
+    rng = random.Random(31)
+    a = ["".join(rng.choice("ACGT") for _ in range(rng.randint(20, 160))).encode() for _ in range(300)]
+    b = [x[rng.randrange(len(x) // 2):] + "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 40))).encode() for x in a]
+    want = B.align_pairs(a, b, B.LOCAL)
+    bufs = B.align_pairs_buffers(len(a) + 5, 8 * len(a))
+    got = B.align_pairs(a, b, B.LOCAL, out=bufs)
+    assert (got[0] == want[0]).all() and (got[2] == want[2]).all() and got[3].shape == want[3].shape
+    for k in range(len(a)):            # a pair's place in the fragment pool depends on the order the warps finish in
+        assert B.fragments(k, got[1], got[2], got[3]) == B.fragments(k, want[1], want[2], want[3]), k
+    assert got[0].ctypes.data == bufs[0].ctypes.data and got[3].ctypes.data == bufs[3].ctypes.data
+    small = B.align_pairs_buffers(len(a), 10)
+    with pytest.raises(B.AlignError) as e:
+        B.align_pairs(a, b, B.LOCAL, out=small)
+    assert e.value.code == B.ERR_FRAG_CAP
+    assert (small[0][:len(a)] == want[0]).all() and (small[2][:len(a)] == want[2]).all()
