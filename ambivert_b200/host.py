@@ -115,7 +115,7 @@ def _reject_gapped(seqs1, seqs2):
                 raise RuntimeError("Aligning Sequences with gaps is not supported", s1, s2)
 
 
-def batched_pairwise(seqs1, seqs2, local):
+def batched_pairwise(seqs1, seqs2, local, raw=False):
     """smith_waterman (local=True, ambivert.py:75-114) / needleman_wunsch (ambivert.py:116-155) for a
     whole batch: -> list of (align_seq1, align_seq2, start_seq1, start_seq2).  The aligner sees
     seq2.upper() in the reference; DNA_MAP is case-insensitive, so seq2 goes in as it is and the gapped
@@ -131,6 +131,8 @@ def batched_pairwise(seqs1, seqs2, local):
         raise ValueError("NULL pointer access")                # alignment.contents.align_frag.contents on an empty list
     t1, t2 = rows1.tobytes().decode("ascii"), rows2.tobytes().decode("ascii")
     offs = off.tolist()
+    if raw:            # the two texts of all gapped rows, their offsets and the start positions: for callers that slice themselves
+        return t1, t2, offs, (st1.tolist() if local else None), (st2.tolist() if local else None)
     if local:
         return [(t1[offs[k]:offs[k + 1]], t2[offs[k]:offs[k + 1]], int(st1[k]), int(st2[k])) for k in range(len(seqs1))]
     return [(t1[offs[k]:offs[k + 1]], t2[offs[k]:offs[k + 1]], 0, 0) for k in range(len(seqs1))]
@@ -245,12 +247,21 @@ def align_to_reference(self, global_align=True):
         for j, i in enumerate(minus):
             queries[i] = rc[j]
             refs[i] = rc[len(minus) + j]
-    for k, (sample, ref, _s, ref_start) in zip(keys, batched_pairwise(queries, refs, not global_align)):
-        if ref.upper() != sample:
-            self.potential_variants.append(k)
-        self.aligned[k] = (sample, ref)
-        rk = self.reference[k]
-        self.location[k] = (rk[1], int(rk[2]), int(rk[3]), ref_start)
+    t1, t2, offs, _st1, st2 = batched_pairwise(queries, refs, not global_align, raw=True)
+    t2_upper = t2.upper()                           # ref.upper() != sample (ambivert.py:566) on one upper-cased text, not per row
+    place = {}                                      # (chromosome, start, end) of a target, converted once per target
+    aligned, location, potential = self.aligned, self.location, self.potential_variants
+    for i, k in enumerate(keys):
+        a, b = offs[i], offs[i + 1]
+        sample = t1[a:b]
+        if t2_upper[a:b] != sample:
+            potential.append(k)
+        aligned[k] = (sample, t2[a:b])
+        rk = ref_keys[i]
+        loc = place.get(rk)
+        if loc is None:
+            loc = place[rk] = (rk[1], int(rk[2]), int(rk[3]))
+        location[k] = loc + (st2[i] if st2 is not None else 0,)
 
 
 def _reference_sha224(self):
