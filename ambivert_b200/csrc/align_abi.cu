@@ -274,15 +274,15 @@ int check_scoring(const Scoring &sc) {
 }
 
 // lengths of a concatenated sequence set; rejects what the reference rejects
-int check_seqs(const char *buf, const long long *off, int n, const char *what, int &maxlen, int &minlen) {
+int check_seqs(const char *buf, const long long *off, int n, const char *what, int &maxlen, int &minlen, int base = 0) {
   maxlen = 0; minlen = INT_MAX;
   if (n < 0) return fail(ABV_ERR_ARGS, "%s: negative count", what);
   if (n == 0) { minlen = 0; return ABV_OK; }
   if (!buf || !off) return fail(ABV_ERR_ARGS, "%s: NULL buffer", what);
   for (int i = 0; i < n; ++i) {
     long long l = off[i + 1] - off[i];
-    if (l <= 0) return fail(ABV_ERR_ARGS, "%s %d has length %lld (the reference returns NULL for length <= 0)", what, i, l);
-    if (l > (1 << 24)) return fail(ABV_ERR_ARGS, "%s %d is longer than 2^24", what, i);
+    if (l <= 0) return fail(ABV_ERR_ARGS, "%s %d has length %lld (the reference returns NULL for length <= 0)", what, base + i, l);
+    if (l > (1 << 24)) return fail(ABV_ERR_ARGS, "%s %d is longer than 2^24", what, base + i);
     maxlen = std::max(maxlen, (int)l);
     minlen = std::min(minlen, (int)l);
   }
@@ -1332,11 +1332,11 @@ struct PairsRun {
 };
 
 static int pairs_validate(int mode, const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
-                          const Scoring &sc, int &max_la, int &max_lb) {
+                          const Scoring &sc, int &max_la, int &max_lb, int base = 0) {
   int rc, min_la, min_lb;
   if ((rc = check_scoring(sc))) return rc;
-  if ((rc = check_seqs(a, a_off, n, "sequence a", max_la, min_la))) return rc;
-  if ((rc = check_seqs(b, b_off, n, "sequence b", max_lb, min_lb))) return rc;
+  if ((rc = check_seqs(a, a_off, n, "sequence a", max_la, min_la, base))) return rc;
+  if ((rc = check_seqs(b, b_off, n, "sequence b", max_lb, min_lb, base))) return rc;
   if (mode < 0 || mode > 3) return fail(ABV_ERR_ARGS, "unknown mode %d", mode);
   if (n > 0 && (rc = check_mode_lengths(mode, min_la, min_lb))) return rc;
   if ((rc = check_symbols(a, a_off, n, sc, "sequence a"))) return rc;
@@ -1491,6 +1491,24 @@ static std::vector<int> pairs_chunk_bounds(int n) {
   }
   return b;
 }
+// Validation of a pipelined job in two stages.  Walking the offsets of a million pairs takes 2 ms in which the device would wait
+// for its first chunk: the pairs of the first two chunks are checked before anything is sent, the others once those two chunks are
+// on their way.  No result leaves the device before the second stage has passed, so a rejected job still writes nothing.
+struct StagedValidation {
+  int mode; const char *a; const long long *a_off; const char *b; const long long *b_off; int n; const Scoring *sc;
+  int first = 0;          // pairs covered by stage 1 (all of them if the job is not pipelined)
+  int stage1(const std::vector<int> &bounds, int &max_la, int &max_lb) {
+    first = bounds.size() > 2 ? bounds[2] : n;
+    return pairs_validate(mode, a, a_off, b, b_off, first, *sc, max_la, max_lb);
+  }
+  int stage2(int &max_la, int &max_lb) const {
+    if (first >= n) return ABV_OK;
+    int la = 0, lb = 0;
+    const int rc = pairs_validate(mode, a, a_off + first, b, b_off + first, n - first, *sc, la, lb, first);
+    max_la = std::max(max_la, la); max_lb = std::max(max_lb, lb);
+    return rc;
+  }
+};
 static int pairs_chunk_begin(PairsRun &R, int c) {
   R.st = (c & 1) ? g.stream2 : g.stream;
   for (auto &e : R.ev) CU(cudaEventCreate(&e));
@@ -1508,7 +1526,9 @@ int abv_align_pairs(int mode, const char *a, const long long *a_off, const char 
   int rc;
   Scoring sc{alpha_len, gap_open, gap_extend, map256, score_matrix};
   PairsRun R;
-  if ((rc = pairs_validate(mode, a, a_off, b, b_off, n, sc, R.max_la, R.max_lb))) return rc;
+  const std::vector<int> bounds = pairs_chunk_bounds(n);
+  StagedValidation val{mode, a, a_off, b, b_off, n, &sc};
+  if ((rc = val.stage1(bounds, R.max_la, R.max_lb))) return rc;
   if (frag_cap < 0 || (frag_cap > 0 && !frags)) return fail(ABV_ERR_ARGS, "bad fragment pool");
   if (frag_total) *frag_total = 0;
   if (n == 0) return ABV_OK;
@@ -1516,7 +1536,7 @@ int abv_align_pairs(int mode, const char *a, const long long *a_off, const char 
   if ((rc = ctx_init())) return rc;
   for (double &v : t_timing) v = 0;
   cudaStream_t st = g.stream;
-  if (const std::vector<int> bounds = pairs_chunk_bounds(n); bounds.size() > 2) {
+  if (bounds.size() > 2) {
     // pipeline of chunks: enqueue two ahead, then per chunk wait, download, enqueue the next one
     const int C = (int)bounds.size() - 1;
     std::vector<std::unique_ptr<PairsRun>> Rs;
@@ -1535,6 +1555,7 @@ int abv_align_pairs(int mode, const char *a, const long long *a_off, const char 
     auto drain = [&]() { cudaStreamSynchronize(g.stream); cudaStreamSynchronize(g.stream2); cudaStreamSynchronize(g.stream3); };
     for (int c = 0; c < std::min(2, C); ++c)
       if ((rc = enqueue(c))) { drain(); return rc; }
+    if ((rc = val.stage2(R.max_la, R.max_lb))) { drain(); return rc; }      // the other chunks' pairs, beside the first kernels
     long long base = 0;
     bool overflow = false, chunk_overflow = false;
     double d2h = 0, h2d = 0, cells = 0, ms_up = 0, ms_k = 0, ms_down = 0;
@@ -1624,8 +1645,8 @@ struct AsmChunk {
   ~AsmChunk() { if (done) cudaEventDestroy(done); }
 };
 static int assemble_chunked(const std::vector<int> &bounds, int what, int mode, const char *a, const long long *a_off, const char *b, const long long *b_off, int n,
-                            const Scoring &sc, int max_la, int max_lb, int minimum_overlap, int *scores, int *status, int *start_a,
-                            int *start_b, long long *out_off, char *out1, char *out2, long long out_cap, long long *out_total) {
+                            const Scoring &sc, int &max_la, int &max_lb, const StagedValidation &val, int minimum_overlap, int *scores, int *status,
+                            int *start_a, int *start_b, long long *out_off, char *out1, char *out2, long long out_cap, long long *out_total) {
   int rc;
   const int C = (int)bounds.size() - 1;
   std::vector<std::unique_ptr<AsmChunk>> Cs;
@@ -1669,6 +1690,7 @@ static int assemble_chunked(const std::vector<int> &bounds, int what, int mode, 
   };
   for (int c = 0; c < std::min(2, C); ++c)
     if ((rc = phase_a(c))) { drain(); return rc; }
+  if ((rc = val.stage2(max_la, max_lb))) { drain(); return rc; }      // the other chunks' pairs, beside the first kernels
   long long byte_base = 0;
   double d2h = 0, h2d = 0, cells = 0, ms_up = 0, ms_k = 0, ms_down = 0;
   for (int c = 0; c < C; ++c) {
@@ -1730,15 +1752,17 @@ static int assemble_impl(int what, int mode, const char *a, const long long *a_o
   int rc;
   Scoring sc{alpha_len, gap_open, gap_extend, map256, score_matrix};
   PairsRun R;
-  if ((rc = pairs_validate(mode, a, a_off, b, b_off, n, sc, R.max_la, R.max_lb))) return rc;
+  const std::vector<int> bounds = pairs_chunk_bounds(n);
+  StagedValidation val{mode, a, a_off, b, b_off, n, &sc};
+  if ((rc = val.stage1(bounds, R.max_la, R.max_lb))) return rc;
   if (out_total) *out_total = 0;
   if (n == 0) { if (out_off) out_off[0] = 0; return ABV_OK; }
   if (!scores || !status || !out_off || out_cap < 0) return fail(ABV_ERR_ARGS, "NULL output");
   if ((rc = ctx_init())) return rc;
   for (double &v : t_timing) v = 0;
   cudaStream_t st = g.stream;
-  if (const std::vector<int> bounds = pairs_chunk_bounds(n); bounds.size() > 2) {
-    rc = assemble_chunked(bounds, what, mode, a, a_off, b, b_off, n, sc, R.max_la, R.max_lb, minimum_overlap, scores, status, start_a, start_b,
+  if (bounds.size() > 2) {
+    rc = assemble_chunked(bounds, what, mode, a, a_off, b, b_off, n, sc, R.max_la, R.max_lb, val, minimum_overlap, scores, status, start_a, start_b,
                           out_off, out1, out2, out_cap, out_total);
     if (rc != ABV_RETRY_WHOLE) return rc;
     for (double &v : t_timing) v = 0;

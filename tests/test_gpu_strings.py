@@ -156,3 +156,36 @@ def test_align_pairs_into_pinned_result_buffers():
         B.align_pairs(a, b, B.LOCAL, out=small)
     assert e.value.code == B.ERR_FRAG_CAP
     assert (small[0][:len(a)] == want[0]).all() and (small[2][:len(a)] == want[2]).all()
+
+
+def test_pipelined_jobs_reject_a_bad_late_pair_like_the_one_piece_run():
+    """the pairs of the later chunks are validated after the first two chunks have been sent (StagedValidation, align_abi.cu): a bad
+    pair anywhere gives the same error as the one-piece run, names the same pair, and nothing is written to the result buffers"""
+    import random
+    from ambivert_b200 import batch as B
+    rng = random.Random(9)
+    n = 3000
+    a = np.frombuffer(bytes(rng.choice(b"ACGT") for _ in range(40 * n)), np.uint8).copy()
+    off = np.arange(n + 1, dtype=np.int64) * 40
+    for bad in (5, 2950):                                   # inside the first chunk / inside the last one
+        boff = off.copy()
+        boff[bad + 1:] -= 40                                # pair `bad` gets an empty second sequence
+        b = a[:int(boff[-1])]
+        msgs = []
+        for per in (0, 250):
+            B.set_option("pairs_chunk", per)
+            try:
+                bufs = B.align_pairs_buffers(n, 4 * n)
+                for x in bufs:
+                    x.fill(-7)
+                with pytest.raises(B.AlignError) as e:
+                    B.align_pairs((a, off), (b, boff), B.LOCAL, out=bufs)
+                assert e.value.code == B.ERR_ARGS and ("sequence b %d " % bad) in str(e.value)
+                assert all((x == -7).all() for x in bufs)
+                with pytest.raises(B.AlignError) as e2:
+                    B.merge_pairs((a, off), (b, boff), 10)
+                assert e2.value.code == B.ERR_ARGS
+                msgs.append((str(e.value), str(e2.value)))
+            finally:
+                B.set_option("pairs_chunk", 200000)
+        assert msgs[0] == msgs[1]
