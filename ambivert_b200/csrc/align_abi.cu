@@ -1419,6 +1419,7 @@ static int pairs_run(PairsRun &R, int mode, const char *a, const long long *a_of
   unsigned long long *counters = R.counters.as<unsigned long long>();   // [0] wf32 pairs, [1] fragment total, [2..] tb16 items per bucket
   int bi = 0;
   for (const auto &B : plan.buckets) {
+    if (B.max_la > tb16_max_la(mode == ABV_LOCAL, B.K)) return fail(ABV_ERR_ARGS, "tb16 plan: a query of %d columns in the K = %d bucket", B.max_la, B.K);
     Tb16Params q{};
     q.a = R.a_codes.as<uint8_t>(); q.a_off = R.a_off.as<long long>();
     q.b = R.b_codes.as<uint8_t>(); q.b_off = R.b_off.as<long long>();
