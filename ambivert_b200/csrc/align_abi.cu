@@ -982,6 +982,7 @@ struct Tb16Plan {
   std::vector<Bucket> buckets;
   int rest_offset = 0, n_rest = 0, rest_max_la = 0, rest_max_lb = 0;
   int pad_score = -1;
+  double cells = 0;          // sum of la * lb over the pairs (the pass over the offsets is made anyway)
 };
 bool tb16_eligible(int mode, const Scoring &sc) {
   if (!g_opt.tb16 || g_opt.path == ABV_PATH_WF32) return false;
@@ -1007,8 +1008,10 @@ void tb16_plan(Tb16Plan &P, int mode, const long long *a_off, const long long *b
     lb_limit[b] = (int)std::min<long long>(TB16_MAX_ROWS, (b16::LIMIT + 2ll * sc.go) / unit - 32ll * TB16_KS[b] - 2);
   }
   P.rest_max_la = P.rest_max_lb = 0;
+  double cells = 0;
   for (int i = 0; i < n; ++i) {
     const int la = (int)std::min<long long>(a_off[i + 1] - a_off[i], INT_MAX), lb = (int)std::min<long long>(b_off[i + 1] - b_off[i], INT_MAX);
+    cells += (double)la * (double)lb;
     int b = TB16_NK;
     if (ok && la <= la_limit[TB16_NK - 1]) {
       b = 0;
@@ -1021,6 +1024,7 @@ void tb16_plan(Tb16Plan &P, int mode, const long long *a_off, const long long *b
     P.key[i] = k;
     ++hist[k + 1];
   }
+  P.cells = cells;
   for (int k = 1; k <= NKEY; ++k) hist[k] += hist[k - 1];
   // list position of the first pair of every bucket (an odd bucket gets one -1 partner at its end)
   P.buckets.clear();
@@ -1371,14 +1375,13 @@ static int pairs_run(PairsRun &R, int mode, const char *a, const long long *a_of
     if ((rc = upload(chunk ? 1 : 0))) return rc;
     CU(R.matrix.alloc(sizeof(int) * sc.alpha * sc.alpha));
     CU(cudaMemcpyAsync(R.matrix.p, sc.matrix, sizeof(int) * sc.alpha * sc.alpha, cudaMemcpyHostToDevice, st));
-    R.cells = 0;
-    for (int i = 0; i < n; ++i) R.cells += (double)(a_off[i + 1] - a_off[i]) * (double)(b_off[i + 1] - b_off[i]);
   }
   // plan: pairs the packed traceback kernel takes (bucketed, partnered) and the rest for the 32-bit kernel
   static thread_local Tb16Plan tl_plan;      // keeps its vectors' capacity from call to call
   Tb16Plan &plan = chunk ? *R.own_plan : tl_plan;
   ABV_TRACE("pairs_run n=%d: uploads issued", n);
   tb16_plan(plan, mode, a_off, b_off, n, sc);
+  R.cells = plan.cells;
   ABV_TRACE("pairs_run n=%d: planned", n);
   const int tmp_cap = R.max_la + R.max_lb + 2;
   const long long dwords = plan.n_rest ? dir_words(plan.rest_max_la, plan.rest_max_lb) : 0;
